@@ -1,0 +1,140 @@
+/*
+ * pointops_b200.h -- C ABI of libpointops_b200.so (sm_100a CUDA kernels for the batched
+ * nearest-neighbour hot path of pytorch3d_pointops).
+ *
+ * This is the drop-in boundary: every entry point below replaces one function the reference
+ * exports from its pybind module `pytorch3d_pointops._C` (csrc/ext.cpp:15-27), or fuses a piece
+ * of torch post-processing the reference does in functions/*.py.  Signatures are plain C:
+ * raw DEVICE pointers, sizes, a CUDA stream handle; no torch / ATen types.  The Python host side
+ * (pytorch3d_pointops_b200/_C.py) binds them with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all tensors dense, row-major, float32 / int64 (exactly what the reference's accessors see);
+ *   - every output buffer is FULLY written by the call (padding values included), so callers may
+ *     pass uninitialised memory;
+ *   - calls enqueue work on `stream` and return without synchronising (same contract as the
+ *     reference's CUDA path, knn.cu:330-331), except where noted;
+ *   - `workspace` is caller-owned scratch of at least pops_*_workspace_bytes(...) bytes, 256-byte
+ *     aligned, on the same device; it may be reused by the next call on the same stream;
+ *   - return value: 0 = success, otherwise a POPS_ERR_* code; pops_last_error() returns a
+ *     thread-local human-readable message (the reference raises c10::Error -> RuntimeError).
+ *   - inputs must be finite; |coordinate| < 1e18.  Indices are exact (ties -> lower index),
+ *     distances are the reference's unfused float32 arithmetic bit for bit.
+ */
+#ifndef POINTOPS_B200_H_
+#define POINTOPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POPS_OK 0
+#define POPS_ERR_INVALID_ARGUMENT 1 /* bad shape / norm / null pointer            */
+#define POPS_ERR_WORKSPACE 2        /* workspace missing or too small             */
+#define POPS_ERR_CUDA 3             /* a CUDA runtime call or kernel launch failed */
+#define POPS_ERR_UNSUPPORTED 4      /* shape outside what the kernels support     */
+
+typedef void* pops_stream_t; /* cudaStream_t */
+
+/* Library / build identification. */
+int pops_abi_version(void);
+const char* pops_build_info(void); /* "sm_100a nvcc 12.9 ..." */
+const char* pops_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
+int64_t pops_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * KNN forward.  Replaces _C.knn_points_idx (ext.cpp:21; knn.h:59-80; knn_cpu.cpp:13-69) AND the
+ * sort + gather post-pass of functions/knn.py:77-89: results come back already in the canonical
+ * order -- the K lexicographically smallest (dist, idx), ascending.
+ *   p1 (N,P1,D) f32, p2 (N,P2,D) f32, lengths1/lengths2 (N) i64 (values clamped to [0,P]),
+ *   norm 1|2, version: accepted for API compatibility (knn.py:121) and ignored.
+ *   idx (N,P1,K) i64, dists (N,P1,K) f32: rows >= lengths1[n] and slots >= min(K,lengths2[n])
+ *   are (0, 0.0f) (knn_cpu.cpp:25-26).
+ * ------------------------------------------------------------------------------------------- */
+size_t pops_knn_workspace_bytes(int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K, int norm);
+int pops_knn_points_idx(const float* p1, const float* p2, const int64_t* lengths1,
+                        const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2, int64_t D,
+                        int64_t K, int norm, int version, int64_t* idx, float* dists,
+                        void* workspace, size_t workspace_bytes, pops_stream_t stream);
+
+/* _C.knn_check_version (ext.cpp:19; knn.cu:292-303): which (D,K) the reference's kernel
+ * variant `version` accepts.  Kept so callers probing it keep working; returns 0/1. */
+int pops_knn_check_version(int version, int64_t D, int64_t K);
+
+/* ---------------------------------------------------------------------------------------------
+ * KNN backward.  Replaces _C.knn_points_backward (ext.cpp:22; knn.h:127-149; knn_cpu.cpp:75-128).
+ *   grad_p1[n,i,:] += sum_k diff, grad_p2[n,idx,:] -= diff, diff = 2*g*(p1-p2) (L2) or g*sign (L1);
+ *   k < min(K, lengths2[n]), i < lengths1[n], idx == -1 skipped (ball_query reuses this, :49-51).
+ *   grad_p1 (N,P1,D) and grad_p2 (N,P2,D) are zero-filled by the call.  float atomics on grad_p2.
+ * ------------------------------------------------------------------------------------------- */
+int pops_knn_points_backward(const float* p1, const float* p2, const int64_t* lengths1,
+                             const int64_t* lengths2, const int64_t* idx, const float* grad_dists,
+                             int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K, int norm,
+                             float* grad_p1, float* grad_p2, pops_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ball query.  Replaces _C.ball_query (ext.cpp:23; ball_query.h:62-93; ball_query_cpu.cpp:12-54):
+ * the first K points of p2 (index order) with dist2 < radius*radius (strict, f32 product).
+ *   idx (N,P1,K) i64 padded with -1, dists (N,P1,K) f32 padded with 0.
+ * ------------------------------------------------------------------------------------------- */
+size_t pops_ball_query_workspace_bytes(int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K);
+int pops_ball_query(const float* p1, const float* p2, const int64_t* lengths1,
+                    const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2, int64_t D,
+                    int64_t K, float radius, int64_t* idx, float* dists, void* workspace,
+                    size_t workspace_bytes, pops_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Farthest point sampling.  Replaces _C.sample_farthest_points (ext.cpp:24;
+ * sample_farthest_points.h:55-76; sample_farthest_points_cpu.cpp:14-103).
+ *   points (N,P,D) f32, lengths/K/start_idxs (N) i64; idx (N,max_K) i64 padded with -1,
+ *   idx[n,0] = start_idxs[n]; ties -> lowest index.  max_K is supplied by the caller (the
+ *   reference syncs on torch::max(K), sample_farthest_points.cu:132); no device sync here.
+ * ------------------------------------------------------------------------------------------- */
+size_t pops_fps_workspace_bytes(int64_t N, int64_t P, int64_t D, int64_t max_K);
+int pops_sample_farthest_points(const float* points, const int64_t* lengths, const int64_t* K,
+                                const int64_t* start_idxs, int64_t N, int64_t P, int64_t D,
+                                int64_t max_K, int64_t* idx, void* workspace,
+                                size_t workspace_bytes, pops_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ragged copies.  Replace _C.packed_to_padded / _C.padded_to_packed (ext.cpp:16-17;
+ * packed_to_padded_tensor.h:78-113; packed_to_padded_tensor_cpu.cpp:11-70).
+ *   packed (F,D) f32, first_idxs (B) i64, padded (B,max_size,D) f32; cloud b owns rows
+ *   [first_idxs[b], b+1<B ? first_idxs[b+1] : F).  Outputs are zero where nothing is copied.
+ * ------------------------------------------------------------------------------------------- */
+int pops_packed_to_padded(const float* packed, const int64_t* first_idxs, int64_t num_inputs,
+                          int64_t B, int64_t max_size, int64_t D, float* padded,
+                          pops_stream_t stream);
+int pops_padded_to_packed(const float* padded, const int64_t* first_idxs, int64_t num_inputs,
+                          int64_t B, int64_t max_size, int64_t D, float* packed,
+                          pops_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused row gather.  Replaces the torch expand+gather+mask of knn_gather (functions/knn.py:200-250)
+ * and masked_gather (functions/utils.py:20-65).
+ *   x (N,M,U) f32, idx (N,L,K) i64 -> out (N,L,K,U) f32.
+ *   mode POPS_GATHER_KNN:    out[n,l,k] = x[n, idx[n,l,k]], zero where k >= lengths[n]
+ *                            (lengths may be NULL = no masking); an index outside [0,M) is an
+ *                            error in the reference (RuntimeError) -- here it sets *oob_flag = 1
+ *                            (int32 on device, may be NULL) and yields zeros.
+ *   mode POPS_GATHER_MASKED: idx == -1 -> zero row.
+ * pops_gather_backward scatters grad_out (N,L,K,U) into grad_x (N,M,U) (zero-filled by the call).
+ * ------------------------------------------------------------------------------------------- */
+#define POPS_GATHER_KNN 0
+#define POPS_GATHER_MASKED 1
+int pops_gather(const float* x, const int64_t* idx, const int64_t* lengths, int64_t N, int64_t M,
+                int64_t U, int64_t L, int64_t K, int mode, float* out, int32_t* oob_flag,
+                pops_stream_t stream);
+int pops_gather_backward(const float* grad_out, const int64_t* idx, const int64_t* lengths,
+                         int64_t N, int64_t M, int64_t U, int64_t L, int64_t K, int mode,
+                         float* grad_x, pops_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTOPS_B200_H_ */

@@ -1,0 +1,255 @@
+"""`pytorch3d_pointops._C` replacement: the reference's pybind surface (csrc/ext.cpp:15-27) on top
+of the C ABI of libpointops_b200.so.
+
+Same names, same positional signatures, same return order and dtypes as the reference module
+(`knn_points_idx` returns `(idx, dists)`; idx int64; KNN pads with 0, ball query / FPS with -1).
+Inputs must be CUDA tensors: there is no CPU path (the reference's CPU loops survive only as the
+test oracle).  Outputs are fresh tensors on the inputs' device; kernels are enqueued on the
+current stream of that device and the call returns without synchronising (knn.cu:330-331).
+
+Extra, additive entry points used by functions/*.py: `gather`, `gather_backward`.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+GATHER_KNN = 0
+GATHER_MASKED = 1
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        # reference: CHECK_CUDA -> "<name> must be a CUDA tensor." (pytorch3d_cutils.h:12)
+        raise RuntimeError(f"{name} must be a CUDA tensor. (pytorch3d_pointops_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"expected scalar type Float but found {t.dtype} for {name}")
+    return t.contiguous()
+
+
+def _cuda_i64(t: torch.Tensor, name: str, like: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor. (pytorch3d_pointops_b200 has no CPU path)")
+    if t.device != like.device:
+        raise RuntimeError(f"{name} must be on the same device as the points ({like.device})")
+    if t.dtype != torch.int64:
+        raise RuntimeError(f"expected scalar type Long but found {t.dtype} for {name}")
+    return t.contiguous()
+
+
+def _same_device(a: torch.Tensor, b: torch.Tensor, what: str) -> None:
+    if a.device != b.device:
+        raise RuntimeError(f"{what} must be on the same GPU")  # checkAllSameGPU, knn.cu:326
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's 7 in-scope names
+# ------------------------------------------------------------------------------------------------
+def knn_points_idx(p1, p2, lengths1, lengths2, norm, K, version):
+    """knn.h:59-66.  Returns (idx (N,P1,K) int64, dists (N,P1,K) float32), canonical order."""
+    lib = _lib.load()
+    p1 = _cuda_f32(p1, "p1")
+    p2 = _cuda_f32(p2, "p2")
+    _same_device(p1, p2, "p1 and p2")
+    if p1.dim() != 3 or p2.dim() != 3 or p1.shape[0] != p2.shape[0] or p1.shape[2] != p2.shape[2]:
+        raise RuntimeError("p1 and p2 must be (N, P, D) with matching N and D")
+    if norm not in (1, 2):
+        raise RuntimeError("Norm must be 1 or 2.")  # knn.cu:339
+    lengths1 = _cuda_i64(lengths1, "lengths1", p1)
+    lengths2 = _cuda_i64(lengths2, "lengths2", p1)
+    N, P1, D = p1.shape
+    P2 = p2.shape[1]
+    K = int(K)
+    idx = torch.empty((N, P1, K), dtype=torch.int64, device=p1.device)
+    dists = torch.empty((N, P1, K), dtype=torch.float32, device=p1.device)
+    if idx.numel() == 0:
+        return idx, dists
+    with torch.cuda.device(p1.device):
+        nbytes = lib.pops_knn_workspace_bytes(N, P1, P2, D, K, int(norm))
+        ws = _ws(nbytes, p1.device)
+        st = lib.pops_knn_points_idx(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
+                                     lengths2.data_ptr(), N, P1, P2, D, K, int(norm), int(version),
+                                     idx.data_ptr(), dists.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     _stream(p1))
+    _lib.check(st, "knn_points_idx")
+    return idx, dists
+
+
+def knn_check_version(version, D, K):
+    """knn.h:161 / knn.cu:292-303."""
+    return bool(_lib.load().pops_knn_check_version(int(version), int(D), int(K)))
+
+
+def knn_points_backward(p1, p2, lengths1, lengths2, idxs, norm, grad_dists):
+    """knn.h:127-134.  Returns (grad_p1, grad_p2)."""
+    lib = _lib.load()
+    p1 = _cuda_f32(p1, "p1")
+    p2 = _cuda_f32(p2, "p2")
+    _same_device(p1, p2, "p1 and p2")
+    grad_dists = _cuda_f32(grad_dists, "grad_dists")
+    lengths1 = _cuda_i64(lengths1, "lengths1", p1)
+    lengths2 = _cuda_i64(lengths2, "lengths2", p1)
+    idxs = _cuda_i64(idxs, "idxs", p1)
+    if norm not in (1, 2):
+        raise RuntimeError("Norm must be 1 or 2.")
+    N, P1, D = p1.shape
+    P2 = p2.shape[1]
+    K = idxs.shape[2]
+    grad_p1 = torch.empty_like(p1)
+    grad_p2 = torch.empty_like(p2)
+    with torch.cuda.device(p1.device):
+        st = lib.pops_knn_points_backward(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
+                                          lengths2.data_ptr(), idxs.data_ptr(),
+                                          grad_dists.data_ptr(), N, P1, P2, D, K, int(norm),
+                                          grad_p1.data_ptr(), grad_p2.data_ptr(), _stream(p1))
+    _lib.check(st, "knn_points_backward")
+    return grad_p1, grad_p2
+
+
+def ball_query(p1, p2, lengths1, lengths2, K, radius):
+    """ball_query.h:62-68.  Returns (idx int64 padded -1, dists float32 padded 0)."""
+    lib = _lib.load()
+    p1 = _cuda_f32(p1, "p1")
+    p2 = _cuda_f32(p2, "p2")
+    _same_device(p1, p2, "p1 and p2")
+    lengths1 = _cuda_i64(lengths1, "lengths1", p1)
+    lengths2 = _cuda_i64(lengths2, "lengths2", p1)
+    N, P1, D = p1.shape
+    P2 = p2.shape[1]
+    K = int(K)
+    idx = torch.empty((N, P1, K), dtype=torch.int64, device=p1.device)
+    dists = torch.empty((N, P1, K), dtype=torch.float32, device=p1.device)
+    if idx.numel() == 0:
+        return idx, dists
+    if P2 == 0 or D == 0:
+        return idx.fill_(-1), dists.zero_()
+    with torch.cuda.device(p1.device):
+        ws = _ws(lib.pops_ball_query_workspace_bytes(N, P1, P2, D, K), p1.device)
+        st = lib.pops_ball_query(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
+                                 lengths2.data_ptr(), N, P1, P2, D, K, float(radius),
+                                 idx.data_ptr(), dists.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 _stream(p1))
+    _lib.check(st, "ball_query")
+    return idx, dists
+
+
+def sample_farthest_points(points, lengths, K, start_idxs, max_K=None):
+    """sample_farthest_points.h:55-59.  `max_K` (optional, additive) avoids the device sync the
+    reference pays for torch::max(K) (sample_farthest_points.cu:132)."""
+    lib = _lib.load()
+    points = _cuda_f32(points, "points")
+    lengths = _cuda_i64(lengths, "lengths", points)
+    K = _cuda_i64(K, "K", points)
+    start_idxs = _cuda_i64(start_idxs, "start_idxs", points)
+    N, P, D = points.shape
+    if max_K is None:
+        max_K = int(K.max().item()) if N > 0 else 0
+    idx = torch.empty((N, max_K), dtype=torch.int64, device=points.device)
+    if idx.numel() == 0:
+        return idx
+    if P == 0:
+        idx.fill_(-1)
+        idx[:, 0] = start_idxs
+        return idx
+    with torch.cuda.device(points.device):
+        ws = _ws(lib.pops_fps_workspace_bytes(N, P, D, max_K), points.device)
+        st = lib.pops_sample_farthest_points(points.data_ptr(), lengths.data_ptr(), K.data_ptr(),
+                                             start_idxs.data_ptr(), N, P, D, max_K,
+                                             idx.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             _stream(points))
+    _lib.check(st, "sample_farthest_points")
+    return idx
+
+
+def packed_to_padded(inputs_packed, first_idxs, max_size):
+    """packed_to_padded_tensor.h:78-94: (F,D) -> (N,max_size,D), zero padded."""
+    lib = _lib.load()
+    x = _cuda_f32(inputs_packed, "inputs_packed")
+    first = _cuda_i64(first_idxs, "first_idxs", x)
+    if x.dim() != 2:
+        raise RuntimeError("inputs_packed must be a 2-dimensional tensor")
+    F, D = x.shape
+    B = first.shape[0]
+    out = torch.empty((B, int(max_size), D), dtype=torch.float32, device=x.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        st = lib.pops_packed_to_padded(x.data_ptr(), first.data_ptr(), F, B, int(max_size), D,
+                                       out.data_ptr(), _stream(x))
+    _lib.check(st, "packed_to_padded")
+    return out
+
+
+def padded_to_packed(inputs_padded, first_idxs, num_inputs):
+    """packed_to_padded_tensor.h:97-113: (N,M,D) -> (F,D)."""
+    lib = _lib.load()
+    x = _cuda_f32(inputs_padded, "inputs_padded")
+    first = _cuda_i64(first_idxs, "first_idxs", x)
+    if x.dim() != 3:
+        raise RuntimeError("inputs_padded must be a 3-dimensional tensor")
+    B, M, D = x.shape
+    out = torch.empty((int(num_inputs), D), dtype=torch.float32, device=x.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        st = lib.pops_padded_to_packed(x.data_ptr(), first.data_ptr(), int(num_inputs), B, M, D,
+                                       out.data_ptr(), _stream(x))
+    _lib.check(st, "padded_to_packed")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# additive fused entry points
+# ------------------------------------------------------------------------------------------------
+def gather(x, idx, lengths, mode, oob_flag=None):
+    """out[n,l,k,:] = x[n, idx[n,l,k], :] with knn_gather / masked_gather masking (one pass).
+
+    x (N,M,U) f32, idx (N,L,K) i64, lengths (N) i64 or None -> (N,L,K,U)."""
+    lib = _lib.load()
+    x = _cuda_f32(x, "x")
+    idx = _cuda_i64(idx, "idx", x)
+    if lengths is not None:
+        lengths = _cuda_i64(lengths, "lengths", x)
+    N, M, U = x.shape
+    _, L, K = idx.shape
+    out = torch.empty((N, L, K, U), dtype=torch.float32, device=x.device)
+    if out.numel() == 0:
+        return out
+    if M == 0:
+        return out.zero_()
+    with torch.cuda.device(x.device):
+        st = lib.pops_gather(x.data_ptr(), idx.data_ptr(), _ptr(lengths), N, M, U, L, K, int(mode),
+                             out.data_ptr(), _ptr(oob_flag), _stream(x))
+    _lib.check(st, "gather")
+    return out
+
+
+def gather_backward(grad_out, idx, lengths, M, mode):
+    """Scatter-add of grad_out (N,L,K,U) into grad_x (N,M,U)."""
+    lib = _lib.load()
+    g = _cuda_f32(grad_out, "grad_out")
+    idx = _cuda_i64(idx, "idx", g)
+    if lengths is not None:
+        lengths = _cuda_i64(lengths, "lengths", g)
+    N, L, K, U = g.shape
+    grad_x = torch.empty((N, int(M), U), dtype=torch.float32, device=g.device)
+    if grad_x.numel() == 0:
+        return grad_x
+    with torch.cuda.device(g.device):
+        st = lib.pops_gather_backward(g.data_ptr(), idx.data_ptr(), _ptr(lengths), N, int(M), U, L,
+                                      K, int(mode), grad_x.data_ptr(), _stream(g))
+    _lib.check(st, "gather_backward")
+    return grad_x

@@ -1,0 +1,269 @@
+// Farthest point sampling for sm_100a.
+//
+// Replaces csrc/sample_farthest_points/{.cu,_cpu.cpp}.  Contract = the reference CPU path
+// (sample_farthest_points_cpu.cpp:14-103): idx[n,0] = start_idxs[n]; then batch_k-1 times
+//   mind[p] = min(mind[p], dist2(last, p))   (unfused f32, (last - p)^2 summed d = 0..D-1)
+//   last    = FIRST maximum of mind          (lowest index on ties)
+// (forcing selected points to 0 in the reference, :68-72, is the same thing: dist2(p,p) = 0).
+//
+// D == 3 design: the whole iteration state lives in REGISTERS.  One thread-block CLUSTER of C
+// CTAs (C in {1,2,4,8,16}) owns one cloud; each of the C*1024 threads keeps PT points
+// (x, y, z, mind) in registers for the entire run, so an iteration touches no global or shared
+// memory for point data -- the reference re-reads 20 B/point/iteration from global memory
+// (sample_farthest_points.cu:63-76).  The arg-max is: REDUX warp reduce -> 32 warp slots in
+// shared memory -> one warp -> the CTA's winner (key, index AND coordinates) is pushed into
+// every CTA of the cluster through distributed shared memory -> one cluster barrier -> every
+// thread picks the cluster winner locally.  2 barriers per iteration, no global round trip.
+//
+// Generic D: one CTA per cloud, mind in a global scratch row (L2 resident), same reduction.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace pops {
+
+constexpr int kFpsThreads = 1024;
+constexpr int kFpsWarps = kFpsThreads / 32;
+
+struct FpsSlot {  // 32 bytes
+  int key;        // float bits of mind (>= 0) or negative when the CTA has no valid point
+  int idx;
+  float x, y, z;
+  int pad0, pad1, pad2;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, int a, int b, int c, int d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+
+// warp arg-max with first-index tie break.  Returns true in the winning lane.
+__device__ __forceinline__ bool warp_argmax(int key, int idx, int* wkey, int* widx) {
+  const int mk = __reduce_max_sync(0xffffffffu, key);
+  const int cand = (key == mk) ? idx : 0x7fffffff;
+  const int mi = __reduce_min_sync(0xffffffffu, cand);
+  *wkey = mk;
+  *widx = mi;
+  return key == mk && idx == mi;
+}
+
+template <int PT>
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ lengths,
+              const int64_t* __restrict__ Ks, const int64_t* __restrict__ start_idxs, int P,
+              int max_K, int C, int64_t* __restrict__ out) {
+  __shared__ __align__(16) FpsSlot wslots[kFpsWarps];
+  __shared__ __align__(16) FpsSlot cslots[2][16];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (C > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int n = blockIdx.x / C;
+  int64_t Ll = lengths[n];
+  const int L = static_cast<int>(Ll < 0 ? 0 : (Ll > P ? P : Ll));
+  int64_t kl = Ks[n];
+  const int kn = static_cast<int>(kl < L ? (kl < 0 ? 0 : kl) : L);  // min(lengths, K)
+  const float* pts = points + static_cast<size_t>(n) * P * 3;
+  int64_t* o = out + static_cast<size_t>(n) * max_K;
+
+  int last = static_cast<int>(start_idxs[n]);
+  if (rank == 0) {
+    for (int k = tid; k < max_K; k += kFpsThreads)
+      if (k == 0) o[0] = last; else if (k >= kn) o[k] = -1;
+  }
+  if (kn <= 1) return;  // uniform across the cluster: nothing else to select
+  last = min(max(last, 0), L - 1);
+
+  float x[PT], y[PT], z[PT], mind[PT];
+  const int stride = C * kFpsThreads;
+#pragma unroll
+  for (int i = 0; i < PT; ++i) {
+    const int p = i * stride + rank * kFpsThreads + tid;
+    const bool v = p < L;
+    x[i] = v ? pts[static_cast<size_t>(p) * 3 + 0] : 0.0f;
+    y[i] = v ? pts[static_cast<size_t>(p) * 3 + 1] : 0.0f;
+    z[i] = v ? pts[static_cast<size_t>(p) * 3 + 2] : 0.0f;
+    mind[i] = v ? FLT_MAX : -1.0f;  // -1: never the maximum, min() keeps it
+  }
+  float lx = pts[static_cast<size_t>(last) * 3 + 0];
+  float ly = pts[static_cast<size_t>(last) * 3 + 1];
+  float lz = pts[static_cast<size_t>(last) * 3 + 2];
+
+  for (int k = 1; k < kn; ++k) {
+    float best = -1.0f;
+    int bi = 0;
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      const float dx = __fsub_rn(lx, x[i]), dy = __fsub_rn(ly, y[i]), dz = __fsub_rn(lz, z[i]);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      mind[i] = fminf(mind[i], d);
+      if (mind[i] > best) {  // strict: lowest local index wins ties (indices ascend with i)
+        best = mind[i];
+        bi = i;
+      }
+    }
+    int wkey, widx;
+    const bool win = warp_argmax(__float_as_int(best), bi * stride + rank * kFpsThreads + tid, &wkey, &widx);
+    if (win) {
+      float bx = x[0], by = y[0], bz = z[0];
+#pragma unroll
+      for (int i = 1; i < PT; ++i)
+        if (bi == i) { bx = x[i]; by = y[i]; bz = z[i]; }
+      FpsSlot s;
+      s.key = wkey; s.idx = widx; s.x = bx; s.y = by; s.z = bz; s.pad0 = s.pad1 = s.pad2 = 0;
+      wslots[warp] = s;
+    }
+    __syncthreads();
+    const int par = k & 1;
+    if (warp == 0) {
+      const FpsSlot s = wslots[lane];
+      int ckey, cidx;
+      const bool cwin = warp_argmax(s.key, s.idx, &ckey, &cidx);
+      if (cwin) {
+        if (C > 1) {
+          const uint32_t local = smem_u32(&cslots[par][rank]);
+          for (int r = 0; r < C; ++r) {
+            const uint32_t remote = map_to_cta(local, static_cast<uint32_t>(r));
+            st_cluster_v4(remote, s.key, s.idx, __float_as_int(s.x), __float_as_int(s.y));
+            st_cluster_v4(remote + 16, __float_as_int(s.z), 0, 0, 0);
+          }
+        } else {
+          cslots[par][0] = s;
+        }
+      }
+    }
+    if (C > 1) cluster_barrier(); else __syncthreads();
+    // every thread: cluster winner = max key, then min idx
+    FpsSlot b = cslots[par][0];
+    for (int r = 1; r < C; ++r) {
+      const FpsSlot s = cslots[par][r];
+      if (s.key > b.key || (s.key == b.key && s.idx < b.idx)) b = s;
+    }
+    lx = b.x; ly = b.y; lz = b.z;
+    if (rank == 0 && tid == 0) o[k] = b.idx;
+  }
+  // keep every CTA's shared memory alive until all remote stores have landed / been read
+  if (C > 1) cluster_barrier();
+}
+
+// Generic D: one CTA per cloud; mind row in global scratch.
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_generic_kernel(const float* __restrict__ points, const int64_t* __restrict__ lengths,
+                   const int64_t* __restrict__ Ks, const int64_t* __restrict__ start_idxs, int P,
+                   int D, int max_K, float* __restrict__ mind_ws, int64_t* __restrict__ out) {
+  __shared__ int wkeys[kFpsWarps], widxs[kFpsWarps];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x;
+  int64_t Ll = lengths[n];
+  const int L = static_cast<int>(Ll < 0 ? 0 : (Ll > P ? P : Ll));
+  int64_t kl = Ks[n];
+  const int kn = static_cast<int>(kl < L ? (kl < 0 ? 0 : kl) : L);
+  const float* pts = points + static_cast<size_t>(n) * P * D;
+  float* mind = mind_ws + static_cast<size_t>(n) * P;
+  int64_t* o = out + static_cast<size_t>(n) * max_K;
+  int last = static_cast<int>(start_idxs[n]);
+  for (int k = tid; k < max_K; k += kFpsThreads)
+    if (k == 0) o[0] = last; else if (k >= kn) o[k] = -1;
+  if (kn <= 1) return;
+  last = min(max(last, 0), L - 1);
+  for (int p = tid; p < L; p += kFpsThreads) mind[p] = FLT_MAX;
+  for (int k = 1; k < kn; ++k) {
+    const float* lp = pts + static_cast<size_t>(last) * D;
+    float best = -1.0f;
+    int bi = 0x7fffffff;
+    for (int p = tid; p < L; p += kFpsThreads) {
+      const float* pp = pts + static_cast<size_t>(p) * D;
+      float d = 0.0f;
+      for (int dd = 0; dd < D; ++dd) d = __fadd_rn(d, dist_term<2>(lp[dd], pp[dd]));
+      const float m = fminf(mind[p], d);
+      mind[p] = m;
+      if (m > best) { best = m; bi = p; }
+    }
+    int wkey, widx;
+    if (warp_argmax(__float_as_int(best), bi, &wkey, &widx)) { wkeys[warp] = wkey; widxs[warp] = widx; }
+    __syncthreads();
+    if (warp == 0) {
+      int ckey, cidx;
+      if (warp_argmax(wkeys[lane], widxs[lane], &ckey, &cidx)) { s_last = cidx; o[k] = cidx; }
+    }
+    __syncthreads();
+    last = s_last;
+  }
+}
+
+namespace {
+template <int PT>
+int launch_fps_d3(const float* points, const int64_t* lengths, const int64_t* K,
+                  const int64_t* start, int N, int P, int max_K, int C, int64_t* out,
+                  cudaStream_t st) {
+  auto kern = fps_d3_kernel<PT>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(N) * C);
+  cfg.blockDim = dim3(kFpsThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (C > 8) POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, points, lengths, K, start, P, max_K, C, out));
+  POPS_LAUNCH_OK("fps_d3_kernel");
+  return POPS_OK;
+}
+}  // namespace
+}  // namespace pops
+
+using namespace pops;
+
+extern "C" size_t pops_fps_workspace_bytes(int64_t N, int64_t P, int64_t D, int64_t max_K) {
+  (void)max_K;
+  if (D == 3 && P <= int64_t(16) * kFpsThreads * 8) return 256;
+  return align_up(size_t(std::max<int64_t>(N, 0)) * size_t(std::max<int64_t>(P, 0)) * 4, 256) + 256;
+}
+
+extern "C" int pops_sample_farthest_points(const float* points, const int64_t* lengths,
+                                           const int64_t* K, const int64_t* start_idxs, int64_t N,
+                                           int64_t P, int64_t D, int64_t max_K, int64_t* idx,
+                                           void* workspace, size_t workspace_bytes,
+                                           pops_stream_t stream) {
+  POPS_CHECK_ARG(N >= 0 && P >= 0 && D >= 0 && max_K >= 0, "negative size");
+  if (N == 0 || max_K == 0) return POPS_OK;
+  POPS_CHECK_ARG(points && lengths && K && start_idxs && idx, "null pointer argument");
+  POPS_CHECK_ARG(P < (int64_t(1) << 31) && N < (int64_t(1) << 24), "size too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 3 && P <= int64_t(16) * kFpsThreads * 8) {
+    // smallest cluster that keeps <= 8 points per thread; widen while the batch leaves SMs idle
+    int C = 1;
+    while (int64_t(C) * kFpsThreads * 8 < P) C *= 2;
+    const int sms = num_sms();
+    while (C < 16 && int64_t(N) * C * 2 <= sms && int64_t(C) * kFpsThreads < P) C *= 2;
+    const int per_thread = int(ceil_div(P, int64_t(C) * kFpsThreads));
+    if (per_thread <= 1) return launch_fps_d3<1>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
+    if (per_thread <= 2) return launch_fps_d3<2>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
+    if (per_thread <= 4) return launch_fps_d3<4>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
+    return launch_fps_d3<8>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
+  }
+  if (workspace_bytes < pops_fps_workspace_bytes(N, P, D, max_K) || !workspace)
+    return fail(POPS_ERR_WORKSPACE, "fps: workspace missing or too small");
+  fps_generic_kernel<<<static_cast<unsigned>(N), kFpsThreads, 0, st>>>(
+      points, lengths, K, start_idxs, int(P), int(D), int(max_K), reinterpret_cast<float*>(workspace), idx);
+  POPS_LAUNCH_OK("fps_generic_kernel");
+  return POPS_OK;
+}

@@ -1,0 +1,671 @@
+// K nearest neighbours, forward + backward, for sm_100a.
+//
+// Replaces csrc/knn/{knn.cu,knn_cpu.cpp} of the reference AND the sort/gather post-pass of
+// functions/knn.py:77-89.  Contract = the reference CPU path (knn_cpu.cpp:13-69): the K
+// lexicographically smallest (dist, idx) per query, ascending, dist computed as the unfused
+// float32 sum  fl(fl(dx*dx) + fl(dy*dy)) + ...  (or |dx| + |dy| + ... for norm 1).
+//
+// Design (DESIGN.md "KNN"):
+//   pack pass   p2 (N,P2,D) AoS -> per-cloud SoA rows x[],y[],z[](,w=|p|^2) padded with
+//               sentinels, plus max|coord| per cloud (bounds the filter's rounding error).
+//   scan pass   one CTA = QPB queries of one cloud.  p2 streams through shared memory in
+//               tiles moved by TMA bulk copies (cp.async.bulk + mbarrier, 2 stages).  Each thread
+//               owns Q queries and, per group of 4 points, evaluates a cheap FILTER:
+//                 D==3, L2:  s = w + (-2qx)x + (-2qy)y + (-2qz)z   (3 FFMA, issued as packed
+//                            FFMA2 over point pairs) tested against T = (dk - |q|^2) + E,
+//                            E >= the filter's worst-case rounding error, so no true
+//                            neighbour is ever dropped;
+//                 otherwise: the exact distance itself, tested against dk.
+//               Groups that pass are appended (branch-free, predicated) to a small per-query
+//               candidate buffer in shared memory.  Buffers are drained in warp-converged
+//               FLUSH phases: exact unfused distance, 64-bit key (dist_bits<<32 | idx), sorted
+//               insertion into the per-query top-K list (shared memory, column per query).
+//               Only the exact key decides membership and order -> bit-exact vs the oracle.
+//   generic     any D / any K fallback: thread per query, exact distance, list in shared or
+//               global memory.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace pops {
+
+constexpr int kGroup = 4;             // points per filter group (one float4 per SoA row)
+constexpr int kChunk = 4;             // groups between candidate-buffer overflow checks
+constexpr int kPadPoints = kGroup * kChunk;  // SoA rows padded to a multiple of this
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+// ---------------------------------------------------------------------------------------------
+// pack pass
+// ---------------------------------------------------------------------------------------------
+// soa layout: [n][row][P2pad], rows = DT (+1 for w when EXP).  j >= len2: sentinel
+// (EXP: x=y=z=0, w=+inf -> s=+inf;  else: row0=+inf -> d=+inf), never a candidate by itself.
+template <int DT, bool EXP>
+__global__ void knn_pack_kernel(const float* __restrict__ p2, const int64_t* __restrict__ len2,
+                                int P2, int P2pad, float* __restrict__ soa,
+                                unsigned* __restrict__ maxabs_bits) {
+  constexpr int ROWS = DT + (EXP ? 1 : 0);
+  const int n = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t L = len2[n];
+  L = L < 0 ? 0 : (L > P2 ? P2 : L);
+  float m = 0.0f;
+  if (j < P2pad) {
+    float v[DT];
+    float w = 0.0f;
+    if (j < L) {
+      const float* src = p2 + (static_cast<size_t>(n) * P2 + j) * DT;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        v[d] = src[d];
+        m = fmaxf(m, fabsf(v[d]));
+        w = fmaf(v[d], v[d], w);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < DT; ++d) v[d] = 0.0f;
+      if (EXP) {
+        w = __int_as_float(0x7f800000);
+      } else {
+        v[0] = __int_as_float(0x7f800000);
+      }
+    }
+    float* dst = soa + static_cast<size_t>(n) * ROWS * P2pad + j;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) dst[static_cast<size_t>(d) * P2pad] = v[d];
+    if (EXP) dst[static_cast<size_t>(DT) * P2pad] = w;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(maxabs_bits + n, __float_as_uint(m));
+}
+
+// max |coord| over the valid rows of p (N,P,D) -> atomicMax into maxabs_bits[n]
+__global__ void maxabs_kernel(const float* __restrict__ p, const int64_t* __restrict__ len, int P,
+                              int D, unsigned* __restrict__ maxabs_bits) {
+  const int n = blockIdx.y;
+  int64_t L = len[n];
+  L = L < 0 ? 0 : (L > P ? P : L);
+  const size_t total = static_cast<size_t>(L) * D;
+  const float* src = p + static_cast<size_t>(n) * P * D;
+  float m = 0.0f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(src[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(maxabs_bits + n, __float_as_uint(m));
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan pass (tiled, buffered candidates)
+// ---------------------------------------------------------------------------------------------
+struct KnnScanParams {
+  const float* p1;
+  const float* soa;
+  const int64_t* len1;
+  const int64_t* len2;
+  const unsigned* maxabs_bits;
+  int64_t* idx;
+  float* dists;
+  int P1, P2, P2pad, K;
+  int TP;    // tile points (multiple of kPadPoints)
+  int BCAP;  // candidate buffer capacity in groups (> kChunk)
+};
+
+template <int DT, int NORM, bool EXP, int Q, int THREADS>
+struct KnnSmem {
+  static constexpr int ROWS = DT + (EXP ? 1 : 0);
+  static constexpr int QPB = Q * THREADS;
+  // offsets in bytes
+  static __host__ __device__ size_t tiles_off() { return 64; }
+  static __host__ __device__ size_t tiles_bytes(int TP) { return size_t(2) * ROWS * TP * 4; }
+  static __host__ __device__ size_t lists_off(int TP) { return tiles_off() + tiles_bytes(TP); }
+  static __host__ __device__ size_t lists_bytes(int K) { return size_t(K) * QPB * 8; }
+  static __host__ __device__ size_t qs_off(int TP, int K) { return lists_off(TP) + lists_bytes(K); }
+  static __host__ __device__ size_t qs_bytes() { return size_t(DT) * QPB * 4; }
+  static __host__ __device__ size_t cand_off(int TP, int K) { return qs_off(TP, K) + qs_bytes(); }
+  static __host__ __device__ size_t cand_bytes(int BCAP) { return size_t(BCAP) * QPB * 2; }
+  static __host__ __device__ size_t total(int TP, int K, int BCAP) {
+    return cand_off(TP, K) + cand_bytes(BCAP);
+  }
+};
+
+template <int DT, int NORM, bool EXP, int Q, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+knn_scan_kernel(const KnnScanParams prm) {
+  using SM = KnnSmem<DT, NORM, EXP, Q, THREADS>;
+  constexpr int ROWS = SM::ROWS;
+  constexpr int QPB = SM::QPB;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const int n = blockIdx.y;
+  const int q_base = blockIdx.x * QPB;
+  const int tid = threadIdx.x;
+  const int K = prm.K, TP = prm.TP, BCAP = prm.BCAP, P2pad = prm.P2pad;
+  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
+  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
+  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
+
+  int64_t* out_idx = prm.idx + (static_cast<size_t>(n) * prm.P1) * K;
+  float* out_d = prm.dists + (static_cast<size_t>(n) * prm.P1) * K;
+
+  // CTA entirely beyond lengths1[n] (or nothing to search): rows are (0, 0).
+  if (q_base >= L1 || L2 == 0) {
+    const int rows = min(QPB, prm.P1 - q_base);
+    for (int e = tid; e < rows * K; e += THREADS) {
+      out_idx[static_cast<size_t>(q_base) * K + e] = 0;
+      out_d[static_cast<size_t>(q_base) * K + e] = 0.0f;
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  float* tiles = reinterpret_cast<float*>(smem + SM::tiles_off());
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + SM::lists_off(TP));
+  float* qs = reinterpret_cast<float*>(smem + SM::qs_off(TP, K));
+  unsigned short* cand = reinterpret_cast<unsigned short*>(smem + SM::cand_off(TP, K));
+
+  const int L2pad = (L2 + kPadPoints - 1) / kPadPoints * kPadPoints;  // <= P2pad
+  const int num_tiles = (L2pad + TP - 1) / TP;
+  const float* soa_n = prm.soa + static_cast<size_t>(n) * ROWS * P2pad;
+
+  auto issue_tile = [&](int tile) {
+    const int stage = tile & 1;
+    const int j0 = tile * TP;
+    const int pts = min(TP, L2pad - j0);
+    const uint32_t bytes = static_cast<uint32_t>(pts) * 4u;
+    mbar_arrive_expect_tx(&bars[stage], bytes * ROWS);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+      tma_bulk_g2s(tiles + (static_cast<size_t>(stage) * ROWS + r) * TP,
+                   soa_n + static_cast<size_t>(r) * P2pad + j0, bytes, &bars[stage]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    issue_tile(0);
+    if (num_tiles > 1) issue_tile(1);
+  }
+
+  // ---- per-thread query state ---------------------------------------------------------------
+  const float M = __uint_as_float(prm.maxabs_bits[n]);
+  // E >= 130.2 * 2^-24 * M^2 bounds |filter - reference| (DESIGN.md "filter error bound").
+  const float E = fmaf(M * M, 1.52587890625e-05f /* 2^-16 */, 1e-37f);
+  float2 a2[Q][DT > 0 ? DT : 1];  // EXP: (-2q_d, -2q_d);  else .x = q_d
+  float qq[Q];
+  float T[Q];     // filter threshold
+  float dk[Q];    // current K-th distance (+inf while the list is not full)
+  int cnt[Q];
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    const int slot = t * THREADS + tid;
+    const int qi = q_base + slot;
+    const bool valid = qi < L1;
+    float q[DT];
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      q[d] = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
+      qs[d * QPB + slot] = q[d];
+      s = fmaf(q[d], q[d], s);
+      a2[t][d] = EXP ? make_float2(-2.0f * q[d], -2.0f * q[d]) : make_float2(q[d], q[d]);
+    }
+    qq[t] = s;
+    dk[t] = valid ? __int_as_float(0x7f800000) : -1.0f;
+    T[t] = valid ? (EXP ? FLT_MAX : __int_as_float(0x7f800000)) : -__int_as_float(0x7f800000);
+    cnt[t] = 0;
+    for (int k = 0; k < K; ++k) lists[static_cast<size_t>(k) * QPB + slot] = kEmptyKey;
+  }
+
+  // ---- flush: exact re-evaluation of buffered groups + sorted insertion -----------------------
+  auto flush = [&](int t, const float* tile, int j0) {
+    const int slot = t * THREADS + tid;
+    float q[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) q[d] = qs[d * QPB + slot];
+    uint64_t worst = lists[static_cast<size_t>(K - 1) * QPB + slot];
+    float dkt = dk[t];
+    const int c_end = cnt[t];
+    for (int c = 0; c < c_end; ++c) {
+      const int g = cand[c * QPB + slot];
+#pragma unroll
+      for (int i = 0; i < kGroup; ++i) {
+        const int jl = g * kGroup + i;
+        float d = 0.0f;
+#pragma unroll
+        for (int dd = 0; dd < DT; ++dd) {
+          const float term = dist_term<NORM>(q[dd], tile[dd * TP + jl]);
+          d = (dd == 0) ? term : __fadd_rn(d, term);
+        }
+        const int j = j0 + jl;
+        if (d <= dkt && j < L2) {
+          const uint64_t key = make_key(d, static_cast<uint32_t>(j));
+          if (key < worst) {
+            int k = K - 1;
+            while (k > 0) {
+              const uint64_t prev = lists[static_cast<size_t>(k - 1) * QPB + slot];
+              if (prev <= key) break;
+              lists[static_cast<size_t>(k) * QPB + slot] = prev;
+              --k;
+            }
+            lists[static_cast<size_t>(k) * QPB + slot] = key;
+            worst = lists[static_cast<size_t>(K - 1) * QPB + slot];
+            if (worst != kEmptyKey) dkt = key_dist(worst);
+          }
+        }
+      }
+    }
+    cnt[t] = 0;
+    dk[t] = dkt;
+    if (worst != kEmptyKey) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
+  };
+
+  // ---- main loop over p2 tiles ------------------------------------------------------------------
+  for (int tile_i = 0; tile_i < num_tiles; ++tile_i) {
+    const int stage = tile_i & 1;
+    const int j0 = tile_i * TP;
+    const int pts = min(TP, L2pad - j0);
+    const int ngroups = pts / kGroup;  // multiple of kChunk
+    const float* tile = tiles + static_cast<size_t>(stage) * ROWS * TP;
+    mbar_wait(&bars[stage], (tile_i >> 1) & 1);
+
+    for (int g0 = 0; g0 < ngroups; g0 += kChunk) {
+#pragma unroll
+      for (int c = 0; c < kChunk; ++c) {
+        const int g = g0 + c;
+        float4 X[DT];
+#pragma unroll
+        for (int d = 0; d < DT; ++d)
+          X[d] = reinterpret_cast<const float4*>(tile + d * TP)[g];
+        float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EXP) W = reinterpret_cast<const float4*>(tile + DT * TP)[g];
+#pragma unroll
+        for (int t = 0; t < Q; ++t) {
+          float m;
+          if (EXP) {
+            float2 s01 = make_float2(W.x, W.y), s23 = make_float2(W.z, W.w);
+#pragma unroll
+            for (int d = 0; d < DT; ++d) {
+              s01 = __ffma2_rn(a2[t][d], make_float2(X[d].x, X[d].y), s01);
+              s23 = __ffma2_rn(a2[t][d], make_float2(X[d].z, X[d].w), s23);
+            }
+            m = fminf(fminf(s01.x, s01.y), fminf(s23.x, s23.y));
+          } else {
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int d = 0; d < DT; ++d) {
+              const float qd = a2[t][d].x;
+              const float t0 = dist_term<NORM>(qd, X[d].x), t1 = dist_term<NORM>(qd, X[d].y);
+              const float t2 = dist_term<NORM>(qd, X[d].z), t3 = dist_term<NORM>(qd, X[d].w);
+              d0 = d == 0 ? t0 : __fadd_rn(d0, t0);
+              d1 = d == 0 ? t1 : __fadd_rn(d1, t1);
+              d2 = d == 0 ? t2 : __fadd_rn(d2, t2);
+              d3 = d == 0 ? t3 : __fadd_rn(d3, t3);
+            }
+            m = fminf(fminf(d0, d1), fminf(d2, d3));
+          }
+          if (m <= T[t]) {
+            cand[cnt[t] * QPB + t * THREADS + tid] = static_cast<unsigned short>(g);
+            ++cnt[t];
+          }
+        }
+      }
+      int mx = cnt[0];
+#pragma unroll
+      for (int t = 1; t < Q; ++t) mx = max(mx, cnt[t]);
+      if (mx > BCAP - kChunk) {
+#pragma unroll
+        for (int t = 0; t < Q; ++t) flush(t, tile, j0);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < Q; ++t) flush(t, tile, j0);
+
+    __syncthreads();  // everyone is done reading this stage
+    if (tid == 0 && tile_i + 2 < num_tiles) {
+      fence_proxy_async();
+      issue_tile(tile_i + 2);
+    }
+  }
+
+  // ---- write out: sorted keys -> (idx, dist); empty slots and rows >= L1 are (0, 0) -----------
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    const int slot = t * THREADS + tid;
+    const int qi = q_base + slot;
+    if (qi >= prm.P1) continue;
+    int64_t* oi = out_idx + static_cast<size_t>(qi) * K;
+    float* od = out_d + static_cast<size_t>(qi) * K;
+    for (int k = 0; k < K; ++k) {
+      const uint64_t key = lists[static_cast<size_t>(k) * QPB + slot];
+      const bool ok = key != kEmptyKey;
+      oi[k] = ok ? static_cast<int64_t>(key & 0xFFFFFFFFull) : 0;
+      od[k] = ok ? key_dist(key) : 0.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic fallback: any D, any K.  Thread per query; p2 tile (AoS) and the CTA's queries in
+// shared memory; exact distance; list column in shared memory when it fits, else in the
+// global workspace.
+// ---------------------------------------------------------------------------------------------
+struct KnnGenericParams {
+  const float* p1;
+  const float* p2;
+  const int64_t* len1;
+  const int64_t* len2;
+  int64_t* idx;
+  float* dists;
+  uint64_t* glists;  // [N][ceil(P1/THREADS)][K][THREADS] when lists live in global memory
+  int P1, P2, D, K, TP;
+  int lists_in_smem;
+};
+
+template <int NORM, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+knn_generic_kernel(const KnnGenericParams prm) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = blockIdx.y, tid = threadIdx.x, q_base = blockIdx.x * THREADS;
+  const int D = prm.D, K = prm.K, TP = prm.TP;
+  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
+  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
+  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
+  const int qi = q_base + tid;
+  const bool valid = qi < L1;
+
+  float* qsm = reinterpret_cast<float*>(smem);                   // [D][THREADS] (transposed)
+  float* tile = qsm + static_cast<size_t>(D) * THREADS;          // [TP][D]
+  uint64_t* lists = prm.lists_in_smem
+                        ? reinterpret_cast<uint64_t*>(smem + align_up((size_t(D) * THREADS + size_t(TP) * D) * 4, 8))
+                        : prm.glists + (static_cast<size_t>(n) * gridDim.x + blockIdx.x) * K * THREADS;
+  for (int d = 0; d < D; ++d)
+    qsm[d * THREADS + tid] = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * D + d] : 0.0f;
+  for (int k = 0; k < K; ++k) lists[static_cast<size_t>(k) * THREADS + tid] = kEmptyKey;
+  uint64_t worst = kEmptyKey;
+  float dk = __int_as_float(0x7f800000);
+
+  const float* p2n = prm.p2 + static_cast<size_t>(n) * prm.P2 * D;
+  for (int j0 = 0; j0 < L2; j0 += TP) {
+    const int pts = min(TP, L2 - j0);
+    __syncthreads();
+    for (int e = tid; e < pts * D; e += THREADS) tile[e] = p2n[static_cast<size_t>(j0) * D + e];
+    __syncthreads();
+    if (!valid) continue;
+    for (int jl = 0; jl < pts; ++jl) {
+      float d = 0.0f;
+      const float* pt = tile + jl * D;
+      for (int dd = 0; dd < D; ++dd) {
+        const float term = dist_term<NORM>(qsm[dd * THREADS + tid], pt[dd]);
+        d = __fadd_rn(d, term);
+      }
+      if (d <= dk) {
+        const uint64_t key = make_key(d, static_cast<uint32_t>(j0 + jl));
+        if (key < worst) {
+          int k = K - 1;
+          while (k > 0) {
+            const uint64_t prev = lists[static_cast<size_t>(k - 1) * THREADS + tid];
+            if (prev <= key) break;
+            lists[static_cast<size_t>(k) * THREADS + tid] = prev;
+            --k;
+          }
+          lists[static_cast<size_t>(k) * THREADS + tid] = key;
+          worst = lists[static_cast<size_t>(K - 1) * THREADS + tid];
+          if (worst != kEmptyKey) dk = key_dist(worst);
+        }
+      }
+    }
+  }
+  if (qi < prm.P1) {
+    int64_t* oi = prm.idx + (static_cast<size_t>(n) * prm.P1 + qi) * K;
+    float* od = prm.dists + (static_cast<size_t>(n) * prm.P1 + qi) * K;
+    for (int k = 0; k < K; ++k) {
+      const uint64_t key = lists[static_cast<size_t>(k) * THREADS + tid];
+      const bool ok = valid && key != kEmptyKey;
+      oi[k] = ok ? static_cast<int64_t>(key & 0xFFFFFFFFull) : 0;
+      od[k] = ok ? key_dist(key) : 0.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (knn_cpu.cpp:75-128)
+// ---------------------------------------------------------------------------------------------
+// One thread per (n, i1, d): accumulates grad_p1 in a register over k (no atomics on p1),
+// scatters -diff into grad_p2 with red.global.add.f32.
+template <int NORM>
+__global__ void knn_backward_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                    const int64_t* __restrict__ len1,
+                                    const int64_t* __restrict__ len2,
+                                    const int64_t* __restrict__ idx,
+                                    const float* __restrict__ grad_dists, int N, int P1, int P2,
+                                    int D, int K, float* __restrict__ grad_p1,
+                                    float* __restrict__ grad_p2) {
+  const size_t total = static_cast<size_t>(N) * P1 * D;
+  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(e % D);
+    const size_t row = e / D;  // n*P1 + i1
+    const int n = static_cast<int>(row / P1);
+    const int i1 = static_cast<int>(row % P1);
+    float acc = 0.0f;
+    int64_t L1 = len1[n], L2 = len2[n];
+    if (i1 < L1) {
+      const int kmax = static_cast<int>(L2 < K ? (L2 < 0 ? 0 : L2) : K);
+      const float a = p1[e];
+      for (int k = 0; k < kmax; ++k) {
+        const int64_t i2 = idx[row * K + k];
+        if (i2 < 0 || i2 >= P2) continue;  // -1 = padding (ball query)
+        const float g = grad_dists[row * K + k];
+        const float b = p2[(static_cast<size_t>(n) * P2 + i2) * D + d];
+        float diff;
+        // same float ops, same order as knn_cpu.cpp:113-122; intrinsics forbid contraction
+        if (NORM == 1) {
+          diff = __fmul_rn(g, (a > b) ? 1.0f : -1.0f);
+        } else {
+          diff = __fmul_rn(__fmul_rn(2.0f, g), __fsub_rn(a, b));
+        }
+        acc = __fadd_rn(acc, diff);
+        atomicAdd(grad_p2 + (static_cast<size_t>(n) * P2 + i2) * D + d, -diff);
+      }
+    }
+    grad_p1[e] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct TiledCfg {
+  int Q, threads, TP, BCAP;
+};
+
+// which (D, norm) the tiled kernel is instantiated for
+inline bool tiled_supported(int64_t D, int norm) { return D >= 1 && D <= 4 && (norm == 1 || norm == 2); }
+
+constexpr int kTiledThreads = 128;
+constexpr int kTiledQ = 4;
+constexpr size_t kMaxSmem = 227 * 1024;
+
+template <int DT, int NORM, bool EXP>
+size_t tiled_smem(int TP, int K, int BCAP) {
+  return KnnSmem<DT, NORM, EXP, kTiledQ, kTiledThreads>::total(TP, K, BCAP);
+}
+
+inline int pad_points(int64_t P2) {
+  return static_cast<int>((P2 + kPadPoints - 1) / kPadPoints * kPadPoints);
+}
+
+template <int DT, int NORM, bool EXP>
+int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
+                 int P1, int P2, int K, int64_t* idx, float* dists, void* ws, cudaStream_t st) {
+  constexpr int ROWS = DT + (EXP ? 1 : 0);
+  constexpr int QPB = kTiledQ * kTiledThreads;
+  const int P2pad = pad_points(P2);
+  unsigned* maxabs = reinterpret_cast<unsigned*>(ws);
+  float* soa = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up(size_t(N) * 4, 256));
+  POPS_CUDA_OK(cudaMemsetAsync(maxabs, 0, size_t(N) * 4, st));
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(P2pad, 256)), N);
+    knn_pack_kernel<DT, EXP><<<grid, 256, 0, st>>>(p2, len2, P2, P2pad, soa, maxabs);
+    POPS_LAUNCH_OK("knn_pack_kernel");
+    if (EXP) {
+      dim3 g2(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, ceil_div(int64_t(P1) * DT, 1024)))), N);
+      maxabs_kernel<<<g2, 256, 0, st>>>(p1, len1, P1, DT, maxabs);
+      POPS_LAUNCH_OK("maxabs_kernel");
+    }
+  }
+  KnnScanParams prm;
+  prm.p1 = p1; prm.soa = soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = maxabs;
+  prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = P2pad; prm.K = K;
+  prm.BCAP = 16;
+  // tile size: as large as fits next to the lists, capped, multiple of kPadPoints
+  int TP = 1024;
+  while (TP > kPadPoints && tiled_smem<DT, NORM, EXP>(TP, K, prm.BCAP) > 110 * 1024) TP /= 2;
+  if (TP > P2pad) TP = P2pad;
+  prm.TP = TP;
+  const size_t smem = tiled_smem<DT, NORM, EXP>(TP, K, prm.BCAP);
+  auto kern = knn_scan_kernel<DT, NORM, EXP, kTiledQ, kTiledThreads>;
+  POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(static_cast<unsigned>(ceil_div(P1, QPB)), N);
+  kern<<<grid, kTiledThreads, smem, st>>>(prm);
+  POPS_LAUNCH_OK("knn_scan_kernel");
+  (void)ROWS;
+  return POPS_OK;
+}
+
+// K small enough that TP >= kPadPoints tile + lists fit in shared memory
+template <int DT, int NORM, bool EXP>
+bool tiled_fits(int K) { return tiled_smem<DT, NORM, EXP>(kPadPoints * 8, K, 16) <= kMaxSmem; }
+
+constexpr int kGenericThreads = 128;
+
+inline void generic_layout(int D, int K, int* TP, int* lists_in_smem, size_t* smem) {
+  const size_t qbytes = size_t(D) * kGenericThreads * 4;
+  int tp = static_cast<int>(std::max<size_t>(8, std::min<size_t>(256, (32 * 1024) / (size_t(D) * 4))));
+  size_t base = align_up(qbytes + size_t(tp) * D * 4, 8);
+  while (base > 96 * 1024 && tp > 1) {
+    tp /= 2;
+    base = align_up(qbytes + size_t(tp) * D * 4, 8);
+  }
+  const size_t lbytes = size_t(K) * kGenericThreads * 8;
+  *TP = tp;
+  *lists_in_smem = (base + lbytes <= 160 * 1024) ? 1 : 0;
+  *smem = base + (*lists_in_smem ? lbytes : 0);
+}
+
+}  // namespace
+}  // namespace pops
+
+using namespace pops;
+
+extern "C" size_t pops_knn_workspace_bytes(int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K,
+                                           int norm) {
+  if (N <= 0 || P1 <= 0 || K <= 0) return 256;
+  size_t tiled = align_up(size_t(N) * 4, 256) + size_t(N) * (D + 1) * pad_points(P2) * 4;
+  size_t generic = size_t(N) * ceil_div(P1, kGenericThreads) * K * kGenericThreads * 8;
+  (void)norm;
+  return align_up(std::max(tiled, generic), 256) + 256;
+}
+
+extern "C" int pops_knn_check_version(int version, int64_t D, int64_t K) {
+  // the predicates of the reference's kernel variants (knn.cu:292-303)
+  if (version == 0) return 1;
+  if (version == 1) return D <= 32;
+  if (version == 2) return D <= 8 && K <= 32;
+  if (version == 3) return D <= 8 && K <= 4;
+  return 0;
+}
+
+extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64_t* lengths1,
+                                   const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2,
+                                   int64_t D, int64_t K, int norm, int version, int64_t* idx,
+                                   float* dists, void* workspace, size_t workspace_bytes,
+                                   pops_stream_t stream) {
+  (void)version;
+  POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
+  POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0 && K >= 0, "negative size");
+  if (N == 0 || P1 == 0 || K == 0) return POPS_OK;  // empty outputs (knn.cu:346-349)
+  POPS_CHECK_ARG(p1 && p2 && lengths1 && lengths2 && idx && dists, "null pointer argument");
+  POPS_CHECK_ARG(P2 < (int64_t(1) << 31) && P1 < (int64_t(1) << 31) && N < 65536, "size too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (workspace_bytes < pops_knn_workspace_bytes(N, P1, P2, D, K, norm) || !workspace)
+    return fail(POPS_ERR_WORKSPACE, "knn: workspace missing or too small");
+  if (P2 == 0 || D == 0) {
+    POPS_CUDA_OK(cudaMemsetAsync(idx, 0, size_t(N) * P1 * K * 8, st));
+    POPS_CUDA_OK(cudaMemsetAsync(dists, 0, size_t(N) * P1 * K * 4, st));
+    return POPS_OK;
+  }
+  const int n = int(N), p1n = int(P1), p2n = int(P2), k = int(K);
+#define POPS_TILED(DT, NORM, EXP)                                                             \
+  if (D == DT && norm == NORM && tiled_fits<DT, NORM, EXP>(k)) \
+    return launch_tiled<DT, NORM, EXP>(p1, p2, lengths1, lengths2, n, p1n, p2n, k, idx, dists, workspace, st);
+  POPS_TILED(3, 2, true)
+  POPS_TILED(3, 1, false)
+  POPS_TILED(2, 2, false)
+  POPS_TILED(2, 1, false)
+  POPS_TILED(4, 2, false)
+  POPS_TILED(4, 1, false)
+  POPS_TILED(1, 2, false)
+  POPS_TILED(1, 1, false)
+#undef POPS_TILED
+  // generic
+  KnnGenericParams prm;
+  prm.p1 = p1; prm.p2 = p2; prm.len1 = lengths1; prm.len2 = lengths2; prm.idx = idx; prm.dists = dists;
+  prm.glists = reinterpret_cast<uint64_t*>(workspace);
+  prm.P1 = p1n; prm.P2 = p2n; prm.D = int(D); prm.K = k;
+  size_t smem = 0;
+  generic_layout(int(D), k, &prm.TP, &prm.lists_in_smem, &smem);
+  if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: D too large for the generic kernel");
+  dim3 grid(static_cast<unsigned>(ceil_div(P1, kGenericThreads)), n);
+  if (norm == 2) {
+    auto kern = knn_generic_kernel<2, kGenericThreads>;
+    POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<grid, kGenericThreads, smem, st>>>(prm);
+  } else {
+    auto kern = knn_generic_kernel<1, kGenericThreads>;
+    POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<grid, kGenericThreads, smem, st>>>(prm);
+  }
+  POPS_LAUNCH_OK("knn_generic_kernel");
+  return POPS_OK;
+}
+
+extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const int64_t* lengths1,
+                                        const int64_t* lengths2, const int64_t* idx,
+                                        const float* grad_dists, int64_t N, int64_t P1, int64_t P2,
+                                        int64_t D, int64_t K, int norm, float* grad_p1,
+                                        float* grad_p2, pops_stream_t stream) {
+  POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
+  POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0 && K >= 0, "negative size");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N * P2 * D > 0) {
+    POPS_CHECK_ARG(grad_p2, "null grad_p2");
+    POPS_CUDA_OK(cudaMemsetAsync(grad_p2, 0, size_t(N) * P2 * D * 4, st));
+  }
+  const size_t total = size_t(N) * P1 * D;
+  if (total == 0) return POPS_OK;
+  POPS_CHECK_ARG(p1 && lengths1 && lengths2 && grad_p1, "null pointer argument");
+  if (K == 0 || P2 == 0) {
+    POPS_CUDA_OK(cudaMemsetAsync(grad_p1, 0, total * 4, st));
+    return POPS_OK;
+  }
+  POPS_CHECK_ARG(p2 && idx && grad_dists, "null pointer argument");
+  const int threads = 256;
+  const int blocks = int(std::min<int64_t>(ceil_div(int64_t(total), threads), int64_t(num_sms()) * 16));
+  if (norm == 2)
+    knn_backward_kernel<2><<<blocks, threads, 0, st>>>(p1, p2, lengths1, lengths2, idx, grad_dists,
+                                                       int(N), int(P1), int(P2), int(D), int(K),
+                                                       grad_p1, grad_p2);
+  else
+    knn_backward_kernel<1><<<blocks, threads, 0, st>>>(p1, p2, lengths1, lengths2, idx, grad_dists,
+                                                       int(N), int(P1), int(P2), int(D), int(K),
+                                                       grad_p1, grad_p2);
+  POPS_LAUNCH_OK("knn_backward_kernel");
+  return POPS_OK;
+}

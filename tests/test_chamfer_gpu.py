@@ -1,0 +1,76 @@
+"""GPU parity: chamfer_distance (all reduction modes, features, weights, norms) against the
+reference's golden outputs and gradients.  Losses/grads within 1e-5 relative."""
+import pytest
+import torch
+
+from test_oracle import chamfer_variants, run_chamfer_variant
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_chamfer_all_variants_vs_golden(golden):
+    from pytorch3d_pointops_b200.functions.chamfer import chamfer_distance
+
+    g = golden("chamfer_cases")
+    for vi, v in enumerate(chamfer_variants(golden)):
+        flat, grads = run_chamfer_variant(chamfer_distance, g, v, DEV)
+        assert len(flat) == int(g.a(f"v{vi}.nout")), v
+        for i, t in enumerate(flat):
+            assert torch.allclose(t.detach().cpu(), g.t(f"v{vi}.out{i}"), rtol=1e-5, atol=1e-7), (v, i)
+        for n, gr in grads.items():
+            want = g.t(f"v{vi}.g_{n}")
+            if want.numel() == 0:
+                assert gr.numel() == 0 or not gr.any(), (v, n)
+            else:
+                assert torch.allclose(gr.cpu(), want, rtol=1e-5, atol=1e-6), (v, n)
+
+
+def test_chamfer_pointclouds_input(golden):
+    from pytorch3d_pointops_b200.functions.chamfer import chamfer_distance
+    from pytorch3d_pointops_b200.structures import Pointclouds
+
+    g = golden("chamfer_cases")
+    x, y, xl, yl = g.t("x", DEV), g.t("y", DEV), g.t("xl").tolist(), g.t("yl").tolist()
+    xn, yn = g.t("xn", DEV), g.t("yn", DEV)
+    pcx = Pointclouds([x[i, :l] for i, l in enumerate(xl)], features={"normals": [xn[i, :l] for i, l in enumerate(xl)]})
+    pcy = Pointclouds([y[i, :l] for i, l in enumerate(yl)], features={"normals": [yn[i, :l] for i, l in enumerate(yl)]})
+    loss, lf = chamfer_distance(pcx, pcy, feature_names=["normals"])
+    assert torch.allclose(loss.cpu(), g.t("pc.loss"), rtol=1e-5)
+    assert torch.allclose(lf["normals"].cpu(), g.t("pc.normals"), rtol=1e-5)
+    # features present but feature_names None -> second element None (chamfer.py:107-112)
+    loss2, lf2 = chamfer_distance(pcx, pcy)
+    assert lf2 is None and torch.allclose(loss2, loss)
+    with pytest.raises(ValueError, match="missing in x_features"):
+        chamfer_distance(Pointclouds([x[0]]), Pointclouds([y[0]]), feature_names=["normals"])
+
+
+def test_chamfer_config2_vs_oracle(oracle):
+    """BASELINE.json configs[1] at reduced batch (B=4, P<=2048 ragged, normals+colors):
+    loss, feature losses and all gradients against the oracle."""
+    from pytorch3d_pointops_b200.functions.chamfer import chamfer_distance
+
+    gen = torch.Generator().manual_seed(1)
+    N, P = 4, 2048
+    x, y = torch.rand(N, P, 3, generator=gen), torch.rand(N, P, 3, generator=gen)
+    xl = torch.randint(P // 2, P + 1, (N,), generator=gen)
+    yl = torch.randint(P // 2, P + 1, (N,), generator=gen)
+    xn = torch.nn.functional.normalize(torch.randn(N, P, 3, generator=gen), dim=-1)
+    yn = torch.nn.functional.normalize(torch.randn(N, P, 3, generator=gen), dim=-1)
+    xc, yc = torch.rand(N, P, 3, generator=gen), torch.rand(N, P, 3, generator=gen)
+
+    def run(fn, dev):
+        ts = [t.to(dev).clone().requires_grad_(True) for t in (x, y, xn, yn, xc, yc)]
+        loss, lf = fn(ts[0], ts[1], x_lengths=xl.to(dev), y_lengths=yl.to(dev),
+                      x_features={"normals": ts[2], "colors": ts[4]},
+                      y_features={"normals": ts[3], "colors": ts[5]},
+                      feature_names=["normals", "colors"])
+        (loss + lf["normals"] + lf["colors"]).backward()
+        return [loss, lf["normals"], lf["colors"]], [t.grad for t in ts]
+
+    o_out, o_grads = run(oracle.chamfer_distance, "cpu")
+    g_out, g_grads = run(chamfer_distance, DEV)
+    for a, b in zip(g_out, o_out):
+        assert torch.allclose(a.detach().cpu(), b.detach(), rtol=1e-5, atol=1e-8)
+    for a, b in zip(g_grads, o_grads):
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-8)

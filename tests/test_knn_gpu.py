@@ -1,0 +1,217 @@
+"""GPU parity: knn_points / knn_gather / backward against the reference's golden vectors and the
+CPU oracle on seeded inputs.  Indices bit-exact (ties -> lower index), distances bit-exact
+(same unfused float32 arithmetic), gradients rtol 1e-5 (float atomics reorder the sums)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+KNN_CASES = ["d3k1", "d3k16", "d3k32_l1", "d3k40", "d2k5", "d5k7", "d33k4", "d128k16", "klen"]
+
+
+def _ops():
+    from pytorch3d_pointops_b200 import _C
+    from pytorch3d_pointops_b200.functions import knn_gather, knn_points
+
+    return _C, knn_points, knn_gather
+
+
+@pytest.mark.parametrize("name", KNN_CASES)
+def test_golden_forward_backward(golden, name):
+    _C, knn_points, _ = _ops()
+    g = golden("knn_cases")
+    p1 = g.t(f"{name}.p1", DEV).requires_grad_(True)
+    p2 = g.t(f"{name}.p2", DEV).requires_grad_(True)
+    l1, l2 = g.t(f"{name}.l1", DEV), g.t(f"{name}.l2", DEV)
+    K, norm = int(g.a(f"{name}.K")), int(g.a(f"{name}.norm"))
+    res = knn_points(p1, p2, l1, l2, norm=norm, K=K, return_nn=True)
+    assert res.idx.dtype == torch.int64
+    assert torch.equal(res.idx.cpu(), g.t(f"{name}.idx"))
+    assert torch.equal(res.dists.detach().cpu(), g.t(f"{name}.dists"))
+    assert torch.equal(res.knn.detach().cpu(), g.t(f"{name}.knn"))
+    ((res.dists * g.t(f"{name}.gd", DEV)).sum() + (res.knn * g.t(f"{name}.gn", DEV)).sum()).backward()
+    assert torch.allclose(p1.grad.cpu(), g.t(f"{name}.grad_p1"), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(p2.grad.cpu(), g.t(f"{name}.grad_p2"), rtol=1e-5, atol=1e-5)
+
+
+def test_readme_config(golden):
+    """BASELINE.json configs[0]: README Pointclouds (1000/800 pts), self-KNN K=8."""
+    from pytorch3d_pointops_b200.structures import Pointclouds
+
+    _, knn_points, _ = _ops()
+    g = golden("knn_readme")
+    pc = Pointclouds([g.t("p0", DEV), g.t("p1", DEV)])
+    X, L = pc.points_padded(), pc.num_points_per_cloud()
+    assert torch.equal(X.cpu(), g.t("padded"))
+    out = knn_points(X, X, lengths1=L, lengths2=L, K=8)
+    assert torch.equal(out.idx.cpu(), g.t("idx"))
+    assert torch.equal(out.dists.cpu(), g.t("dists"))
+
+
+@pytest.mark.parametrize("K", [1, 3, 7, 16, 17, 32, 33])
+def test_exact_ties_integer_grid(golden, K):
+    _C, _, _ = _ops()
+    g = golden("knn_cases")
+    p = g.t("grid.p", DEV)
+    L = torch.tensor([p.shape[1]], device=DEV)
+    idx, dists = _C.knn_points_idx(p, p, L, L, 2, K, -1)
+    assert torch.equal(idx.cpu(), g.t(f"grid.K{K}.idx"))
+    assert torch.equal(dists.cpu(), g.t(f"grid.K{K}.dists"))
+
+
+def test_tie_vector(golden):
+    _, knn_points, _ = _ops()
+    g = golden("knn_cases")
+    for K in (3, 4, 5):
+        r = knn_points(g.t("tie.p1", DEV), g.t("tie.p2", DEV), K=K)
+        assert torch.equal(r.idx.cpu(), g.t(f"tie.K{K}.idx"))
+
+
+SWEEP = [
+    # N, P1, P2, D, K, norm
+    (2, 700, 900, 3, 16, 2), (3, 513, 2049, 3, 1, 2), (2, 100, 5000, 3, 32, 2),
+    (1, 2000, 2000, 3, 8, 1), (2, 257, 300, 2, 5, 2), (2, 300, 257, 4, 12, 1),
+    (2, 300, 257, 1, 3, 2), (1, 64, 200, 8, 8, 2), (2, 50, 120, 16, 40, 2),
+    (1, 40, 300, 64, 4, 1), (1, 33, 97, 3, 100, 2), (2, 1, 1, 3, 1, 2), (1, 5, 3, 3, 7, 2),
+    (1, 130, 70, 3, 64, 2), (1, 60, 500, 5, 200, 2),
+]
+
+
+@pytest.mark.parametrize("N,P1,P2,D,K,norm", SWEEP)
+def test_oracle_sweep(oracle, N, P1, P2, D, K, norm):
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(N * 1000 + P1 + P2 + D + K + norm)
+    p1 = torch.randn(N, P1, D, generator=gen)
+    p2 = torch.randn(N, P2, D, generator=gen)
+    l1 = torch.randint(0, P1 + 1, (N,), generator=gen)
+    l2 = torch.randint(0, P2 + 1, (N,), generator=gen)
+    l1[0], l2[0] = P1, P2
+    oi, od = oracle.knn_points_idx(p1, p2, l1, l2, norm, K)
+    gi, gd = _C.knn_points_idx(p1.to(DEV), p2.to(DEV), l1.to(DEV), l2.to(DEV), norm, K, -1)
+    assert torch.equal(gi.cpu(), oi)
+    assert torch.equal(gd.cpu(), od)
+    grad = torch.randn(N, P1, K, generator=gen)
+    o1, o2 = oracle.knn_points_backward(p1, p2, l1, l2, oi, norm, grad)
+    g1, g2 = _C.knn_points_backward(p1.to(DEV), p2.to(DEV), l1.to(DEV), l2.to(DEV), gi, norm, grad.to(DEV))
+    assert torch.equal(g1.cpu(), o1)  # no atomics on p1: same op order as the reference
+    assert torch.allclose(g2.cpu(), o2, rtol=1e-5, atol=1e-5)
+
+
+def test_duplicates_offsets_and_scales(oracle):
+    """Adversarial inputs for the filter: duplicated points, large offsets (cancellation in the
+    expanded form), tiny and huge scales, clustered queries."""
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(77)
+    base = torch.rand(2, 600, 3, generator=gen)
+    cases = {
+        "dups": base[:, torch.randint(0, 40, (600,), generator=gen)],
+        "offset1e3": base + 1000.0,
+        "offset1e5": base * 0.01 + 1e5,
+        "tiny": base * 1e-20,
+        "huge": base * 1e15,
+        "mixed": torch.cat([base[:, :300] * 1e-3, base[:, 300:] * 50 + 7], 1),
+        "line": torch.stack([base[..., 0], base[..., 0] * 0, base[..., 0] * 0], -1),
+    }
+    for name, p in cases.items():
+        p = p.contiguous()
+        L = torch.tensor([600, 431])
+        for K in (1, 16):
+            oi, od = oracle.knn_points_idx(p, p, L, L, 2, K)
+            gi, gd = _C.knn_points_idx(p.to(DEV), p.to(DEV), L.to(DEV), L.to(DEV), 2, K, -1)
+            assert torch.equal(gi.cpu(), oi), (name, K)
+            assert torch.equal(gd.cpu(), od), (name, K)
+
+
+def test_backward_many_to_one(oracle):
+    """Every query shares one neighbour: heavy atomic contention on a single grad_p2 row."""
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(3)
+    p1 = torch.rand(1, 4096, 3, generator=gen) + 5.0
+    p2 = torch.cat([torch.full((1, 1, 3), 5.5), torch.rand(1, 63, 3, generator=gen) - 100.0], 1)
+    oi, od = oracle.knn_points_idx(p1, p2, None, None, 2, 1)
+    assert not oi.any()
+    g = torch.rand(1, 4096, 1, generator=gen)
+    o1, o2 = oracle.knn_points_backward(p1, p2, None, None, oi, 2, g)
+    L1 = torch.tensor([4096], device=DEV)
+    L2 = torch.tensor([64], device=DEV)
+    g1, g2 = _C.knn_points_backward(p1.to(DEV), p2.to(DEV), L1, L2, oi.to(DEV), 2, g.to(DEV))
+    assert torch.equal(g1.cpu(), o1)
+    assert torch.allclose(g2.cpu(), o2, rtol=1e-5, atol=1e-4)
+
+
+def test_knn_gather_semantics(golden):
+    _, _, knn_gather = _ops()
+    from pytorch3d_pointops_b200.functions import masked_gather
+
+    g = golden("gather_cases")
+    x = g.t("kg.x", DEV)
+    idx = g.t("kg.idx", DEV)
+    assert torch.equal(knn_gather(x, idx, g.t("kg.lengths", DEV)).cpu(), g.t("kg.out"))
+    assert torch.equal(knn_gather(x, idx).cpu(), g.t("kg.out_full"))
+    assert torch.equal(masked_gather(x, g.t("mg.idx3", DEV)).cpu(), g.t("mg.out3"))
+    assert torch.equal(masked_gather(x, g.t("mg.idx2", DEV)).cpu(), g.t("mg.out2"))
+    # -1 is an error for knn_gather in the reference
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        knn_gather(x, g.t("mg.idx3", DEV))
+    # vectorised path (U % 4 == 0) and other dtypes
+    x8 = torch.randn(3, 40, 8, device=DEV)
+    want = x8.cpu()[:, :, None].expand(-1, -1, 6, -1).gather(1, idx.cpu()[..., None].expand(-1, -1, -1, 8))
+    assert torch.equal(knn_gather(x8, idx).cpu(), want)
+    xi = torch.randint(0, 1 << 40, (3, 40, 3), device=DEV)
+    wanti = xi.cpu()[:, :, None].expand(-1, -1, 6, -1).gather(1, idx.cpu()[..., None].expand(-1, -1, -1, 3))
+    assert torch.equal(knn_gather(xi, idx).cpu(), wanti)
+    # backward = scatter-add
+    xr = x.clone().requires_grad_(True)
+    w = torch.randn(3, 25, 6, 7, device=DEV)
+    (knn_gather(xr, idx) * w).sum().backward()
+    ref = torch.zeros_like(x).index_put_(
+        (torch.arange(3, device=DEV)[:, None, None].expand_as(idx), idx), w, accumulate=True)
+    assert torch.allclose(xr.grad, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_headline_shape_properties(oracle):
+    """BASELINE target shape (B=32, P=16384, K=16, D=3): size-independent properties on the full
+    output plus exact oracle agreement on a sample of queries."""
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(0)
+    N, P, K = 32, 16384, 16
+    p = torch.rand(N, P, 3, generator=gen)
+    lengths = torch.randint(8192, P + 1, (N,), generator=gen)
+    lengths[0] = P
+    pd, ld = p.to(DEV), lengths.to(DEV)
+    idx, dists = _C.knn_points_idx(pd, pd, ld, ld, 2, K, -1)
+    valid = torch.arange(P, device=DEV)[None] < ld[:, None]
+    # self is the nearest neighbour at distance 0 (random floats: no duplicates)
+    assert torch.equal(idx[..., 0][valid], torch.arange(P, device=DEV)[None].expand(N, -1)[valid])
+    assert not dists[..., 0].any()
+    # ascending, in range, padding rows zero
+    assert (dists[..., 1:] >= dists[..., :-1]).all()
+    assert (idx < ld[:, None, None]).all() and (idx >= 0).all()
+    assert not idx[~valid].any() and not dists[~valid].any()
+    # distances recomputed from the indices agree bit for bit (unfused arithmetic)
+    nb = pd[torch.arange(N, device=DEV)[:, None, None], idx]
+    diff = pd[:, :, None, :] - nb
+    sq = diff * diff
+    recomputed = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+    assert torch.equal(recomputed[valid], dists[valid])
+    # exact agreement with the oracle on 64 queries of 3 clouds
+    for n in (0, 7, 31):
+        oi, od = oracle.knn_points_idx(p[n:n + 1], p[n:n + 1], lengths[n:n + 1], lengths[n:n + 1], 2, K,
+                                       q0=1000, q1=1064, threads=8)
+        assert torch.equal(idx[n, 1000:1064].cpu(), oi[0, 1000:1064])
+        assert torch.equal(dists[n, 1000:1064].cpu(), od[0, 1000:1064])
+
+
+def test_no_cuda_errors_and_streams():
+    """Runs on a non-default stream and leaves no sticky CUDA error behind."""
+    _C, knn_points, _ = _ops()
+    s = torch.cuda.Stream(device=DEV)
+    p = torch.rand(2, 3000, 3, device=DEV)
+    ref = knn_points(p, p, K=4)
+    s.wait_stream(torch.cuda.current_stream(DEV))
+    with torch.cuda.stream(s):
+        out = knn_points(p, p, K=4)
+    s.synchronize()
+    assert torch.equal(out.idx, ref.idx) and torch.equal(out.dists, ref.dists)
+    torch.cuda.synchronize()
