@@ -47,6 +47,20 @@ const char* pops_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 int64_t pops_launch_count(void);
 
+/* Optional per-kernel timing (bench.py "roofline"): while enabled, the library brackets its
+ * dominant kernels with CUDA events on the launching stream.  pops_profile_read synchronises
+ * those events and returns, for the named kernel ("knn_scan", "fps", "ball_query", "gather",
+ * "knn_backward", "chamfer"), the number of launches seen since the last reset and their total
+ * device time in milliseconds.  Off by default; costs two event records per launch when on. */
+void pops_profile_enable(int on);
+void pops_profile_reset(void);
+int pops_profile_read(const char* kernel, int64_t* launches, double* total_ms);
+
+/* Register-only FP32 FMA probe: runs `iters` dependent-chain FFMA rounds on every SM and returns
+ * the achieved TFLOP/s (2 flop per FMA) measured with CUDA events on `stream`.  Used by bench.py
+ * as the measured FP32 roofline denominator (MEASURED_PEAKS.json has no FP32 entry). */
+double pops_fp32_peak_probe(int iters, pops_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * KNN forward.  Replaces _C.knn_points_idx (ext.cpp:21; knn.h:59-80; knn_cpu.cpp:13-69) AND the
  * sort + gather post-pass of functions/knn.py:77-89: results come back already in the canonical

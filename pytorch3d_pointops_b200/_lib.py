@@ -20,6 +20,10 @@ SIGNATURES = {
     "pops_build_info": (c_char_p, []),
     "pops_last_error": (c_char_p, []),
     "pops_launch_count": (c_int64, []),
+    "pops_profile_enable": (None, [c_int]),
+    "pops_profile_reset": (None, []),
+    "pops_profile_read": (c_int, [c_char_p, _P, _P]),
+    "pops_fp32_peak_probe": (ctypes.c_double, [c_int, _P]),
     "pops_knn_workspace_bytes": (c_size_t, [c_int64] * 5 + [c_int]),
     "pops_knn_points_idx": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "pops_knn_check_version": (c_int, [c_int, c_int64, c_int64]),

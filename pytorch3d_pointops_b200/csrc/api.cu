@@ -1,4 +1,7 @@
 // Library-level plumbing of libpointops_b200.so: error string, build info, launch counter.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace pops {
@@ -7,7 +10,109 @@ std::string& last_error_ref() {
   return err;
 }
 std::atomic<int64_t> g_launch_count{0};
+
+// ---- optional per-kernel timing ---------------------------------------------------------------
+namespace {
+struct ProfRec {
+  std::string name;
+  cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_open;  // begin events waiting for their end
+}  // namespace
+
+void profile_begin(const char* kernel, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.name = kernel;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void profile_end(const char* kernel, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto it = g_prof.rbegin(); it != g_prof.rend(); ++it)
+    if (it->name == kernel) {
+      cudaEventRecord(it->b, st);
+      return;
+    }
+}
 }  // namespace pops
+
+extern "C" void pops_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(pops::g_prof_mu);
+  pops::g_prof_on = on != 0;
+}
+extern "C" void pops_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(pops::g_prof_mu);
+  for (auto& r : pops::g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  pops::g_prof.clear();
+}
+extern "C" int pops_profile_read(const char* kernel, int64_t* launches, double* total_ms) {
+  std::lock_guard<std::mutex> lk(pops::g_prof_mu);
+  int64_t n = 0;
+  double ms = 0.0;
+  for (auto& r : pops::g_prof) {
+    if (r.name != kernel) continue;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return POPS_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return POPS_ERR_CUDA;
+    ms += t;
+    ++n;
+  }
+  if (launches) *launches = n;
+  if (total_ms) *total_ms = ms;
+  return POPS_OK;
+}
+
+// ---- FP32 FMA probe ----------------------------------------------------------------------------
+namespace pops {
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters, float a, float b) {
+  float r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = threadIdx.x * 1e-3f + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += r[i];
+  if (s == 123.456f) out[0] = s;  // never true; keeps the chain alive
+}
+}  // namespace pops
+
+extern "C" double pops_fp32_peak_probe(int iters, pops_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* d = nullptr;
+  if (cudaMalloc(&d, 4) != cudaSuccess) return -1.0;
+  const int blocks = pops::num_sms() * 8;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  pops::fp32_probe_kernel<<<blocks, 256, 0, st>>>(d, 64, 1.0001f, 0.5f);  // warm-up
+  cudaEventRecord(a, st);
+  pops::fp32_probe_kernel<<<blocks, 256, 0, st>>>(d, iters, 1.0001f, 0.5f);
+  cudaEventRecord(b, st);
+  cudaEventSynchronize(b);
+  pops::g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (ms <= 0.f) return -1.0;
+  const double flops = 2.0 * 16.0 * double(iters) * 256.0 * double(blocks);
+  return flops / (double(ms) * 1e-3) / 1e12;
+}
 
 extern "C" int pops_abi_version(void) { return 1; }
 

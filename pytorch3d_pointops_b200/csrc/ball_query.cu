@@ -188,7 +188,9 @@ extern "C" int pops_ball_query(const float* p1, const float* p2, const int64_t* 
   if (D == 3) {
     prm.TP = 2048;
     const size_t smem = size_t(4) * prm.TP * 4;
+    profile_begin("ball_query", st);
     ball_query_d3_kernel<<<grid, kBqThreads, smem, st>>>(prm);
+    profile_end("ball_query", st);
     POPS_LAUNCH_OK("ball_query_d3_kernel");
     return POPS_OK;
   }

@@ -43,6 +43,10 @@ inline int fail(int code, const std::string& msg) {
       return ::pops::fail(POPS_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// per-kernel timing (api.cu); no-ops unless pops_profile_enable(1)
+void profile_begin(const char* kernel, cudaStream_t st);
+void profile_end(const char* kernel, cudaStream_t st);
+
 inline int num_sms() {
   static int cached = 0;
   if (cached == 0) {

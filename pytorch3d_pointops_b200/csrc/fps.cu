@@ -223,7 +223,9 @@ int launch_fps_d3(const float* points, const int64_t* lengths, const int64_t* K,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (C > 8) POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  profile_begin("fps", st);
   POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, points, lengths, K, start, P, max_K, C, out));
+  profile_end("fps", st);
   POPS_LAUNCH_OK("fps_d3_kernel");
   return POPS_OK;
 }

@@ -32,6 +32,7 @@ namespace pops {
 constexpr int kGroup = 4;             // points per filter group (one float4 per SoA row)
 constexpr int kChunk = 4;             // groups between candidate-buffer overflow checks
 constexpr int kPadPoints = kGroup * kChunk;  // SoA rows padded to a multiple of this
+constexpr int kSurvCap = 16;           // survivor keys a lane may hold between two merges
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
 // ---------------------------------------------------------------------------------------------
@@ -123,8 +124,12 @@ struct KnnSmem {
   static __host__ __device__ size_t qs_bytes() { return size_t(DT) * QPB * 4; }
   static __host__ __device__ size_t cand_off(int TP, int K) { return qs_off(TP, K) + qs_bytes(); }
   static __host__ __device__ size_t cand_bytes(int BCAP) { return size_t(BCAP) * QPB * 2; }
+  static __host__ __device__ size_t surv_off(int TP, int K, int BCAP) {
+    return (cand_off(TP, K) + cand_bytes(BCAP) + 7) / 8 * 8;
+  }
+  static __host__ __device__ size_t surv_bytes() { return size_t(kSurvCap) * THREADS * 8; }
   static __host__ __device__ size_t total(int TP, int K, int BCAP) {
-    return cand_off(TP, K) + cand_bytes(BCAP);
+    return surv_off(TP, K, BCAP) + surv_bytes();
   }
 };
 
@@ -162,6 +167,7 @@ knn_scan_kernel(const KnnScanParams prm) {
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + SM::lists_off(TP));
   float* qs = reinterpret_cast<float*>(smem + SM::qs_off(TP, K));
   unsigned short* cand = reinterpret_cast<unsigned short*>(smem + SM::cand_off(TP, K));
+  uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off(TP, K, BCAP));
 
   const int L2pad = (L2 + kPadPoints - 1) / kPadPoints * kPadPoints;  // <= P2pad
   const int num_tiles = (L2pad + TP - 1) / TP;
@@ -194,76 +200,124 @@ knn_scan_kernel(const KnnScanParams prm) {
   const float M = __uint_as_float(prm.maxabs_bits[n]);
   // E >= 130.2 * 2^-24 * M^2 bounds |filter - reference| (DESIGN.md "filter error bound").
   const float E = fmaf(M * M, 1.52587890625e-05f /* 2^-16 */, 1e-37f);
-  float2 a2[Q][DT > 0 ? DT : 1];  // EXP: (-2q_d, -2q_d);  else .x = q_d
+  constexpr uint32_t CSTRIDE = QPB * 2;  // bytes between consecutive entries of one candidate buffer
+  float a[Q][DT];   // EXP: -2 q_d (FFMA2 takes it as a broadcast scalar operand);  else q_d
   float qq[Q];
-  float T[Q];     // filter threshold
-  float dk[Q];    // current K-th distance (+inf while the list is not full)
-  int cnt[Q];
+  float T[Q];       // filter threshold
+  float dk[Q];      // current K-th distance (+inf while the list is not full)
+  uint32_t cw[Q];   // shared-memory byte address of the next free candidate slot
+  const uint32_t cand_base = smem_u32(cand) + static_cast<uint32_t>(tid) * 2u;
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
     const int slot = t * THREADS + tid;
     const int qi = q_base + slot;
     const bool valid = qi < L1;
-    float q[DT];
     float s = 0.0f;
 #pragma unroll
     for (int d = 0; d < DT; ++d) {
-      q[d] = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
-      qs[d * QPB + slot] = q[d];
-      s = fmaf(q[d], q[d], s);
-      a2[t][d] = EXP ? make_float2(-2.0f * q[d], -2.0f * q[d]) : make_float2(q[d], q[d]);
+      const float q = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
+      qs[d * QPB + slot] = q;
+      s = fmaf(q, q, s);
+      a[t][d] = EXP ? -2.0f * q : q;
     }
     qq[t] = s;
     dk[t] = valid ? __int_as_float(0x7f800000) : -1.0f;
     T[t] = valid ? (EXP ? FLT_MAX : __int_as_float(0x7f800000)) : -__int_as_float(0x7f800000);
-    cnt[t] = 0;
+    cw[t] = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
     for (int k = 0; k < K; ++k) lists[static_cast<size_t>(k) * QPB + slot] = kEmptyKey;
   }
 
-  // ---- flush: exact re-evaluation of buffered groups + sorted insertion -----------------------
+  // ---- flush: drain one query's candidate buffer -------------------------------------------------
+  // Called warp-converged (every lane flushes together) and kept converged inside: rare events
+  // never sit inside a dense loop.
+  //   fill   per buffered group, all 4 points get the exact unfused distance (branch-free); points
+  //          with d <= dk are appended as 64-bit keys to the lane's survivor column (predicated);
+  //   merge  the (few) survivors are sorted, the number r that belongs to the K smallest is
+  //          counted, and a backward in-place merge shifts the sorted list -- cost ~ r + shifted
+  //          elements, independent of where the survivors land.
   auto flush = [&](int t, const float* tile, int j0) {
     const int slot = t * THREADS + tid;
+    const uint32_t base = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
+    const int c_end = static_cast<int>((cw[t] - base) / CSTRIDE);
+    cw[t] = base;
+    if (!__any_sync(0xffffffffu, c_end > 0)) return;
     float q[DT];
 #pragma unroll
     for (int d = 0; d < DT; ++d) q[d] = qs[d * QPB + slot];
-    uint64_t worst = lists[static_cast<size_t>(K - 1) * QPB + slot];
+    uint64_t* L = lists + slot;   // element k at L[k * QPB]
+    uint64_t* S = surv + tid;     // element a at S[a * THREADS]
     float dkt = dk[t];
-    const int c_end = cnt[t];
-    for (int c = 0; c < c_end; ++c) {
-      const int g = cand[c * QPB + slot];
+    int c = 0;
+    for (;;) {
+      if (!__any_sync(0xffffffffu, c < c_end)) break;
+      // ---- fill ----
+      int ns = 0;
+      while (c < c_end && ns <= kSurvCap - kGroup) {
+        const int g = cand[c * QPB + slot];
+        ++c;
+        float4 X[DT];
 #pragma unroll
-      for (int i = 0; i < kGroup; ++i) {
-        const int jl = g * kGroup + i;
-        float d = 0.0f;
+        for (int d = 0; d < DT; ++d) X[d] = reinterpret_cast<const float4*>(tile + d * TP)[g];
 #pragma unroll
-        for (int dd = 0; dd < DT; ++dd) {
-          const float term = dist_term<NORM>(q[dd], tile[dd * TP + jl]);
-          d = (dd == 0) ? term : __fadd_rn(d, term);
-        }
-        const int j = j0 + jl;
-        if (d <= dkt && j < L2) {
-          const uint64_t key = make_key(d, static_cast<uint32_t>(j));
-          if (key < worst) {
-            int k = K - 1;
-            while (k > 0) {
-              const uint64_t prev = lists[static_cast<size_t>(k - 1) * QPB + slot];
-              if (prev <= key) break;
-              lists[static_cast<size_t>(k) * QPB + slot] = prev;
-              --k;
-            }
-            lists[static_cast<size_t>(k) * QPB + slot] = key;
-            worst = lists[static_cast<size_t>(K - 1) * QPB + slot];
-            if (worst != kEmptyKey) dkt = key_dist(worst);
+        for (int i = 0; i < kGroup; ++i) {
+          float dist = 0.0f;
+#pragma unroll
+          for (int d = 0; d < DT; ++d) {
+            const float xv = i == 0 ? X[d].x : (i == 1 ? X[d].y : (i == 2 ? X[d].z : X[d].w));
+            const float term = dist_term<NORM>(q[d], xv);
+            dist = (d == 0) ? term : __fadd_rn(dist, term);
+          }
+          const int j = j0 + g * kGroup + i;
+          if (dist <= dkt && j < L2) {
+            S[ns * THREADS] = make_key(dist, static_cast<uint32_t>(j));
+            ++ns;
           }
         }
       }
+      __syncwarp();
+      // ---- merge ----
+      if (ns > 0) {
+        // insertion sort of the survivors (ns is small)
+        for (int a2 = 1; a2 < ns; ++a2) {
+          const uint64_t key = S[a2 * THREADS];
+          int b2 = a2 - 1;
+          while (b2 >= 0) {
+            const uint64_t prev = S[b2 * THREADS];
+            if (prev <= key) break;
+            S[(b2 + 1) * THREADS] = prev;
+            --b2;
+          }
+          S[(b2 + 1) * THREADS] = key;
+        }
+        // r = how many survivors are among the K smallest of (list U survivors)
+        int r = 0;
+        while (r < ns && r < K && S[r * THREADS] < L[static_cast<size_t>(K - 1 - r) * QPB]) ++r;
+        // backward in-place merge of S[0..r) into L[0..K)
+        int i = K - 1 - r, jj = r - 1, o = K - 1;
+        while (jj >= 0) {
+          const uint64_t sv = S[jj * THREADS];
+          uint64_t lv = 0;
+          if (i >= 0) lv = L[static_cast<size_t>(i) * QPB];
+          if (i >= 0 && lv > sv) {
+            L[static_cast<size_t>(o) * QPB] = lv;
+            --i;
+          } else {
+            L[static_cast<size_t>(o) * QPB] = sv;
+            --jj;
+          }
+          --o;
+        }
+        const uint64_t worst = L[static_cast<size_t>(K - 1) * QPB];
+        if (worst != kEmptyKey) dkt = key_dist(worst);
+      }
+      __syncwarp();
     }
-    cnt[t] = 0;
     dk[t] = dkt;
-    if (worst != kEmptyKey) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
+    if (dkt < __int_as_float(0x7f800000)) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
   };
 
   // ---- main loop over p2 tiles ------------------------------------------------------------------
+  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(BCAP - kChunk) * CSTRIDE;
   for (int tile_i = 0; tile_i < num_tiles; ++tile_i) {
     const int stage = tile_i & 1;
     const int j0 = tile_i * TP;
@@ -272,34 +326,38 @@ knn_scan_kernel(const KnnScanParams prm) {
     const float* tile = tiles + static_cast<size_t>(stage) * ROWS * TP;
     mbar_wait(&bars[stage], (tile_i >> 1) & 1);
 
+    // software pipeline: the next group's rows are loaded while the current group is evaluated
+    float4 Xc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) Xc[r] = reinterpret_cast<const float4*>(tile + r * TP)[0];
+
     for (int g0 = 0; g0 < ngroups; g0 += kChunk) {
 #pragma unroll
       for (int c = 0; c < kChunk; ++c) {
         const int g = g0 + c;
-        float4 X[DT];
+        const int gn = min(g + 1, ngroups - 1);
+        float4 Xn[ROWS];
 #pragma unroll
-        for (int d = 0; d < DT; ++d)
-          X[d] = reinterpret_cast<const float4*>(tile + d * TP)[g];
-        float4 W = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EXP) W = reinterpret_cast<const float4*>(tile + DT * TP)[g];
+        for (int r = 0; r < ROWS; ++r) Xn[r] = reinterpret_cast<const float4*>(tile + r * TP)[gn];
 #pragma unroll
         for (int t = 0; t < Q; ++t) {
           float m;
           if (EXP) {
-            float2 s01 = make_float2(W.x, W.y), s23 = make_float2(W.z, W.w);
+            float2 s01 = make_float2(Xc[DT].x, Xc[DT].y), s23 = make_float2(Xc[DT].z, Xc[DT].w);
 #pragma unroll
             for (int d = 0; d < DT; ++d) {
-              s01 = __ffma2_rn(a2[t][d], make_float2(X[d].x, X[d].y), s01);
-              s23 = __ffma2_rn(a2[t][d], make_float2(X[d].z, X[d].w), s23);
+              const float2 ad = make_float2(a[t][d], a[t][d]);
+              s01 = __ffma2_rn(ad, make_float2(Xc[d].x, Xc[d].y), s01);
+              s23 = __ffma2_rn(ad, make_float2(Xc[d].z, Xc[d].w), s23);
             }
             m = fminf(fminf(s01.x, s01.y), fminf(s23.x, s23.y));
           } else {
             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
             for (int d = 0; d < DT; ++d) {
-              const float qd = a2[t][d].x;
-              const float t0 = dist_term<NORM>(qd, X[d].x), t1 = dist_term<NORM>(qd, X[d].y);
-              const float t2 = dist_term<NORM>(qd, X[d].z), t3 = dist_term<NORM>(qd, X[d].w);
+              const float qd = a[t][d];
+              const float t0 = dist_term<NORM>(qd, Xc[d].x), t1 = dist_term<NORM>(qd, Xc[d].y);
+              const float t2 = dist_term<NORM>(qd, Xc[d].z), t3 = dist_term<NORM>(qd, Xc[d].w);
               d0 = d == 0 ? t0 : __fadd_rn(d0, t0);
               d1 = d == 0 ? t1 : __fadd_rn(d1, t1);
               d2 = d == 0 ? t2 : __fadd_rn(d2, t2);
@@ -307,16 +365,19 @@ knn_scan_kernel(const KnnScanParams prm) {
             }
             m = fminf(fminf(d0, d1), fminf(d2, d3));
           }
-          if (m <= T[t]) {
-            cand[cnt[t] * QPB + t * THREADS + tid] = static_cast<unsigned short>(g);
-            ++cnt[t];
+          if (m <= T[t]) {  // predicated: one STS.U16 + one IADD
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(cw[t]), "h"(static_cast<unsigned short>(g)) : "memory");
+            cw[t] += CSTRIDE;
           }
         }
-      }
-      int mx = cnt[0];
 #pragma unroll
-      for (int t = 1; t < Q; ++t) mx = max(mx, cnt[t]);
-      if (mx > BCAP - kChunk) {
+        for (int r = 0; r < ROWS; ++r) Xc[r] = Xn[r];
+      }
+      // warp-converged overflow check: flush everything when ANY lane's buffer is nearly full
+      uint32_t mx = cw[0];
+#pragma unroll
+      for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (THREADS * 2u));
+      if (__any_sync(0xffffffffu, mx > cw_limit)) {
 #pragma unroll
         for (int t = 0; t < Q; ++t) flush(t, tile, j0);
       }
@@ -481,31 +542,46 @@ __global__ void knn_backward_kernel(const float* __restrict__ p1, const float* _
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-struct TiledCfg {
-  int Q, threads, TP, BCAP;
-};
-
-// which (D, norm) the tiled kernel is instantiated for
-inline bool tiled_supported(int64_t D, int norm) { return D >= 1 && D <= 4 && (norm == 1 || norm == 2); }
-
 constexpr int kTiledThreads = 128;
-constexpr int kTiledQ = 4;
 constexpr size_t kMaxSmem = 227 * 1024;
-
-template <int DT, int NORM, bool EXP>
-size_t tiled_smem(int TP, int K, int BCAP) {
-  return KnnSmem<DT, NORM, EXP, kTiledQ, kTiledThreads>::total(TP, K, BCAP);
-}
+constexpr int kBufCap = 16;
 
 inline int pad_points(int64_t P2) {
   return static_cast<int>((P2 + kPadPoints - 1) / kPadPoints * kPadPoints);
 }
 
+// Queries per thread by K: the per-CTA top-K lists (K * Q*128 * 8 B) stay <= 64 KB so that two
+// CTAs share an SM; beyond K = 64 a single CTA per SM holds up to K = 128.
+inline int tiled_q_for(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
+inline bool tiled_k_ok(int K) { return K <= 128; }
+
+template <int DT, int NORM, bool EXP, int Q>
+int launch_scan(const KnnScanParams& base, int N, cudaStream_t st) {
+  using SM = KnnSmem<DT, NORM, EXP, Q, kTiledThreads>;
+  constexpr int QPB = Q * kTiledThreads;
+  KnnScanParams prm = base;
+  prm.BCAP = kBufCap;
+  // tile size: largest power of two that leaves room for two CTAs per SM (one when K is large)
+  const size_t budget = (SM::lists_bytes(prm.K) > 64 * 1024) ? kMaxSmem : 112 * 1024;
+  int TP = 1024;
+  while (TP > kPadPoints && SM::total(TP, prm.K, prm.BCAP) > budget) TP /= 2;
+  if (TP > prm.P2pad) TP = prm.P2pad;
+  prm.TP = TP;
+  const size_t smem = SM::total(TP, prm.K, prm.BCAP);
+  if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: K too large for the tiled kernel");
+  auto kern = knn_scan_kernel<DT, NORM, EXP, Q, kTiledThreads>;
+  POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(static_cast<unsigned>(ceil_div(prm.P1, QPB)), N);
+  profile_begin("knn_scan", st);
+  kern<<<grid, kTiledThreads, smem, st>>>(prm);
+  profile_end("knn_scan", st);
+  POPS_LAUNCH_OK("knn_scan_kernel");
+  return POPS_OK;
+}
+
 template <int DT, int NORM, bool EXP>
 int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
                  int P1, int P2, int K, int64_t* idx, float* dists, void* ws, cudaStream_t st) {
-  constexpr int ROWS = DT + (EXP ? 1 : 0);
-  constexpr int QPB = kTiledQ * kTiledThreads;
   const int P2pad = pad_points(P2);
   unsigned* maxabs = reinterpret_cast<unsigned*>(ws);
   float* soa = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up(size_t(N) * 4, 256));
@@ -523,25 +599,12 @@ int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const in
   KnnScanParams prm;
   prm.p1 = p1; prm.soa = soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = maxabs;
   prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = P2pad; prm.K = K;
-  prm.BCAP = 16;
-  // tile size: as large as fits next to the lists, capped, multiple of kPadPoints
-  int TP = 1024;
-  while (TP > kPadPoints && tiled_smem<DT, NORM, EXP>(TP, K, prm.BCAP) > 110 * 1024) TP /= 2;
-  if (TP > P2pad) TP = P2pad;
-  prm.TP = TP;
-  const size_t smem = tiled_smem<DT, NORM, EXP>(TP, K, prm.BCAP);
-  auto kern = knn_scan_kernel<DT, NORM, EXP, kTiledQ, kTiledThreads>;
-  POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid(static_cast<unsigned>(ceil_div(P1, QPB)), N);
-  kern<<<grid, kTiledThreads, smem, st>>>(prm);
-  POPS_LAUNCH_OK("knn_scan_kernel");
-  (void)ROWS;
-  return POPS_OK;
+  prm.TP = 0; prm.BCAP = kBufCap;
+  const int q = tiled_q_for(K);
+  if (q == 4) return launch_scan<DT, NORM, EXP, 4>(prm, N, st);
+  if (EXP && q == 2) return launch_scan<DT, NORM, EXP, EXP ? 2 : 1>(prm, N, st);
+  return launch_scan<DT, NORM, EXP, 1>(prm, N, st);
 }
-
-// K small enough that TP >= kPadPoints tile + lists fit in shared memory
-template <int DT, int NORM, bool EXP>
-bool tiled_fits(int K) { return tiled_smem<DT, NORM, EXP>(kPadPoints * 8, K, 16) <= kMaxSmem; }
 
 constexpr int kGenericThreads = 128;
 
@@ -603,7 +666,7 @@ extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64
   }
   const int n = int(N), p1n = int(P1), p2n = int(P2), k = int(K);
 #define POPS_TILED(DT, NORM, EXP)                                                             \
-  if (D == DT && norm == NORM && tiled_fits<DT, NORM, EXP>(k)) \
+  if (D == DT && norm == NORM && tiled_k_ok(k)) \
     return launch_tiled<DT, NORM, EXP>(p1, p2, lengths1, lengths2, n, p1n, p2n, k, idx, dists, workspace, st);
   POPS_TILED(3, 2, true)
   POPS_TILED(3, 1, false)
@@ -658,6 +721,7 @@ extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const 
   POPS_CHECK_ARG(p2 && idx && grad_dists, "null pointer argument");
   const int threads = 256;
   const int blocks = int(std::min<int64_t>(ceil_div(int64_t(total), threads), int64_t(num_sms()) * 16));
+  profile_begin("knn_backward", st);
   if (norm == 2)
     knn_backward_kernel<2><<<blocks, threads, 0, st>>>(p1, p2, lengths1, lengths2, idx, grad_dists,
                                                        int(N), int(P1), int(P2), int(D), int(K),
@@ -666,6 +730,7 @@ extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const 
     knn_backward_kernel<1><<<blocks, threads, 0, st>>>(p1, p2, lengths1, lengths2, idx, grad_dists,
                                                        int(N), int(P1), int(P2), int(D), int(K),
                                                        grad_p1, grad_p2);
+  profile_end("knn_backward", st);
   POPS_LAUNCH_OK("knn_backward_kernel");
   return POPS_OK;
 }

@@ -16,14 +16,19 @@ def test_chamfer_all_variants_vs_golden(golden):
     for vi, v in enumerate(chamfer_variants(golden)):
         flat, grads = run_chamfer_variant(chamfer_distance, g, v, DEV)
         assert len(flat) == int(g.a(f"v{vi}.nout")), v
+        n_loss = 2 if (v["pr"] is None and not v["sd"]) else 1
         for i, t in enumerate(flat):
-            assert torch.allclose(t.detach().cpu(), g.t(f"v{vi}.out{i}"), rtol=1e-5, atol=1e-7), (v, i)
+            # distance terms: 1e-5 relative.  cosine terms are 1 - cos: one ulp of cos (6e-8) is an
+            # ABSOLUTE error of the result, so they get atol 1e-6 on O(1) values.
+            atol = 1e-7 if i < n_loss else 1e-6
+            assert torch.allclose(t.detach().cpu(), g.t(f"v{vi}.out{i}"), rtol=1e-5, atol=atol), (v, i)
         for n, gr in grads.items():
             want = g.t(f"v{vi}.g_{n}")
             if want.numel() == 0:
                 assert gr.numel() == 0 or not gr.any(), (v, n)
             else:
-                assert torch.allclose(gr.cpu(), want, rtol=1e-5, atol=1e-6), (v, n)
+                # float atomics reorder the scatter-add: 1e-5 relative to the gradient scale
+                assert torch.allclose(gr.cpu(), want, rtol=1e-5, atol=1e-5 * float(want.abs().max())), (v, n)
 
 
 def test_chamfer_pointclouds_input(golden):
@@ -73,4 +78,4 @@ def test_chamfer_config2_vs_oracle(oracle):
     for a, b in zip(g_out, o_out):
         assert torch.allclose(a.detach().cpu(), b.detach(), rtol=1e-5, atol=1e-8)
     for a, b in zip(g_grads, o_grads):
-        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-8)
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-5 * float(b.abs().max()))
