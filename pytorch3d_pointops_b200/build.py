@@ -28,6 +28,9 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+    # never contract a*b+c: the reference arithmetic is unfused and ptxas was seen
+    # fusing mul.rn.f32x2 + add.rn.f32x2 into FFMA2.  Explicit fmaf()/__ffma2_rn() are unaffected.
+    "-fmad=false",
     "-Xptxas", "-v",
 ]
 

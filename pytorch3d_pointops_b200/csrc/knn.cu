@@ -107,44 +107,87 @@ struct KnnScanParams {
   int64_t* idx;
   float* dists;
   int P1, P2, P2pad, K;
-  int TP;    // tile points (multiple of kPadPoints)
-  int BCAP;  // candidate buffer capacity in groups (> kChunk)
 };
 
-template <int DT, int NORM, bool EXP, int Q, int THREADS>
+constexpr int kBufCap = 16;  // candidate buffer capacity (groups) per query
+
+// Shared-memory carve-up.  RS = floats per tile row (compile time, so tile loads in the hot loop
+// are immediate-offset LDS.128); a tile holds RS points of every row, two stages.
+template <int DT, bool EXP, int Q, int THREADS>
 struct KnnSmem {
   static constexpr int ROWS = DT + (EXP ? 1 : 0);
   static constexpr int QPB = Q * THREADS;
-  // offsets in bytes
-  static __host__ __device__ size_t tiles_off() { return 64; }
-  static __host__ __device__ size_t tiles_bytes(int TP) { return size_t(2) * ROWS * TP * 4; }
-  static __host__ __device__ size_t lists_off(int TP) { return tiles_off() + tiles_bytes(TP); }
+  static constexpr int RS = (Q >= 2) ? 1024 : 512;
+  static constexpr size_t tiles_off = 64;
+  static constexpr size_t tiles_bytes = size_t(2) * ROWS * RS * 4;
+  static constexpr size_t lists_off = tiles_off + tiles_bytes;
   static __host__ __device__ size_t lists_bytes(int K) { return size_t(K) * QPB * 8; }
-  static __host__ __device__ size_t qs_off(int TP, int K) { return lists_off(TP) + lists_bytes(K); }
-  static __host__ __device__ size_t qs_bytes() { return size_t(DT) * QPB * 4; }
-  static __host__ __device__ size_t cand_off(int TP, int K) { return qs_off(TP, K) + qs_bytes(); }
-  static __host__ __device__ size_t cand_bytes(int BCAP) { return size_t(BCAP) * QPB * 2; }
-  static __host__ __device__ size_t surv_off(int TP, int K, int BCAP) {
-    return (cand_off(TP, K) + cand_bytes(BCAP) + 7) / 8 * 8;
-  }
-  static __host__ __device__ size_t surv_bytes() { return size_t(kSurvCap) * THREADS * 8; }
-  static __host__ __device__ size_t total(int TP, int K, int BCAP) {
-    return surv_off(TP, K, BCAP) + surv_bytes();
-  }
+  static __host__ __device__ size_t qs_off(int K) { return lists_off + lists_bytes(K); }
+  static constexpr size_t qs_bytes = size_t(DT) * QPB * 4;
+  static __host__ __device__ size_t cand_off(int K) { return qs_off(K) + qs_bytes; }
+  static constexpr size_t cand_bytes = size_t(kBufCap) * QPB * 2;
+  static __host__ __device__ size_t surv_off(int K) { return (cand_off(K) + cand_bytes + 7) / 8 * 8; }
+  static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
+  static __host__ __device__ size_t total(int K) { return surv_off(K) + surv_bytes; }
 };
 
-template <int DT, int NORM, bool EXP, int Q, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// ---- register sorting networks on 64-bit keys ------------------------------------------------
+__device__ __forceinline__ void ce64(uint64_t& lo, uint64_t& hi) {  // lo <- min, hi <- max
+  const bool sw = hi < lo;
+  const uint64_t a = sw ? hi : lo, b = sw ? lo : hi;
+  lo = a;
+  hi = b;
+}
+
+// Batcher odd-even merge sort of 16 keys: 63 compare-exchanges (pairs generated offline and
+// verified with the 0-1 principle); constexpr tables so that every index resolves statically.
+constexpr int kSort16N = 63;
+__device__ constexpr unsigned char kSort16A[kSort16N] = {0,2,4,6,8,10,12,14,0,1,4,5,8,9,12,13,1,5,9,13,0,1,2,3,8,9,10,11,2,3,10,11,1,3,5,9,11,13,0,1,2,3,4,5,6,7,4,5,6,7,2,3,6,7,10,11,1,3,5,7,9,11,13};
+__device__ constexpr unsigned char kSort16B[kSort16N] = {1,3,5,7,9,11,13,15,2,3,6,7,10,11,14,15,2,6,10,14,4,5,6,7,12,13,14,15,4,5,12,13,2,4,6,10,12,14,8,9,10,11,12,13,14,15,8,9,10,11,4,5,8,9,12,13,2,4,6,8,10,12,14};
+__device__ __forceinline__ void sort16(uint64_t (&v)[16]) {
+#pragma unroll
+  for (int e = 0; e < kSort16N; ++e) ce64(v[kSort16A[e]], v[kSort16B[e]]);
+}
+
+// v is bitonic -> ascending
+template <int N>
+__device__ __forceinline__ void bitonic_merge(uint64_t (&v)[N]) {
+#pragma unroll
+  for (int k = N / 2; k >= 1; k /= 2) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if ((i & k) == 0) ce64(v[i], v[i + k]);
+    }
+  }
+}
+
+// sorted insertion of one key into the ascending register list (branch-free, all compares
+// against the OLD list, so the KT steps are independent)
+template <int KT>
+__device__ __forceinline__ void insert_network(uint64_t (&Lr)[KT], uint64_t key) {
+  bool lt[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) lt[k] = key < Lr[k];
+#pragma unroll
+  for (int k = KT - 1; k >= 1; --k) Lr[k] = lt[k - 1] ? Lr[k - 1] : (lt[k] ? key : Lr[k]);
+  Lr[0] = lt[0] ? key : Lr[0];
+}
+
+static_assert(kSurvCap == 16, "sort16 assumes 16 survivor slots");
+
+template <int DT, int NORM, bool EXP, int Q, int THREADS, int KT>
+__global__ void __launch_bounds__(THREADS, 2)
 knn_scan_kernel(const KnnScanParams prm) {
-  using SM = KnnSmem<DT, NORM, EXP, Q, THREADS>;
+  using SM = KnnSmem<DT, EXP, Q, THREADS>;
   constexpr int ROWS = SM::ROWS;
   constexpr int QPB = SM::QPB;
+  constexpr int RS = SM::RS;
   extern __shared__ __align__(128) unsigned char smem[];
 
   const int n = blockIdx.y;
   const int q_base = blockIdx.x * QPB;
   const int tid = threadIdx.x;
-  const int K = prm.K, TP = prm.TP, BCAP = prm.BCAP, P2pad = prm.P2pad;
+  const int K = prm.K, P2pad = prm.P2pad;
   int64_t L1l = prm.len1[n], L2l = prm.len2[n];
   const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
   const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
@@ -163,25 +206,25 @@ knn_scan_kernel(const KnnScanParams prm) {
   }
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  float* tiles = reinterpret_cast<float*>(smem + SM::tiles_off());
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + SM::lists_off(TP));
-  float* qs = reinterpret_cast<float*>(smem + SM::qs_off(TP, K));
-  unsigned short* cand = reinterpret_cast<unsigned short*>(smem + SM::cand_off(TP, K));
-  uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off(TP, K, BCAP));
+  float* tiles = reinterpret_cast<float*>(smem + SM::tiles_off);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + SM::lists_off);
+  float* qs = reinterpret_cast<float*>(smem + SM::qs_off(K));
+  unsigned short* cand = reinterpret_cast<unsigned short*>(smem + SM::cand_off(K));
+  uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off(K));
 
   const int L2pad = (L2 + kPadPoints - 1) / kPadPoints * kPadPoints;  // <= P2pad
-  const int num_tiles = (L2pad + TP - 1) / TP;
+  const int num_tiles = (L2pad + RS - 1) / RS;
   const float* soa_n = prm.soa + static_cast<size_t>(n) * ROWS * P2pad;
 
   auto issue_tile = [&](int tile) {
     const int stage = tile & 1;
-    const int j0 = tile * TP;
-    const int pts = min(TP, L2pad - j0);
+    const int j0 = tile * RS;
+    const int pts = min(RS, L2pad - j0);
     const uint32_t bytes = static_cast<uint32_t>(pts) * 4u;
     mbar_arrive_expect_tx(&bars[stage], bytes * ROWS);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
-      tma_bulk_g2s(tiles + (static_cast<size_t>(stage) * ROWS + r) * TP,
+      tma_bulk_g2s(tiles + (static_cast<size_t>(stage) * ROWS + r) * RS,
                    soa_n + static_cast<size_t>(r) * P2pad + j0, bytes, &bars[stage]);
   };
 
@@ -201,6 +244,7 @@ knn_scan_kernel(const KnnScanParams prm) {
   // E >= 130.2 * 2^-24 * M^2 bounds |filter - reference| (DESIGN.md "filter error bound").
   const float E = fmaf(M * M, 1.52587890625e-05f /* 2^-16 */, 1e-37f);
   constexpr uint32_t CSTRIDE = QPB * 2;  // bytes between consecutive entries of one candidate buffer
+  const float INF = __int_as_float(0x7f800000);
   float a[Q][DT];   // EXP: -2 q_d (FFMA2 takes it as a broadcast scalar operand);  else q_d
   float qq[Q];
   float T[Q];       // filter threshold
@@ -221,8 +265,8 @@ knn_scan_kernel(const KnnScanParams prm) {
       a[t][d] = EXP ? -2.0f * q : q;
     }
     qq[t] = s;
-    dk[t] = valid ? __int_as_float(0x7f800000) : -1.0f;
-    T[t] = valid ? (EXP ? FLT_MAX : __int_as_float(0x7f800000)) : -__int_as_float(0x7f800000);
+    dk[t] = valid ? INF : -1.0f;
+    T[t] = valid ? (EXP ? FLT_MAX : INF) : -INF;
     cw[t] = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
     for (int k = 0; k < K; ++k) lists[static_cast<size_t>(k) * QPB + slot] = kEmptyKey;
   }
@@ -230,11 +274,12 @@ knn_scan_kernel(const KnnScanParams prm) {
   // ---- flush: drain one query's candidate buffer -------------------------------------------------
   // Called warp-converged (every lane flushes together) and kept converged inside: rare events
   // never sit inside a dense loop.
-  //   fill   per buffered group, all 4 points get the exact unfused distance (branch-free); points
-  //          with d <= dk are appended as 64-bit keys to the lane's survivor column (predicated);
-  //   merge  the (few) survivors are sorted, the number r that belongs to the K smallest is
-  //          counted, and a backward in-place merge shifts the sorted list -- cost ~ r + shifted
-  //          elements, independent of where the survivors land.
+  //   fill   per buffered group, all 4 points get the exact unfused distance (branch-free, packed
+  //          f32x2 add/mul -- IEEE, never fused); points with d <= dk are appended as 64-bit keys
+  //          to the lane's survivor column (predicated);
+  //   merge  KT > 0: the list is pulled into registers; few survivors -> branch-free insertion
+  //          network per survivor, many -> sort network + bitonic merge.  KT == 0 (any K): sorted
+  //          survivors are merged backward in place in shared memory.
   auto flush = [&](int t, const float* tile, int j0) {
     const int slot = t * THREADS + tid;
     const uint32_t base = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
@@ -257,88 +302,140 @@ knn_scan_kernel(const KnnScanParams prm) {
         ++c;
         float4 X[DT];
 #pragma unroll
-        for (int d = 0; d < DT; ++d) X[d] = reinterpret_cast<const float4*>(tile + d * TP)[g];
-#pragma unroll
-        for (int i = 0; i < kGroup; ++i) {
-          float dist = 0.0f;
+        for (int d = 0; d < DT; ++d) X[d] = reinterpret_cast<const float4*>(tile + d * RS)[g];
+        float dist[kGroup];
+        if (NORM == 2) {
+          float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int d = 0; d < DT; ++d) {
-            const float xv = i == 0 ? X[d].x : (i == 1 ? X[d].y : (i == 2 ? X[d].z : X[d].w));
-            const float term = dist_term<NORM>(q[d], xv);
-            dist = (d == 0) ? term : __fadd_rn(dist, term);
+            const float2 qd = make_float2(q[d], q[d]);
+            const float2 d01 = __fadd2_rn(qd, make_float2(-X[d].x, -X[d].y));
+            const float2 d23 = __fadd2_rn(qd, make_float2(-X[d].z, -X[d].w));
+            const float2 t01 = __fmul2_rn(d01, d01), t23 = __fmul2_rn(d23, d23);
+            // scalar adds on purpose: ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+            // (even with -fmad=false), which would break bit parity with the unfused reference
+            acc01 = d == 0 ? t01 : make_float2(__fadd_rn(acc01.x, t01.x), __fadd_rn(acc01.y, t01.y));
+            acc23 = d == 0 ? t23 : make_float2(__fadd_rn(acc23.x, t23.x), __fadd_rn(acc23.y, t23.y));
           }
-          const int j = j0 + g * kGroup + i;
-          if (dist <= dkt && j < L2) {
-            S[ns * THREADS] = make_key(dist, static_cast<uint32_t>(j));
+          dist[0] = acc01.x; dist[1] = acc01.y; dist[2] = acc23.x; dist[3] = acc23.y;
+        } else {
+#pragma unroll
+          for (int i = 0; i < kGroup; ++i) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int d = 0; d < DT; ++d) {
+              const float xv = i == 0 ? X[d].x : (i == 1 ? X[d].y : (i == 2 ? X[d].z : X[d].w));
+              const float term = dist_term<NORM>(q[d], xv);
+              acc = (d == 0) ? term : __fadd_rn(acc, term);
+            }
+            dist[i] = acc;
+          }
+        }
+        const int jg = j0 + g * kGroup;
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i) {
+          if (dist[i] <= dkt && jg + i < L2) {
+            S[ns * THREADS] = make_key(dist[i], static_cast<uint32_t>(jg + i));
             ++ns;
           }
         }
       }
       __syncwarp();
       // ---- merge ----
-      if (ns > 0) {
-        // insertion sort of the survivors (ns is small)
-        for (int a2 = 1; a2 < ns; ++a2) {
-          const uint64_t key = S[a2 * THREADS];
-          int b2 = a2 - 1;
-          while (b2 >= 0) {
-            const uint64_t prev = S[b2 * THREADS];
-            if (prev <= key) break;
-            S[(b2 + 1) * THREADS] = prev;
-            --b2;
-          }
-          S[(b2 + 1) * THREADS] = key;
-        }
-        // r = how many survivors are among the K smallest of (list U survivors)
-        int r = 0;
-        while (r < ns && r < K && S[r * THREADS] < L[static_cast<size_t>(K - 1 - r) * QPB]) ++r;
-        // backward in-place merge of S[0..r) into L[0..K)
-        int i = K - 1 - r, jj = r - 1, o = K - 1;
-        while (jj >= 0) {
-          const uint64_t sv = S[jj * THREADS];
-          uint64_t lv = 0;
-          if (i >= 0) lv = L[static_cast<size_t>(i) * QPB];
-          if (i >= 0 && lv > sv) {
-            L[static_cast<size_t>(o) * QPB] = lv;
-            --i;
+      const int ns_max = __reduce_max_sync(0xffffffffu, ns);
+      if (ns_max > 0) {
+        if (KT > 0) {
+          constexpr int KR = KT > 0 ? KT : 1;
+          uint64_t Lr[KR];
+#pragma unroll
+          for (int k = 0; k < KR; ++k) Lr[k] = (k < K) ? L[static_cast<size_t>(k) * QPB] : kEmptyKey;
+          if (ns_max <= 5 || KR < 4) {
+            for (int s2 = 0; s2 < ns_max; ++s2) {
+              const uint64_t key = (s2 < ns) ? S[s2 * THREADS] : kEmptyKey;
+              insert_network<KR>(Lr, key);
+            }
           } else {
-            L[static_cast<size_t>(o) * QPB] = sv;
-            --jj;
+            uint64_t Sr[kSurvCap];
+#pragma unroll
+            for (int s2 = 0; s2 < kSurvCap; ++s2) Sr[s2] = (s2 < ns) ? S[s2 * THREADS] : kEmptyKey;
+            sort16(Sr);
+            // K smallest of (Lr U Sr): C[i] = min(Lr[i], Sr[KR-1-i]) is bitonic, then merge
+#pragma unroll
+            for (int i = 0; i < KR; ++i) {
+              const int si = KR - 1 - i;
+              if (si < kSurvCap) Lr[i] = (Sr[si] < Lr[i]) ? Sr[si] : Lr[i];
+            }
+            bitonic_merge<KR>(Lr);
           }
-          --o;
+#pragma unroll
+          for (int k = 0; k < KR; ++k)
+            if (k < K) L[static_cast<size_t>(k) * QPB] = Lr[k];
+          const uint64_t worst = L[static_cast<size_t>(K - 1) * QPB];  // re-read: K is a runtime index
+          if (worst != kEmptyKey) dkt = key_dist(worst);
+        } else if (ns > 0) {
+          for (int a2 = 1; a2 < ns; ++a2) {  // insertion sort of the survivors
+            const uint64_t key = S[a2 * THREADS];
+            int b2 = a2 - 1;
+            while (b2 >= 0) {
+              const uint64_t prev = S[b2 * THREADS];
+              if (prev <= key) break;
+              S[(b2 + 1) * THREADS] = prev;
+              --b2;
+            }
+            S[(b2 + 1) * THREADS] = key;
+          }
+          int r = 0;  // survivors that belong to the K smallest of (list U survivors)
+          while (r < ns && r < K && S[r * THREADS] < L[static_cast<size_t>(K - 1 - r) * QPB]) ++r;
+          int i = K - 1 - r, jj = r - 1, o = K - 1;  // backward in-place merge
+          while (jj >= 0) {
+            const uint64_t sv = S[jj * THREADS];
+            uint64_t lv = 0;
+            if (i >= 0) lv = L[static_cast<size_t>(i) * QPB];
+            if (i >= 0 && lv > sv) {
+              L[static_cast<size_t>(o) * QPB] = lv;
+              --i;
+            } else {
+              L[static_cast<size_t>(o) * QPB] = sv;
+              --jj;
+            }
+            --o;
+          }
+          const uint64_t worst = L[static_cast<size_t>(K - 1) * QPB];
+          if (worst != kEmptyKey) dkt = key_dist(worst);
         }
-        const uint64_t worst = L[static_cast<size_t>(K - 1) * QPB];
-        if (worst != kEmptyKey) dkt = key_dist(worst);
       }
       __syncwarp();
     }
     dk[t] = dkt;
-    if (dkt < __int_as_float(0x7f800000)) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
+    if (dkt < INF) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
   };
 
   // ---- main loop over p2 tiles ------------------------------------------------------------------
-  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(BCAP - kChunk) * CSTRIDE;
+  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(kBufCap - kChunk) * CSTRIDE;
   for (int tile_i = 0; tile_i < num_tiles; ++tile_i) {
     const int stage = tile_i & 1;
-    const int j0 = tile_i * TP;
-    const int pts = min(TP, L2pad - j0);
+    const int j0 = tile_i * RS;
+    const int pts = min(RS, L2pad - j0);
     const int ngroups = pts / kGroup;  // multiple of kChunk
-    const float* tile = tiles + static_cast<size_t>(stage) * ROWS * TP;
+    const float* tile = tiles + static_cast<size_t>(stage) * ROWS * RS;
     mbar_wait(&bars[stage], (tile_i >> 1) & 1);
 
     // software pipeline: the next group's rows are loaded while the current group is evaluated
+    // (the last prefetch of a tile reads one group past the valid data: in-bounds shared memory,
+    // never used)
+    const float4* tp = reinterpret_cast<const float4*>(tile);
     float4 Xc[ROWS];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) Xc[r] = reinterpret_cast<const float4*>(tile + r * TP)[0];
+    for (int r = 0; r < ROWS; ++r) Xc[r] = tp[r * (RS / 4)];
 
     for (int g0 = 0; g0 < ngroups; g0 += kChunk) {
 #pragma unroll
       for (int c = 0; c < kChunk; ++c) {
         const int g = g0 + c;
-        const int gn = min(g + 1, ngroups - 1);
         float4 Xn[ROWS];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) Xn[r] = reinterpret_cast<const float4*>(tile + r * TP)[gn];
+        for (int r = 0; r < ROWS; ++r) Xn[r] = tp[r * (RS / 4) + g + 1];
+        const unsigned short g16 = static_cast<unsigned short>(g);
 #pragma unroll
         for (int t = 0; t < Q; ++t) {
           float m;
@@ -366,7 +463,7 @@ knn_scan_kernel(const KnnScanParams prm) {
             m = fminf(fminf(d0, d1), fminf(d2, d3));
           }
           if (m <= T[t]) {  // predicated: one STS.U16 + one IADD
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(cw[t]), "h"(static_cast<unsigned short>(g)) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(cw[t]), "h"(g16) : "memory");
             cw[t] += CSTRIDE;
           }
         }
@@ -544,7 +641,6 @@ namespace {
 
 constexpr int kTiledThreads = 128;
 constexpr size_t kMaxSmem = 227 * 1024;
-constexpr int kBufCap = 16;
 
 inline int pad_points(int64_t P2) {
   return static_cast<int>((P2 + kPadPoints - 1) / kPadPoints * kPadPoints);
@@ -555,21 +651,13 @@ inline int pad_points(int64_t P2) {
 inline int tiled_q_for(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
 inline bool tiled_k_ok(int K) { return K <= 128; }
 
-template <int DT, int NORM, bool EXP, int Q>
-int launch_scan(const KnnScanParams& base, int N, cudaStream_t st) {
-  using SM = KnnSmem<DT, NORM, EXP, Q, kTiledThreads>;
+template <int DT, int NORM, bool EXP, int Q, int KT>
+int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
+  using SM = KnnSmem<DT, EXP, Q, kTiledThreads>;
   constexpr int QPB = Q * kTiledThreads;
-  KnnScanParams prm = base;
-  prm.BCAP = kBufCap;
-  // tile size: largest power of two that leaves room for two CTAs per SM (one when K is large)
-  const size_t budget = (SM::lists_bytes(prm.K) > 64 * 1024) ? kMaxSmem : 112 * 1024;
-  int TP = 1024;
-  while (TP > kPadPoints && SM::total(TP, prm.K, prm.BCAP) > budget) TP /= 2;
-  if (TP > prm.P2pad) TP = prm.P2pad;
-  prm.TP = TP;
-  const size_t smem = SM::total(TP, prm.K, prm.BCAP);
+  const size_t smem = SM::total(prm.K);
   if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: K too large for the tiled kernel");
-  auto kern = knn_scan_kernel<DT, NORM, EXP, Q, kTiledThreads>;
+  auto kern = knn_scan_kernel<DT, NORM, EXP, Q, kTiledThreads, KT>;
   POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(ceil_div(prm.P1, QPB)), N);
   profile_begin("knn_scan", st);
@@ -599,11 +687,16 @@ int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const in
   KnnScanParams prm;
   prm.p1 = p1; prm.soa = soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = maxabs;
   prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = P2pad; prm.K = K;
-  prm.TP = 0; prm.BCAP = kBufCap;
-  const int q = tiled_q_for(K);
-  if (q == 4) return launch_scan<DT, NORM, EXP, 4>(prm, N, st);
-  if (EXP && q == 2) return launch_scan<DT, NORM, EXP, EXP ? 2 : 1>(prm, N, st);
-  return launch_scan<DT, NORM, EXP, 1>(prm, N, st);
+  if (EXP) {
+    // register-merge buckets for the headline kernel (D = 3, L2): KT = next power of two >= K
+    if (K == 1) return launch_scan<DT, NORM, EXP, 4, EXP ? 1 : 0>(prm, N, st);
+    if (K <= 4) return launch_scan<DT, NORM, EXP, 4, EXP ? 4 : 0>(prm, N, st);
+    if (K <= 16) return launch_scan<DT, NORM, EXP, 4, EXP ? 16 : 0>(prm, N, st);
+    if (K <= 32) return launch_scan<DT, NORM, EXP, EXP ? 2 : 1, EXP ? 32 : 0>(prm, N, st);
+    return launch_scan<DT, NORM, EXP, 1, 0>(prm, N, st);
+  }
+  if (tiled_q_for(K) == 4) return launch_scan<DT, NORM, EXP, 4, 0>(prm, N, st);
+  return launch_scan<DT, NORM, EXP, 1, 0>(prm, N, st);
 }
 
 constexpr int kGenericThreads = 128;

@@ -62,6 +62,31 @@ def test_sass_is_blackwell_native():
     assert "FFMA2" in out, "packed FP32 FMA missing from SASS"
 
 
+def test_exact_kernels_have_no_fused_multiply_add():
+    """Kernels that compute the reference's unfused distance must contain no FFMA/FFMA2 except
+    where a fused filter is intended (the D=3 L2 scan) -- guards against compiler contraction
+    (ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false)."""
+    import shutil
+    import subprocess
+
+    from pytorch3d_pointops_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", _lib.lib_path()], capture_output=True, text=True).stdout
+    fn, bad = None, []
+    for line in out.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif fn and re.search(r"\bFFMA2?\b", line):
+            exact = ("knn_scan_kernelILi" in fn and "ELb0E" in fn) or "knn_generic_kernel" in fn \
+                or "ball_query_generic" in fn or "fps_generic" in fn or "knn_backward" in fn
+            if exact:
+                bad.append(fn)
+    assert not bad, sorted(set(bad))
+
+
 def test_no_cpu_fallback():
     """CPU tensors are rejected loudly: the product has no CPU path."""
     import torch
