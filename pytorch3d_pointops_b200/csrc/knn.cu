@@ -24,6 +24,7 @@
 //   generic     any D / any K fallback: thread per query, exact distance, list in shared or
 //               global memory.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -111,20 +112,18 @@ struct KnnScanParams {
 
 constexpr int kBufCap = 16;  // candidate buffer capacity (groups) per query
 
-// Shared-memory carve-up.  RS = floats per tile row (compile time, so tile loads in the hot loop
-// are immediate-offset LDS.128); a tile holds RS points of every row, two stages.
-template <int DT, bool EXP, int Q, int THREADS>
+// Shared-memory carve-up.  RS = points per tile row (compile time, so tile loads in the hot loop
+// are immediate-offset LDS.128).  ONE tile stage: the TMA refill of a CTA overlaps with the other
+// resident CTA's compute; a single large tile halves the number of forced end-of-tile flushes.
+template <int DT, bool EXP, int Q, int THREADS, int RS>
 struct KnnSmem {
   static constexpr int ROWS = DT + (EXP ? 1 : 0);
   static constexpr int QPB = Q * THREADS;
-  static constexpr int RS = (Q >= 2) ? 1024 : 512;
   static constexpr size_t tiles_off = 64;
-  static constexpr size_t tiles_bytes = size_t(2) * ROWS * RS * 4;
+  static constexpr size_t tiles_bytes = size_t(ROWS) * RS * 4 + 64;  // +64: the prefetch over-read
   static constexpr size_t lists_off = tiles_off + tiles_bytes;
   static __host__ __device__ size_t lists_bytes(int K) { return size_t(K) * QPB * 8; }
-  static __host__ __device__ size_t qs_off(int K) { return lists_off + lists_bytes(K); }
-  static constexpr size_t qs_bytes = size_t(DT) * QPB * 4;
-  static __host__ __device__ size_t cand_off(int K) { return qs_off(K) + qs_bytes; }
+  static __host__ __device__ size_t cand_off(int K) { return lists_off + lists_bytes(K); }
   static constexpr size_t cand_bytes = size_t(kBufCap) * QPB * 2;
   static __host__ __device__ size_t surv_off(int K) { return (cand_off(K) + cand_bytes + 7) / 8 * 8; }
   static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
@@ -175,13 +174,12 @@ __device__ __forceinline__ void insert_network(uint64_t (&Lr)[KT], uint64_t key)
 
 static_assert(kSurvCap == 16, "sort16 assumes 16 survivor slots");
 
-template <int DT, int NORM, bool EXP, int Q, int THREADS, int KT>
-__global__ void __launch_bounds__(THREADS, 2)
+template <int DT, int NORM, bool EXP, int Q, int THREADS, int KT, int RS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 192 ? 2 : 1))
 knn_scan_kernel(const KnnScanParams prm) {
-  using SM = KnnSmem<DT, EXP, Q, THREADS>;
+  using SM = KnnSmem<DT, EXP, Q, THREADS, RS>;
   constexpr int ROWS = SM::ROWS;
   constexpr int QPB = SM::QPB;
-  constexpr int RS = SM::RS;
   extern __shared__ __align__(128) unsigned char smem[];
 
   const int n = blockIdx.y;
@@ -208,7 +206,6 @@ knn_scan_kernel(const KnnScanParams prm) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   float* tiles = reinterpret_cast<float*>(smem + SM::tiles_off);
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + SM::lists_off);
-  float* qs = reinterpret_cast<float*>(smem + SM::qs_off(K));
   unsigned short* cand = reinterpret_cast<unsigned short*>(smem + SM::cand_off(K));
   uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off(K));
 
@@ -217,27 +214,22 @@ knn_scan_kernel(const KnnScanParams prm) {
   const float* soa_n = prm.soa + static_cast<size_t>(n) * ROWS * P2pad;
 
   auto issue_tile = [&](int tile) {
-    const int stage = tile & 1;
     const int j0 = tile * RS;
     const int pts = min(RS, L2pad - j0);
     const uint32_t bytes = static_cast<uint32_t>(pts) * 4u;
-    mbar_arrive_expect_tx(&bars[stage], bytes * ROWS);
+    mbar_arrive_expect_tx(&bars[0], bytes * ROWS);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
-      tma_bulk_g2s(tiles + (static_cast<size_t>(stage) * ROWS + r) * RS,
-                   soa_n + static_cast<size_t>(r) * P2pad + j0, bytes, &bars[stage]);
+      tma_bulk_g2s(tiles + static_cast<size_t>(r) * RS, soa_n + static_cast<size_t>(r) * P2pad + j0, bytes,
+                   &bars[0]);
   };
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    issue_tile(0);
-    if (num_tiles > 1) issue_tile(1);
-  }
+  if (tid == 0) issue_tile(0);
 
   // ---- per-thread query state ---------------------------------------------------------------
   const float M = __uint_as_float(prm.maxabs_bits[n]);
@@ -260,7 +252,6 @@ knn_scan_kernel(const KnnScanParams prm) {
 #pragma unroll
     for (int d = 0; d < DT; ++d) {
       const float q = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
-      qs[d * QPB + slot] = q;
       s = fmaf(q, q, s);
       a[t][d] = EXP ? -2.0f * q : q;
     }
@@ -286,9 +277,9 @@ knn_scan_kernel(const KnnScanParams prm) {
     const int c_end = static_cast<int>((cw[t] - base) / CSTRIDE);
     cw[t] = base;
     if (!__any_sync(0xffffffffu, c_end > 0)) return;
-    float q[DT];
+    float q[DT];  // a = -2q exactly (power-of-two scaling), so q = -a/2 exactly
 #pragma unroll
-    for (int d = 0; d < DT; ++d) q[d] = qs[d * QPB + slot];
+    for (int d = 0; d < DT; ++d) q[d] = EXP ? -0.5f * a[t][d] : a[t][d];
     uint64_t* L = lists + slot;   // element k at L[k * QPB]
     uint64_t* S = surv + tid;     // element a at S[a * THREADS]
     float dkt = dk[t];
@@ -413,12 +404,11 @@ knn_scan_kernel(const KnnScanParams prm) {
   // ---- main loop over p2 tiles ------------------------------------------------------------------
   const uint32_t cw_limit = cand_base + static_cast<uint32_t>(kBufCap - kChunk) * CSTRIDE;
   for (int tile_i = 0; tile_i < num_tiles; ++tile_i) {
-    const int stage = tile_i & 1;
     const int j0 = tile_i * RS;
     const int pts = min(RS, L2pad - j0);
     const int ngroups = pts / kGroup;  // multiple of kChunk
-    const float* tile = tiles + static_cast<size_t>(stage) * ROWS * RS;
-    mbar_wait(&bars[stage], (tile_i >> 1) & 1);
+    const float* tile = tiles;
+    mbar_wait(&bars[0], tile_i & 1);
 
     // software pipeline: the next group's rows are loaded while the current group is evaluated
     // (the last prefetch of a tile reads one group past the valid data: in-bounds shared memory,
@@ -482,10 +472,10 @@ knn_scan_kernel(const KnnScanParams prm) {
 #pragma unroll
     for (int t = 0; t < Q; ++t) flush(t, tile, j0);
 
-    __syncthreads();  // everyone is done reading this stage
-    if (tid == 0 && tile_i + 2 < num_tiles) {
+    __syncthreads();  // everyone is done reading the tile
+    if (tid == 0 && tile_i + 1 < num_tiles) {
       fence_proxy_async();
-      issue_tile(tile_i + 2);
+      issue_tile(tile_i + 1);
     }
   }
 
@@ -646,22 +636,19 @@ inline int pad_points(int64_t P2) {
   return static_cast<int>((P2 + kPadPoints - 1) / kPadPoints * kPadPoints);
 }
 
-// Queries per thread by K: the per-CTA top-K lists (K * Q*128 * 8 B) stay <= 64 KB so that two
-// CTAs share an SM; beyond K = 64 a single CTA per SM holds up to K = 128.
-inline int tiled_q_for(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
 inline bool tiled_k_ok(int K) { return K <= 128; }
 
-template <int DT, int NORM, bool EXP, int Q, int KT>
+template <int DT, int NORM, bool EXP, int Q, int KT, int RS, int THREADS = kTiledThreads>
 int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
-  using SM = KnnSmem<DT, EXP, Q, kTiledThreads>;
-  constexpr int QPB = Q * kTiledThreads;
+  using SM = KnnSmem<DT, EXP, Q, THREADS, RS>;
+  constexpr int QPB = Q * THREADS;
   const size_t smem = SM::total(prm.K);
   if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: K too large for the tiled kernel");
-  auto kern = knn_scan_kernel<DT, NORM, EXP, Q, kTiledThreads, KT>;
+  auto kern = knn_scan_kernel<DT, NORM, EXP, Q, THREADS, KT, RS>;
   POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(ceil_div(prm.P1, QPB)), N);
   profile_begin("knn_scan", st);
-  kern<<<grid, kTiledThreads, smem, st>>>(prm);
+  kern<<<grid, THREADS, smem, st>>>(prm);
   profile_end("knn_scan", st);
   POPS_LAUNCH_OK("knn_scan_kernel");
   return POPS_OK;
@@ -687,16 +674,24 @@ int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const in
   KnnScanParams prm;
   prm.p1 = p1; prm.soa = soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = maxabs;
   prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = P2pad; prm.K = K;
+  // (Q queries/thread, tile points) by K so that two CTAs share an SM:
+  //   lists K*Q*128*8 B + candidates + survivors + tile <= ~112 KB
   if (EXP) {
     // register-merge buckets for the headline kernel (D = 3, L2): KT = next power of two >= K
-    if (K == 1) return launch_scan<DT, NORM, EXP, 4, EXP ? 1 : 0>(prm, N, st);
-    if (K <= 4) return launch_scan<DT, NORM, EXP, 4, EXP ? 4 : 0>(prm, N, st);
-    if (K <= 16) return launch_scan<DT, NORM, EXP, 4, EXP ? 16 : 0>(prm, N, st);
-    if (K <= 32) return launch_scan<DT, NORM, EXP, EXP ? 2 : 1, EXP ? 32 : 0>(prm, N, st);
-    return launch_scan<DT, NORM, EXP, 1, 0>(prm, N, st);
+    if (K == 1) return launch_scan<DT, NORM, EXP, 4, EXP ? 1 : 0, 2048>(prm, N, st);
+    if (K <= 4) return launch_scan<DT, NORM, EXP, 4, EXP ? 4 : 0, 2048>(prm, N, st);
+    if (K <= 16) {
+      static const int cfg = getenv("POPS_KNN_CFG") ? atoi(getenv("POPS_KNN_CFG")) : 0;  // tuning aid
+      if (cfg == 1) return launch_scan<DT, NORM, EXP, EXP ? 2 : 4, EXP ? 16 : 0, 1024>(prm, N, st);
+      if (cfg == 2) return launch_scan<DT, NORM, EXP, EXP ? 2 : 4, EXP ? 16 : 0, EXP ? 1536 : 2048, EXP ? 192 : 128>(prm, N, st);
+      if (cfg == 3) return launch_scan<DT, NORM, EXP, EXP ? 2 : 4, EXP ? 16 : 0, 2048, EXP ? 384 : 128>(prm, N, st);
+      return launch_scan<DT, NORM, EXP, EXP ? 3 : 4, EXP ? 16 : 0, 2048>(prm, N, st);
+    }
+    if (K <= 32) return launch_scan<DT, NORM, EXP, EXP ? 2 : 1, EXP ? 32 : 0, 1024>(prm, N, st);
+    return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
   }
-  if (tiled_q_for(K) == 4) return launch_scan<DT, NORM, EXP, 4, 0>(prm, N, st);
-  return launch_scan<DT, NORM, EXP, 1, 0>(prm, N, st);
+  if (K <= 12) return launch_scan<DT, NORM, EXP, 4, 0, 2048>(prm, N, st);
+  return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
 }
 
 constexpr int kGenericThreads = 128;
