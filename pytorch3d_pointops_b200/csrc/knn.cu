@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "knn_order.cuh"
 
 namespace pops {
 
@@ -108,21 +109,33 @@ struct KnnScanParams {
   int64_t* idx;
   float* dists;
   int P1, P2, P2pad, K;
+  // ordered (Morton) variant only
+  const float4* qsorted;   // [N][P1] x,y,z,orig-index bits, Morton order
+  const unsigned* qhome;   // [N][P1] home position of the query in the sorted p2
 };
+
+// k-th element of the "outward from s" visiting order of 0..n-1:  s, s+1, s-1, s+2, ... and, once
+// one side is exhausted, the rest of the other side moving away from s.
+__host__ __device__ __forceinline__ int outward_seq(int k, int s, int n) {
+  const int m = min(s, n - 1 - s);
+  if (k <= 2 * m) return (k & 1) ? s + ((k + 1) >> 1) : s - (k >> 1);
+  return (s - m == 0) ? k : n - 1 - k;
+}
 
 constexpr int kBufCap = 16;  // candidate buffer capacity (groups) per query
 
 // Shared-memory carve-up.  RS = points per tile row (compile time, so tile loads in the hot loop
 // are immediate-offset LDS.128).  ONE tile stage: the TMA refill of a CTA overlaps with the other
 // resident CTA's compute; a single large tile halves the number of forced end-of-tile flushes.
-template <int DT, bool EXP, int Q, int THREADS, int RS>
+template <int DT, bool EXP, bool ORD, bool GL, int Q, int THREADS, int RS>
 struct KnnSmem {
-  static constexpr int ROWS = DT + (EXP ? 1 : 0);
+  static constexpr int ROWS = DT + (EXP ? 1 : 0) + (ORD ? 1 : 0);  // ORD: + original-index row
   static constexpr int QPB = Q * THREADS;
   static constexpr size_t tiles_off = 64;
   static constexpr size_t tiles_bytes = size_t(ROWS) * RS * 4 + 64;  // +64: the prefetch over-read
   static constexpr size_t lists_off = tiles_off + tiles_bytes;
-  static __host__ __device__ size_t lists_bytes(int K) { return size_t(K) * QPB * 8; }
+  // GL: the top-K lists live in the OUTPUT arrays (global memory), not in shared memory
+  static __host__ __device__ size_t lists_bytes(int K) { return GL ? 0 : size_t(K) * QPB * 8; }
   static __host__ __device__ size_t cand_off(int K) { return lists_off + lists_bytes(K); }
   static constexpr size_t cand_bytes = size_t(kBufCap) * QPB * 2;
   static __host__ __device__ size_t surv_off(int K) { return (cand_off(K) + cand_bytes + 7) / 8 * 8; }
@@ -174,122 +187,38 @@ __device__ __forceinline__ void insert_network(uint64_t (&Lr)[KT], uint64_t key)
 
 static_assert(kSurvCap == 16, "sort16 assumes 16 survivor slots");
 
-template <int DT, int NORM, bool EXP, int Q, int THREADS, int KT, int RS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 192 ? 2 : 1))
-knn_scan_kernel(const KnnScanParams prm) {
-  using SM = KnnSmem<DT, EXP, Q, THREADS, RS>;
-  constexpr int ROWS = SM::ROWS;
-  constexpr int QPB = SM::QPB;
-  extern __shared__ __align__(128) unsigned char smem[];
-
-  const int n = blockIdx.y;
-  const int q_base = blockIdx.x * QPB;
-  const int tid = threadIdx.x;
-  const int K = prm.K, P2pad = prm.P2pad;
-  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
-  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
-  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
-
-  int64_t* out_idx = prm.idx + (static_cast<size_t>(n) * prm.P1) * K;
-  float* out_d = prm.dists + (static_cast<size_t>(n) * prm.P1) * K;
-
-  // CTA entirely beyond lengths1[n] (or nothing to search): rows are (0, 0).
-  if (q_base >= L1 || L2 == 0) {
-    const int rows = min(QPB, prm.P1 - q_base);
-    for (int e = tid; e < rows * K; e += THREADS) {
-      out_idx[static_cast<size_t>(q_base) * K + e] = 0;
-      out_d[static_cast<size_t>(q_base) * K + e] = 0.0f;
-    }
-    return;
-  }
-
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  float* tiles = reinterpret_cast<float*>(smem + SM::tiles_off);
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + SM::lists_off);
-  unsigned short* cand = reinterpret_cast<unsigned short*>(smem + SM::cand_off(K));
-  uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off(K));
-
-  const int L2pad = (L2 + kPadPoints - 1) / kPadPoints * kPadPoints;  // <= P2pad
-  const int num_tiles = (L2pad + RS - 1) / RS;
-  const float* soa_n = prm.soa + static_cast<size_t>(n) * ROWS * P2pad;
-
-  auto issue_tile = [&](int tile) {
-    const int j0 = tile * RS;
-    const int pts = min(RS, L2pad - j0);
-    const uint32_t bytes = static_cast<uint32_t>(pts) * 4u;
-    mbar_arrive_expect_tx(&bars[0], bytes * ROWS);
+// ---------------------------------------------------------------------------------------------
+// flush: drain ONE query's candidate buffer.  A real (non-inlined) function: it is big, runs
+// rarely, and must exist once, not once per call site and query slot -- the scan loop has to stay
+// resident in the instruction cache.  Called warp-converged and kept converged inside: rare events
+// never sit inside a dense loop.
+//   fill   per buffered group, all 4 points get the exact unfused distance (branch-free, packed
+//          f32x2 sub/mul, scalar adds -- IEEE, never fused); points with d <= dk are appended as
+//          64-bit keys to the lane's survivor column (predicated);
+//   merge  KT > 0: the list (kept in the OUTPUT arrays) is pulled into registers by the lanes that
+//          hold survivors; few survivors -> branch-free insertion network per survivor, many ->
+//          sort network + bitonic merge.  KT == 0 (any K): sorted survivors are merged backward in
+//          place into the shared-memory list.
+// Returns the query's new K-th distance (+inf while the list is not full).
+template <int DT, int NORM, bool EXP, bool ORD, int THREADS, int KT, int RS, int QPB>
+__device__ __noinline__ float knn_flush_one(const float* tile, const unsigned short* cand_col, int c_end,
+                                            uint64_t* L, uint64_t* S, float4 qv, float dkt, int j0,
+                                            int L2, int K, float* od, int64_t* oi) {
+  if (!__any_sync(0xffffffffu, c_end > 0)) return dkt;
+  const float qarr[4] = {qv.x, qv.y, qv.z, qv.w};
+  float q[DT];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-      tma_bulk_g2s(tiles + static_cast<size_t>(r) * RS, soa_n + static_cast<size_t>(r) * P2pad + j0, bytes,
-                   &bars[0]);
-  };
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid == 0) issue_tile(0);
-
-  // ---- per-thread query state ---------------------------------------------------------------
-  const float M = __uint_as_float(prm.maxabs_bits[n]);
-  // E >= 130.2 * 2^-24 * M^2 bounds |filter - reference| (DESIGN.md "filter error bound").
-  const float E = fmaf(M * M, 1.52587890625e-05f /* 2^-16 */, 1e-37f);
-  constexpr uint32_t CSTRIDE = QPB * 2;  // bytes between consecutive entries of one candidate buffer
+  for (int d = 0; d < DT; ++d) q[d] = qarr[d];
+  constexpr bool GL = KT > 0;
+  constexpr int IDXROW = DT + 1;
   const float INF = __int_as_float(0x7f800000);
-  float a[Q][DT];   // EXP: -2 q_d (FFMA2 takes it as a broadcast scalar operand);  else q_d
-  float qq[Q];
-  float T[Q];       // filter threshold
-  float dk[Q];      // current K-th distance (+inf while the list is not full)
-  uint32_t cw[Q];   // shared-memory byte address of the next free candidate slot
-  const uint32_t cand_base = smem_u32(cand) + static_cast<uint32_t>(tid) * 2u;
-#pragma unroll
-  for (int t = 0; t < Q; ++t) {
-    const int slot = t * THREADS + tid;
-    const int qi = q_base + slot;
-    const bool valid = qi < L1;
-    float s = 0.0f;
-#pragma unroll
-    for (int d = 0; d < DT; ++d) {
-      const float q = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
-      s = fmaf(q, q, s);
-      a[t][d] = EXP ? -2.0f * q : q;
-    }
-    qq[t] = s;
-    dk[t] = valid ? INF : -1.0f;
-    T[t] = valid ? (EXP ? FLT_MAX : INF) : -INF;
-    cw[t] = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
-    for (int k = 0; k < K; ++k) lists[static_cast<size_t>(k) * QPB + slot] = kEmptyKey;
-  }
-
-  // ---- flush: drain one query's candidate buffer -------------------------------------------------
-  // Called warp-converged (every lane flushes together) and kept converged inside: rare events
-  // never sit inside a dense loop.
-  //   fill   per buffered group, all 4 points get the exact unfused distance (branch-free, packed
-  //          f32x2 add/mul -- IEEE, never fused); points with d <= dk are appended as 64-bit keys
-  //          to the lane's survivor column (predicated);
-  //   merge  KT > 0: the list is pulled into registers; few survivors -> branch-free insertion
-  //          network per survivor, many -> sort network + bitonic merge.  KT == 0 (any K): sorted
-  //          survivors are merged backward in place in shared memory.
-  auto flush = [&](int t, const float* tile, int j0) {
-    const int slot = t * THREADS + tid;
-    const uint32_t base = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
-    const int c_end = static_cast<int>((cw[t] - base) / CSTRIDE);
-    cw[t] = base;
-    if (!__any_sync(0xffffffffu, c_end > 0)) return;
-    float q[DT];  // a = -2q exactly (power-of-two scaling), so q = -a/2 exactly
-#pragma unroll
-    for (int d = 0; d < DT; ++d) q[d] = EXP ? -0.5f * a[t][d] : a[t][d];
-    uint64_t* L = lists + slot;   // element k at L[k * QPB]
-    uint64_t* S = surv + tid;     // element a at S[a * THREADS]
-    float dkt = dk[t];
     int c = 0;
     for (;;) {
       if (!__any_sync(0xffffffffu, c < c_end)) break;
       // ---- fill ----
       int ns = 0;
       while (c < c_end && ns <= kSurvCap - kGroup) {
-        const int g = cand[c * QPB + slot];
+        const int g = cand_col[c * QPB];
         ++c;
         float4 X[DT];
 #pragma unroll
@@ -323,10 +252,14 @@ knn_scan_kernel(const KnnScanParams prm) {
           }
         }
         const int jg = j0 + g * kGroup;
+        uint4 pix = make_uint4(jg, jg + 1, jg + 2, jg + 3);  // original point indices
+        if (ORD) pix = reinterpret_cast<const uint4*>(tile + IDXROW * RS)[g];
+        const unsigned oix[kGroup] = {pix.x, pix.y, pix.z, pix.w};
 #pragma unroll
         for (int i = 0; i < kGroup; ++i) {
-          if (dist[i] <= dkt && jg + i < L2) {
-            S[ns * THREADS] = make_key(dist[i], static_cast<uint32_t>(jg + i));
+          const bool real = ORD ? (oix[i] != kNoPoint) : (jg + i < L2);
+          if (dist[i] <= dkt && real) {
+            S[ns * THREADS] = make_key(dist[i], oix[i]);
             ++ns;
           }
         }
@@ -338,8 +271,29 @@ knn_scan_kernel(const KnnScanParams prm) {
         if (KT > 0) {
           constexpr int KR = KT > 0 ? KT : 1;
           uint64_t Lr[KR];
+          const bool mine = ns > 0;  // only lanes that hold survivors touch their list
 #pragma unroll
-          for (int k = 0; k < KR; ++k) Lr[k] = (k < K) ? L[static_cast<size_t>(k) * QPB] : kEmptyKey;
+          for (int k = 0; k < KR; ++k) Lr[k] = kEmptyKey;
+          if (mine) {
+            if (KR >= 4 && (K & 3) == 0) {  // rows are 16-byte aligned: 128-bit loads
+#pragma unroll
+              for (int k4 = 0; k4 < KR / 4; ++k4) {
+                if (k4 * 4 < K) {
+                  const float4 dv = reinterpret_cast<const float4*>(od)[k4];
+                  const longlong2 i01 = reinterpret_cast<const longlong2*>(oi)[k4 * 2];
+                  const longlong2 i23 = reinterpret_cast<const longlong2*>(oi)[k4 * 2 + 1];
+                  Lr[k4 * 4 + 0] = make_key(dv.x, static_cast<uint32_t>(i01.x));
+                  Lr[k4 * 4 + 1] = make_key(dv.y, static_cast<uint32_t>(i01.y));
+                  Lr[k4 * 4 + 2] = make_key(dv.z, static_cast<uint32_t>(i23.x));
+                  Lr[k4 * 4 + 3] = make_key(dv.w, static_cast<uint32_t>(i23.y));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < KR; ++k)
+                if (k < K) Lr[k] = make_key(od[k], static_cast<uint32_t>(oi[k]));
+            }
+          }
           if (ns_max <= 5 || KR < 4) {
             for (int s2 = 0; s2 < ns_max; ++s2) {
               const uint64_t key = (s2 < ns) ? S[s2 * THREADS] : kEmptyKey;
@@ -358,11 +312,37 @@ knn_scan_kernel(const KnnScanParams prm) {
             }
             bitonic_merge<KR>(Lr);
           }
+          if (mine) {
+            if (KR >= 4 && (K & 3) == 0) {
 #pragma unroll
-          for (int k = 0; k < KR; ++k)
-            if (k < K) L[static_cast<size_t>(k) * QPB] = Lr[k];
-          const uint64_t worst = L[static_cast<size_t>(K - 1) * QPB];  // re-read: K is a runtime index
-          if (worst != kEmptyKey) dkt = key_dist(worst);
+              for (int k4 = 0; k4 < KR / 4; ++k4) {
+                if (k4 * 4 < K) {
+                  reinterpret_cast<float4*>(od)[k4] =
+                      make_float4(key_dist(Lr[k4 * 4]), key_dist(Lr[k4 * 4 + 1]), key_dist(Lr[k4 * 4 + 2]),
+                                  key_dist(Lr[k4 * 4 + 3]));
+                  reinterpret_cast<longlong2*>(oi)[k4 * 2] =
+                      make_longlong2(static_cast<long long>(Lr[k4 * 4] & 0xFFFFFFFFull),
+                                     static_cast<long long>(Lr[k4 * 4 + 1] & 0xFFFFFFFFull));
+                  reinterpret_cast<longlong2*>(oi)[k4 * 2 + 1] =
+                      make_longlong2(static_cast<long long>(Lr[k4 * 4 + 2] & 0xFFFFFFFFull),
+                                     static_cast<long long>(Lr[k4 * 4 + 3] & 0xFFFFFFFFull));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < KR; ++k) {
+                if (k < K) {
+                  od[k] = key_dist(Lr[k]);
+                  oi[k] = static_cast<int64_t>(Lr[k] & 0xFFFFFFFFull);
+                }
+              }
+            }
+            uint64_t worst = kEmptyKey;
+#pragma unroll
+            for (int k = 0; k < KR; ++k)
+              if (k == K - 1) worst = Lr[k];
+            dkt = key_dist(worst);  // +inf while the list is not full
+          }
         } else if (ns > 0) {
           for (int a2 = 1; a2 < ns; ++a2) {  // insertion sort of the survivors
             const uint64_t key = S[a2 * THREADS];
@@ -397,35 +377,220 @@ knn_scan_kernel(const KnnScanParams prm) {
       }
       __syncwarp();
     }
+    return dkt;
+}
+
+
+
+template <int DT, int NORM, bool EXP, bool ORD, int Q, int THREADS, int KT, int RS>
+__global__ void __launch_bounds__(THREADS, (THREADS > 192 ? 1 : ((KT > 0 && KT <= 16) ? 3 : 2)))
+knn_scan_kernel(const KnnScanParams prm) {
+  static_assert(!ORD || (EXP && DT == 3), "the ordered variant is the D=3 L2 kernel");
+  constexpr bool GL = KT > 0;  // register-merge variants keep their lists in the output arrays
+  using SM = KnnSmem<DT, EXP, ORD, GL, Q, THREADS, RS>;
+  constexpr int IDXROW = DT + 1;  // ORD: tile row holding the original point indices
+  constexpr int ROWS = SM::ROWS;
+  constexpr int QPB = SM::QPB;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const int n = blockIdx.y;
+  const int q_base = blockIdx.x * QPB;
+  const int tid = threadIdx.x;
+  const int K = prm.K, P2pad = prm.P2pad;
+  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
+  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
+  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
+
+  int64_t* out_idx = prm.idx + (static_cast<size_t>(n) * prm.P1) * K;
+  float* out_d = prm.dists + (static_cast<size_t>(n) * prm.P1) * K;
+
+  // CTA entirely beyond lengths1[n] (or nothing to search): rows are (0, 0).
+  if (q_base >= L1 || L2 == 0) {
+    const int rows = min(QPB, prm.P1 - q_base);
+    for (int e = tid; e < rows * K; e += THREADS) {
+      size_t row = static_cast<size_t>(q_base) + e / K;
+      if (ORD) row = __float_as_uint(prm.qsorted[static_cast<size_t>(n) * prm.P1 + row].w);
+      out_idx[row * K + e % K] = 0;
+      out_d[row * K + e % K] = 0.0f;
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  float* tiles = reinterpret_cast<float*>(smem + SM::tiles_off);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + SM::lists_off);
+  unsigned short* cand = reinterpret_cast<unsigned short*>(smem + SM::cand_off(K));
+  uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off(K));
+
+  const int L2pad = (L2 + kPadPoints - 1) / kPadPoints * kPadPoints;  // <= P2pad
+  const int num_tiles = (L2pad + RS - 1) / RS;
+  const float* soa_n = prm.soa + static_cast<size_t>(n) * ROWS * P2pad;
+
+  // Thread -> query slots.  ORD: a warp's Q*32 queries are contiguous in Morton order.
+  constexpr int SLOT_STRIDE = ORD ? 32 : THREADS;
+  const int slot0 = ORD ? (tid >> 5) * (Q * 32) + (tid & 31) : tid;
+
+  // ORD: tiles are visited outward from the tile that holds the CTA's own neighbourhood
+  int tile_h = 0, warp_home = 0;
+  if (ORD) {
+    const int nvalid = min(QPB, L1 - q_base);
+    const unsigned* qh = prm.qhome + static_cast<size_t>(n) * prm.P1 + q_base;
+    tile_h = min(static_cast<int>(qh[nvalid >> 1]) / RS, num_tiles - 1);
+    const int wmid = min((tid >> 5) * (Q * 32) + Q * 16, nvalid - 1);
+    warp_home = static_cast<int>(qh[wmid]);
+  }
+
+  auto issue_tile = [&](int tile) {
+    const int j0 = tile * RS;
+    const int pts = min(RS, L2pad - j0);
+    const uint32_t bytes = static_cast<uint32_t>(pts) * 4u;
+    mbar_arrive_expect_tx(&bars[0], bytes * ROWS);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+      tma_bulk_g2s(tiles + static_cast<size_t>(r) * RS, soa_n + static_cast<size_t>(r) * P2pad + j0, bytes,
+                   &bars[0]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) issue_tile(ORD ? tile_h : 0);
+
+  // ---- per-thread query state ---------------------------------------------------------------
+  const float M = __uint_as_float(prm.maxabs_bits[n]);
+  // E >= 130.2 * 2^-24 * M^2 bounds |filter - reference| (DESIGN.md "filter error bound").
+  const float E = fmaf(M * M, 1.52587890625e-05f /* 2^-16 */, 1e-37f);
+  constexpr uint32_t CSTRIDE = QPB * 2;  // bytes between consecutive entries of one candidate buffer
+  const float INF = __int_as_float(0x7f800000);
+  float a[Q][DT];   // EXP: -2 q_d (FFMA2 takes it as a broadcast scalar operand);  else q_d
+  float qq[Q];
+  float T[Q];       // filter threshold
+  float dk[Q];      // current K-th distance (+inf while the list is not full)
+  uint32_t cw[Q];   // shared-memory byte address of the next free candidate slot
+  const uint32_t cand_base = smem_u32(cand) + static_cast<uint32_t>(slot0) * 2u;
+  unsigned orow[Q];  // output row (original query index)
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    const int slot = slot0 + t * SLOT_STRIDE;
+    const int qi = q_base + slot;
+    const bool valid = qi < L1;
+    float qv[DT];
+    orow[t] = static_cast<unsigned>(qi);
+    if (ORD) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (qi < prm.P1) v = prm.qsorted[static_cast<size_t>(n) * prm.P1 + qi];
+      qv[0] = v.x; qv[1 % DT] = v.y; qv[2 % DT] = v.z;
+      orow[t] = __float_as_uint(v.w);
+    } else {
+#pragma unroll
+      for (int d = 0; d < DT; ++d)
+        qv[d] = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      const float q = valid ? qv[d] : 0.0f;
+      s = fmaf(q, q, s);
+      a[t][d] = EXP ? -2.0f * q : q;
+    }
+    qq[t] = s;
+    dk[t] = valid ? INF : -1.0f;
+    T[t] = valid ? (EXP ? FLT_MAX : INF) : -INF;
+    cw[t] = cand_base + static_cast<uint32_t>(t) * (SLOT_STRIDE * 2u);
+    if (GL) {
+      // empty list = (+inf, 0xFFFFFFFF) in every slot; rows beyond lengths1 are final zeros
+      if (qi < prm.P1) {
+        float* od = out_d + static_cast<size_t>(orow[t]) * K;
+        int64_t* oi = out_idx + static_cast<size_t>(orow[t]) * K;
+        for (int k = 0; k < K; ++k) {
+          od[k] = valid ? INF : 0.0f;
+          oi[k] = valid ? static_cast<int64_t>(0xFFFFFFFFll) : 0;
+        }
+      }
+    } else {
+      for (int k = 0; k < K; ++k) lists[static_cast<size_t>(k) * QPB + slot] = kEmptyKey;
+    }
+  }
+
+  // ---- flush glue: drain query t's candidate buffer (knn_flush_one, defined above) ---------------
+  auto flush = [&](int t, const float* tile, int j0) {
+    const int slot = slot0 + t * SLOT_STRIDE;
+    const uint32_t base = cand_base + static_cast<uint32_t>(t) * (SLOT_STRIDE * 2u);
+    const int c_end = static_cast<int>((cw[t] - base) / CSTRIDE);
+    cw[t] = base;
+    float4 qv;  // a = -2q exactly (power-of-two scaling), so q = -a/2 exactly
+    qv.x = EXP ? -0.5f * a[t][0] : a[t][0];
+    qv.y = EXP ? -0.5f * a[t][1 % DT] : a[t][1 % DT];
+    qv.z = EXP ? -0.5f * a[t][2 % DT] : a[t][2 % DT];
+    qv.w = EXP ? -0.5f * a[t][3 % DT] : a[t][3 % DT];
+    const float dkt = knn_flush_one<DT, NORM, EXP, ORD, THREADS, KT, RS, QPB>(
+        tile, cand + slot, c_end, GL ? nullptr : lists + slot, surv + tid, qv, dk[t], j0, L2, K,
+        out_d + static_cast<size_t>(orow[t]) * K, out_idx + static_cast<size_t>(orow[t]) * K);
     dk[t] = dkt;
-    if (dkt < INF) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
+    if (dkt >= 0.0f && dkt < INF) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
   };
 
   // ---- main loop over p2 tiles ------------------------------------------------------------------
   const uint32_t cw_limit = cand_base + static_cast<uint32_t>(kBufCap - kChunk) * CSTRIDE;
-  for (int tile_i = 0; tile_i < num_tiles; ++tile_i) {
+  for (int tile_k = 0; tile_k < num_tiles; ++tile_k) {
+    const int tile_i = ORD ? outward_seq(tile_k, tile_h, num_tiles) : tile_k;
     const int j0 = tile_i * RS;
     const int pts = min(RS, L2pad - j0);
     const int ngroups = pts / kGroup;  // multiple of kChunk
     const float* tile = tiles;
-    mbar_wait(&bars[0], tile_i & 1);
+    mbar_wait(&bars[0], tile_k & 1);
 
-    // software pipeline: the next group's rows are loaded while the current group is evaluated
-    // (the last prefetch of a tile reads one group past the valid data: in-bounds shared memory,
-    // never used)
+    // The tile is scanned in RUNS: contiguous ascending ranges of groups, a multiple of kChunk
+    // long, read with immediate-offset LDS.128; the next group's rows are loaded while the current
+    // group is evaluated (the last prefetch of a run reads one group past it: in-bounds shared
+    // memory, never used).  Non-ORD: one run.  ORD: nearest first at block granularity -- blocks of
+    // kRunGroups groups alternately to the right and to the left of the warp's own position (home
+    // tile), or starting from the edge that faces the home tile (other tiles).
+    // One loop, ONE flush call site (overflow of any lane, or end of tile).
     const float4* tp = reinterpret_cast<const float4*>(tile);
-    float4 Xc[ROWS];
+    constexpr int SROWS = DT + (EXP ? 1 : 0);  // rows the scan reads (not the index row)
+    constexpr int kRunGroups = 16;
+    int R = 0, Lc = 0;  // ORD: next block to the right starts at R, next to the left ends at Lc
+    if (ORD) {
+      R = (tile_i == tile_h) ? (min(max((warp_home - j0) / kGroup, 0), ngroups) & ~(kChunk - 1))
+                             : (tile_i > tile_h ? 0 : ngroups);
+      Lc = R;
+    }
+    bool go_right = true;
+    int g = 0, g_end = 0;  // current run [g, g_end)
+    float4 Xc[SROWS];
+    for (;;) {
+      if (g >= g_end) {  // start the next run
+        if (ORD) {
+          const bool can_r = R < ngroups, can_l = Lc > 0;
+          if (!can_r && !can_l) break;
+          if ((go_right && can_r) || !can_l) {
+            g = R;
+            g_end = min(R + kRunGroups, ngroups);
+            R = g_end;
+          } else {
+            g_end = Lc;
+            g = max(Lc - kRunGroups, 0);
+            Lc = g;
+          }
+          go_right = !go_right;
+        } else {
+          if (R >= ngroups) break;
+          g = 0;
+          g_end = ngroups;
+          R = ngroups;
+        }
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) Xc[r] = tp[r * (RS / 4)];
-
-    for (int g0 = 0; g0 < ngroups; g0 += kChunk) {
+        for (int r = 0; r < SROWS; ++r) Xc[r] = tp[r * (RS / 4) + g];
+      }
 #pragma unroll
       for (int c = 0; c < kChunk; ++c) {
-        const int g = g0 + c;
-        float4 Xn[ROWS];
+        float4 Xn[SROWS];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) Xn[r] = tp[r * (RS / 4) + g + 1];
-        const unsigned short g16 = static_cast<unsigned short>(g);
+        for (int r = 0; r < SROWS; ++r) Xn[r] = tp[r * (RS / 4) + g + c + 1];
+        const unsigned short g16 = static_cast<unsigned short>(g + c);
 #pragma unroll
         for (int t = 0; t < Q; ++t) {
           float m;
@@ -458,35 +623,54 @@ knn_scan_kernel(const KnnScanParams prm) {
           }
         }
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) Xc[r] = Xn[r];
+        for (int r = 0; r < SROWS; ++r) Xc[r] = Xn[r];
       }
-      // warp-converged overflow check: flush everything when ANY lane's buffer is nearly full
+      g += kChunk;
+      const bool tile_done = (g >= g_end) && (ORD ? (R >= ngroups && Lc <= 0) : true);
+      // warp-converged: flush everything when ANY lane's buffer is nearly full, or at tile end
       uint32_t mx = cw[0];
 #pragma unroll
-      for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (THREADS * 2u));
-      if (__any_sync(0xffffffffu, mx > cw_limit)) {
+      for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (SLOT_STRIDE * 2u));
+      if (tile_done || __any_sync(0xffffffffu, mx > cw_limit)) {
 #pragma unroll
         for (int t = 0; t < Q; ++t) flush(t, tile, j0);
       }
     }
-#pragma unroll
-    for (int t = 0; t < Q; ++t) flush(t, tile, j0);
 
     __syncthreads();  // everyone is done reading the tile
-    if (tid == 0 && tile_i + 1 < num_tiles) {
+    if (tid == 0 && tile_k + 1 < num_tiles) {
       fence_proxy_async();
-      issue_tile(tile_i + 1);
+      issue_tile(ORD ? outward_seq(tile_k + 1, tile_h, num_tiles) : tile_k + 1);
     }
   }
 
-  // ---- write out: sorted keys -> (idx, dist); empty slots and rows >= L1 are (0, 0) -----------
+  // ---- write out ---------------------------------------------------------------------------------
+  if (GL) {
+    // the lists ARE the outputs; only slots beyond lengths2 (K > lengths2) still hold the empty
+    // marker and become the reference's (0, 0) padding
+    if (L2 < K) {
+#pragma unroll
+      for (int t = 0; t < Q; ++t) {
+        const int qi = q_base + slot0 + t * SLOT_STRIDE;
+        if (qi >= L1) continue;
+        float* od = out_d + static_cast<size_t>(orow[t]) * K;
+        int64_t* oi = out_idx + static_cast<size_t>(orow[t]) * K;
+        for (int k = L2; k < K; ++k) {
+          od[k] = 0.0f;
+          oi[k] = 0;
+        }
+      }
+    }
+    return;
+  }
+  // sorted keys -> (idx, dist); empty slots and rows >= L1 are (0, 0)
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
-    const int slot = t * THREADS + tid;
+    const int slot = slot0 + t * SLOT_STRIDE;
     const int qi = q_base + slot;
     if (qi >= prm.P1) continue;
-    int64_t* oi = out_idx + static_cast<size_t>(qi) * K;
-    float* od = out_d + static_cast<size_t>(qi) * K;
+    int64_t* oi = out_idx + static_cast<size_t>(orow[t]) * K;
+    float* od = out_d + static_cast<size_t>(orow[t]) * K;
     for (int k = 0; k < K; ++k) {
       const uint64_t key = lists[static_cast<size_t>(k) * QPB + slot];
       const bool ok = key != kEmptyKey;
@@ -638,13 +822,13 @@ inline int pad_points(int64_t P2) {
 
 inline bool tiled_k_ok(int K) { return K <= 128; }
 
-template <int DT, int NORM, bool EXP, int Q, int KT, int RS, int THREADS = kTiledThreads>
+template <int DT, int NORM, bool EXP, bool ORD, int Q, int KT, int RS, int THREADS = kTiledThreads>
 int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
-  using SM = KnnSmem<DT, EXP, Q, THREADS, RS>;
+  using SM = KnnSmem<DT, EXP, ORD, (KT > 0), Q, THREADS, RS>;
   constexpr int QPB = Q * THREADS;
   const size_t smem = SM::total(prm.K);
   if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: K too large for the tiled kernel");
-  auto kern = knn_scan_kernel<DT, NORM, EXP, Q, THREADS, KT, RS>;
+  auto kern = knn_scan_kernel<DT, NORM, EXP, ORD, Q, THREADS, KT, RS>;
   POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(ceil_div(prm.P1, QPB)), N);
   profile_begin("knn_scan", st);
@@ -654,9 +838,40 @@ int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
   return POPS_OK;
 }
 
+// D = 3, L2: Morton-ordered clouds + outward scan order (knn_order.cu).  Worth its pre-pass once
+// the cloud spans more than a tile.
+inline bool use_ordered(int64_t P2) {
+  static const int force = getenv("POPS_KNN_ORDER") ? atoi(getenv("POPS_KNN_ORDER")) : -1;  // test aid
+  if (force >= 0) return force != 0;
+  return P2 >= 2048;
+}
+
+int launch_ordered(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
+                   int P1, int P2, int K, int64_t* idx, float* dists, void* ws, cudaStream_t st) {
+  KnnOrderBuffers ob;
+  knn_order_carve(ws, N, P1, P2, &ob);
+  const bool self_knn = (p1 == p2) && (len1 == len2) && (P1 == P2);
+  const int rc = knn_order_prepass(p1, p2, len1, len2, N, P1, P2, self_knn, ob, st);
+  if (rc != POPS_OK) return rc;
+  KnnScanParams prm;
+  prm.p1 = p1; prm.soa = ob.soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits;
+  prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = pad_points(P2); prm.K = K;
+  prm.qsorted = ob.qsorted; prm.qhome = ob.qhome;
+  // (Q queries/thread, tile points) by K so that two CTAs share an SM:
+  //   lists K*Q*128*8 B + candidates + survivors + 5-row tile <= ~112 KB;  KT = merge bucket >= K
+  // lists live in the output arrays (KT > 0): shared memory = 5-row tile + candidates + survivors
+  // = 72 KB -> three CTAs per SM
+  if (K == 1) return launch_scan<3, 2, true, true, 4, 1, 2048>(prm, N, st);
+  if (K <= 4) return launch_scan<3, 2, true, true, 4, 4, 2048>(prm, N, st);
+  if (K <= 16) return launch_scan<3, 2, true, true, 4, 16, 2048>(prm, N, st);
+  if (K <= 32) return launch_scan<3, 2, true, true, 4, 32, 2048>(prm, N, st);
+  return launch_scan<3, 2, true, true, 1, 0, 1024>(prm, N, st);
+}
+
 template <int DT, int NORM, bool EXP>
 int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
                  int P1, int P2, int K, int64_t* idx, float* dists, void* ws, cudaStream_t st) {
+  if (EXP && use_ordered(P2)) return launch_ordered(p1, p2, len1, len2, N, P1, P2, K, idx, dists, ws, st);
   const int P2pad = pad_points(P2);
   unsigned* maxabs = reinterpret_cast<unsigned*>(ws);
   float* soa = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up(size_t(N) * 4, 256));
@@ -674,24 +889,17 @@ int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const in
   KnnScanParams prm;
   prm.p1 = p1; prm.soa = soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = maxabs;
   prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = P2pad; prm.K = K;
-  // (Q queries/thread, tile points) by K so that two CTAs share an SM:
-  //   lists K*Q*128*8 B + candidates + survivors + tile <= ~112 KB
+  prm.qsorted = nullptr; prm.qhome = nullptr;
   if (EXP) {
-    // register-merge buckets for the headline kernel (D = 3, L2): KT = next power of two >= K
-    if (K == 1) return launch_scan<DT, NORM, EXP, 4, EXP ? 1 : 0, 2048>(prm, N, st);
-    if (K <= 4) return launch_scan<DT, NORM, EXP, 4, EXP ? 4 : 0, 2048>(prm, N, st);
-    if (K <= 16) {
-      static const int cfg = getenv("POPS_KNN_CFG") ? atoi(getenv("POPS_KNN_CFG")) : 0;  // tuning aid
-      if (cfg == 1) return launch_scan<DT, NORM, EXP, EXP ? 2 : 4, EXP ? 16 : 0, 1024>(prm, N, st);
-      if (cfg == 2) return launch_scan<DT, NORM, EXP, EXP ? 2 : 4, EXP ? 16 : 0, EXP ? 1536 : 2048, EXP ? 192 : 128>(prm, N, st);
-      if (cfg == 3) return launch_scan<DT, NORM, EXP, EXP ? 2 : 4, EXP ? 16 : 0, 2048, EXP ? 384 : 128>(prm, N, st);
-      return launch_scan<DT, NORM, EXP, EXP ? 3 : 4, EXP ? 16 : 0, 2048>(prm, N, st);
-    }
-    if (K <= 32) return launch_scan<DT, NORM, EXP, EXP ? 2 : 1, EXP ? 32 : 0, 1024>(prm, N, st);
-    return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
+    // register-merge buckets (KT = next power of two >= K)
+    if (K == 1) return launch_scan<DT, NORM, EXP, false, 4, EXP ? 1 : 0, 2048>(prm, N, st);
+    if (K <= 4) return launch_scan<DT, NORM, EXP, false, 4, EXP ? 4 : 0, 2048>(prm, N, st);
+    if (K <= 16) return launch_scan<DT, NORM, EXP, false, 4, EXP ? 16 : 0, 2048>(prm, N, st);
+    if (K <= 32) return launch_scan<DT, NORM, EXP, false, EXP ? 4 : 1, EXP ? 32 : 0, EXP ? 2048 : 1024>(prm, N, st);
+    return launch_scan<DT, NORM, EXP, false, 1, 0, 1024>(prm, N, st);
   }
-  if (K <= 12) return launch_scan<DT, NORM, EXP, 4, 0, 2048>(prm, N, st);
-  return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
+  if (K <= 12) return launch_scan<DT, NORM, EXP, false, 4, 0, 2048>(prm, N, st);
+  return launch_scan<DT, NORM, EXP, false, 1, 0, 1024>(prm, N, st);
 }
 
 constexpr int kGenericThreads = 128;
@@ -719,6 +927,7 @@ extern "C" size_t pops_knn_workspace_bytes(int64_t N, int64_t P1, int64_t P2, in
                                            int norm) {
   if (N <= 0 || P1 <= 0 || K <= 0) return 256;
   size_t tiled = align_up(size_t(N) * 4, 256) + size_t(N) * (D + 1) * pad_points(P2) * 4;
+  if (D == 3 && norm == 2) tiled = std::max(tiled, knn_order_workspace_bytes(N, P1, P2));
   size_t generic = size_t(N) * ceil_div(P1, kGenericThreads) * K * kGenericThreads * 8;
   (void)norm;
   return align_up(std::max(tiled, generic), 256) + 256;

@@ -1,0 +1,32 @@
+// Spatial ordering pre-pass for the D = 3 KNN scan (see knn_order.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pops {
+
+// Everything the ordered scan reads, carved out of the caller's workspace.
+struct KnnOrderBuffers {
+  unsigned* maxabs_bits;  // [N]        max |coordinate| over p1 and p2 of the cloud (float bits)
+  float* bbox;            // [N][6]     min xyz, max xyz of the valid p2 points
+  float* soa;             // [N][5][P2pad]  x, y, z, w=|p|^2, original index (u32 bits), Morton order
+  float4* qsorted;        // [N][P1]    x, y, z, original index (u32 bits), Morton order
+  unsigned* qhome;        // [N][P1]    position in the sorted p2 where the query's code would go
+  // scratch
+  unsigned* keys_in;      // [N*(P1+P2)]
+  unsigned* keys_out;
+  unsigned* vals_in;
+  unsigned* vals_out;
+  void* cub_temp;
+  size_t cub_temp_bytes;
+};
+
+constexpr unsigned kNoPoint = 0xFFFFFFFFu;  // "original index" of padding entries
+
+size_t knn_order_workspace_bytes(int64_t N, int64_t P1, int64_t P2);
+// Lays the buffers out inside `ws` (256-byte aligned pieces).  Returns bytes used.
+size_t knn_order_carve(void* ws, int64_t N, int64_t P1, int64_t P2, KnnOrderBuffers* out);
+// Runs the pre-pass on `st`.  self_knn: p1/lengths1 are the same arrays as p2/lengths2.
+int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2,
+                      int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st);
+
+}  // namespace pops

@@ -26,6 +26,14 @@ if "knn" in which:
         p = torch.rand(N, P, 3, generator=g).to(dev)
         L = torch.full((N,), P, device=dev)
         mn, med = timeit(lambda: _C.knn_points_idx(p, p, L, L, 2, K, -1))
+        import ctypes
+        from pytorch3d_pointops_b200 import _lib
+        lib = _lib.load(); lib.pops_profile_reset(); lib.pops_profile_enable(1)
+        for _ in range(3): _C.knn_points_idx(p, p, L, L, 2, K, -1)
+        torch.cuda.synchronize()
+        nl, ms = ctypes.c_int64(0), ctypes.c_double(0)
+        lib.pops_profile_read(b"knn_scan", ctypes.byref(nl), ctypes.byref(ms)); lib.pops_profile_enable(0)
+        print(f"   scan kernel alone: {ms.value / max(1, nl.value):.3f} ms")
         pairs = N * P * P
         print(f"knn N={N} P={P} K={K}: min {mn:.3f} ms med {med:.3f} ms  {N*P/mn/1e3:.1f} Mq/s  {pairs*9/mn/1e9:.1f} TFLOP/s-alg")
 if "chamfer" in which:
