@@ -17,13 +17,17 @@
 //
 // Generic D: one CTA per cloud, mind in a global scratch row (L2 resident), same reduction.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace pops {
 
-constexpr int kFpsThreads = 1024;
+constexpr int kFpsThreads = 1024;  // generic-D kernel
 constexpr int kFpsWarps = kFpsThreads / 32;
+constexpr int kFps3Threads = 256;  // D = 3 kernel: few fat threads (<= 32 points each in registers)
+constexpr int kFps3Warps = kFps3Threads / 32;
+constexpr int kFps3MaxPT = 32;
 
 struct FpsSlot {  // 32 bytes
   int key;        // float bits of mind (>= 0) or negative when the CTA has no valid point
@@ -61,12 +65,12 @@ __device__ __forceinline__ bool warp_argmax(int key, int idx, int* wkey, int* wi
 }
 
 template <int PT>
-__global__ void __launch_bounds__(kFpsThreads, 1)
+__global__ void __launch_bounds__(kFps3Threads, 1)
 fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ lengths,
               const int64_t* __restrict__ Ks, const int64_t* __restrict__ start_idxs, int P,
               int max_K, int C, int64_t* __restrict__ out) {
-  __shared__ __align__(16) FpsSlot wslots[kFpsWarps];
-  __shared__ __align__(16) FpsSlot cslots[2][16];
+  __shared__ __align__(16) FpsSlot wslots[2][kFps3Warps];  // per-warp winners, double buffered
+  __shared__ __align__(16) FpsSlot cslots[2][16];         // per-CTA winners of the cluster
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (C > 1) ? static_cast<int>(cluster_ctarank()) : 0;
@@ -80,17 +84,19 @@ fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ leng
 
   int last = static_cast<int>(start_idxs[n]);
   if (rank == 0) {
-    for (int k = tid; k < max_K; k += kFpsThreads)
+    for (int k = tid; k < max_K; k += kFps3Threads)
       if (k == 0) o[0] = last; else if (k >= kn) o[k] = -1;
   }
   if (kn <= 1) return;  // uniform across the cluster: nothing else to select
   last = min(max(last, 0), L - 1);
 
+  // point i of this thread has index  i*stride + base  (indices ascend with i)
+  const int stride = C * kFps3Threads;
+  const int base = rank * kFps3Threads + tid;
   float x[PT], y[PT], z[PT], mind[PT];
-  const int stride = C * kFpsThreads;
 #pragma unroll
   for (int i = 0; i < PT; ++i) {
-    const int p = i * stride + rank * kFpsThreads + tid;
+    const int p = i * stride + base;
     const bool v = p < L;
     x[i] = v ? pts[static_cast<size_t>(p) * 3 + 0] : 0.0f;
     y[i] = v ? pts[static_cast<size_t>(p) * 3 + 1] : 0.0f;
@@ -102,54 +108,93 @@ fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ leng
   float lz = pts[static_cast<size_t>(last) * 3 + 2];
 
   for (int k = 1; k < kn; ++k) {
+    const int par = k & 1;
+    // ---- update min-distances; track only the maximum VALUE in the dense loop -----------------
     float best = -1.0f;
-    int bi = 0;
+    if (PT >= 2) {
 #pragma unroll
-    for (int i = 0; i < PT; ++i) {
-      const float dx = __fsub_rn(lx, x[i]), dy = __fsub_rn(ly, y[i]), dz = __fsub_rn(lz, z[i]);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      mind[i] = fminf(mind[i], d);
-      if (mind[i] > best) {  // strict: lowest local index wins ties (indices ascend with i)
-        best = mind[i];
-        bi = i;
+      for (int i = 0; i < PT; i += 2) {
+        const int i1 = (i + 1 < PT) ? i + 1 : i;
+        // packed subtract / multiply (IEEE, unfused), scalar adds (ptxas would fuse mul2+add2)
+        const float2 dx = __fadd2_rn(make_float2(lx, lx), make_float2(-x[i], -x[i1]));
+        const float2 dy = __fadd2_rn(make_float2(ly, ly), make_float2(-y[i], -y[i1]));
+        const float2 dz = __fadd2_rn(make_float2(lz, lz), make_float2(-z[i], -z[i1]));
+        const float2 xx = __fmul2_rn(dx, dx), yy = __fmul2_rn(dy, dy), zz = __fmul2_rn(dz, dz);
+        const float d0 = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
+        const float d1 = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
+        mind[i] = fminf(mind[i], d0);
+        mind[i1] = fminf(mind[i1], d1);
+        best = fmaxf(best, fmaxf(mind[i], mind[i1]));
       }
+    } else {
+      const float dx = __fsub_rn(lx, x[0]), dy = __fsub_rn(ly, y[0]), dz = __fsub_rn(lz, z[0]);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      mind[0] = fminf(mind[0], d);
+      best = mind[0];
     }
-    int wkey, widx;
-    const bool win = warp_argmax(__float_as_int(best), bi * stride + rank * kFpsThreads + tid, &wkey, &widx);
-    if (win) {
+    // ---- warp arg-max: value first, the index only for lanes that hold the maximum ------------
+    const int bkey = __float_as_int(best);
+    const int wkey = __reduce_max_sync(0xffffffffu, bkey);
+    int cand = 0x7fffffff, ci = 0;
+    if (bkey == wkey) {
+#pragma unroll
+      for (int i = PT - 1; i >= 0; --i)
+        if (mind[i] == best) ci = i;  // lowest local slot holding the maximum
+      cand = ci * stride + base;
+    }
+    const int widx = __reduce_min_sync(0xffffffffu, cand);
+    if (cand == widx) {  // exactly one lane (indices are unique)
       float bx = x[0], by = y[0], bz = z[0];
 #pragma unroll
       for (int i = 1; i < PT; ++i)
-        if (bi == i) { bx = x[i]; by = y[i]; bz = z[i]; }
+        if (ci == i) { bx = x[i]; by = y[i]; bz = z[i]; }
       FpsSlot s;
       s.key = wkey; s.idx = widx; s.x = bx; s.y = by; s.z = bz; s.pad0 = s.pad1 = s.pad2 = 0;
-      wslots[warp] = s;
+      wslots[par][warp] = s;
     }
     __syncthreads();
-    const int par = k & 1;
-    if (warp == 0) {
-      const FpsSlot s = wslots[lane];
-      int ckey, cidx;
-      const bool cwin = warp_argmax(s.key, s.idx, &ckey, &cidx);
-      if (cwin) {
-        if (C > 1) {
+
+    FpsSlot b;
+    if (C == 1) {
+      // every warp reduces the 32 warp slots itself: one barrier per iteration
+      FpsSlot s;
+      s.key = static_cast<int>(0x80000000u); s.idx = 0x7fffffff; s.x = s.y = s.z = 0.f;
+      if (lane < kFps3Warps) s = wslots[par][lane];
+      const int ck = __reduce_max_sync(0xffffffffu, s.key);
+      const int cidx = __reduce_min_sync(0xffffffffu, s.key == ck ? s.idx : 0x7fffffff);
+      const int src = __ffs(__ballot_sync(0xffffffffu, s.key == ck && s.idx == cidx)) - 1;
+      b.idx = cidx;
+      b.x = __shfl_sync(0xffffffffu, s.x, src);
+      b.y = __shfl_sync(0xffffffffu, s.y, src);
+      b.z = __shfl_sync(0xffffffffu, s.z, src);
+    } else {
+      if (warp == 0) {
+        FpsSlot s;
+        s.key = static_cast<int>(0x80000000u); s.idx = 0x7fffffff; s.x = s.y = s.z = 0.f;
+        if (lane < kFps3Warps) s = wslots[par][lane];
+        const int ck = __reduce_max_sync(0xffffffffu, s.key);
+        const int cidx = __reduce_min_sync(0xffffffffu, s.key == ck ? s.idx : 0x7fffffff);
+        if (s.key == ck && s.idx == cidx) {  // the CTA's winner goes to every CTA of the cluster
           const uint32_t local = smem_u32(&cslots[par][rank]);
           for (int r = 0; r < C; ++r) {
             const uint32_t remote = map_to_cta(local, static_cast<uint32_t>(r));
             st_cluster_v4(remote, s.key, s.idx, __float_as_int(s.x), __float_as_int(s.y));
             st_cluster_v4(remote + 16, __float_as_int(s.z), 0, 0, 0);
           }
-        } else {
-          cslots[par][0] = s;
         }
       }
-    }
-    if (C > 1) cluster_barrier(); else __syncthreads();
-    // every thread: cluster winner = max key, then min idx
-    FpsSlot b = cslots[par][0];
-    for (int r = 1; r < C; ++r) {
-      const FpsSlot s = cslots[par][r];
-      if (s.key > b.key || (s.key == b.key && s.idx < b.idx)) b = s;
+      cluster_barrier();
+      // every warp picks the cluster winner from the C CTA slots (lane r reads slot r)
+      FpsSlot s;
+      s.key = static_cast<int>(0x80000000u); s.idx = 0x7fffffff; s.x = s.y = s.z = 0.f;
+      if (lane < C) s = cslots[par][lane];
+      const int ck = __reduce_max_sync(0xffffffffu, s.key);
+      const int cidx = __reduce_min_sync(0xffffffffu, s.key == ck ? s.idx : 0x7fffffff);
+      const int src = __ffs(__ballot_sync(0xffffffffu, s.key == ck && s.idx == cidx)) - 1;
+      b.idx = cidx;
+      b.x = __shfl_sync(0xffffffffu, s.x, src);
+      b.y = __shfl_sync(0xffffffffu, s.y, src);
+      b.z = __shfl_sync(0xffffffffu, s.z, src);
     }
     lx = b.x; ly = b.y; lz = b.z;
     if (rank == 0 && tid == 0) o[k] = b.idx;
@@ -212,7 +257,7 @@ int launch_fps_d3(const float* points, const int64_t* lengths, const int64_t* K,
   auto kern = fps_d3_kernel<PT>;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(N) * C);
-  cfg.blockDim = dim3(kFpsThreads);
+  cfg.blockDim = dim3(kFps3Threads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -236,7 +281,7 @@ using namespace pops;
 
 extern "C" size_t pops_fps_workspace_bytes(int64_t N, int64_t P, int64_t D, int64_t max_K) {
   (void)max_K;
-  if (D == 3 && P <= int64_t(16) * kFpsThreads * 8) return 256;
+  if (D == 3 && P <= int64_t(16) * kFps3Threads * kFps3MaxPT) return 256;
   return align_up(size_t(std::max<int64_t>(N, 0)) * size_t(std::max<int64_t>(P, 0)) * 4, 256) + 256;
 }
 
@@ -250,17 +295,25 @@ extern "C" int pops_sample_farthest_points(const float* points, const int64_t* l
   POPS_CHECK_ARG(points && lengths && K && start_idxs && idx, "null pointer argument");
   POPS_CHECK_ARG(P < (int64_t(1) << 31) && N < (int64_t(1) << 24), "size too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 3 && P <= int64_t(16) * kFpsThreads * 8) {
-    // smallest cluster that keeps <= 8 points per thread; widen while the batch leaves SMs idle
+  if (D == 3 && P <= int64_t(16) * kFps3Threads * kFps3MaxPT) {
+    // smallest cluster that keeps <= 32 points per thread; widen while the batch leaves SMs idle
+    // and threads still have >= 4 points (fewer, fatter threads keep the per-iteration reduction
+    // overhead small)
     int C = 1;
-    while (int64_t(C) * kFpsThreads * 8 < P) C *= 2;
+    while (int64_t(C) * kFps3Threads * kFps3MaxPT < P) C *= 2;
     const int sms = num_sms();
-    while (C < 16 && int64_t(N) * C * 2 <= sms && int64_t(C) * kFpsThreads < P) C *= 2;
-    const int per_thread = int(ceil_div(P, int64_t(C) * kFpsThreads));
-    if (per_thread <= 1) return launch_fps_d3<1>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
-    if (per_thread <= 2) return launch_fps_d3<2>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
-    if (per_thread <= 4) return launch_fps_d3<4>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
-    return launch_fps_d3<8>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st);
+    while (C < 16 && int64_t(N) * C * 2 <= sms && int64_t(C) * kFps3Threads * 4 < P) C *= 2;
+    static const int force_c = getenv("POPS_FPS_C") ? atoi(getenv("POPS_FPS_C")) : 0;  // tuning aid
+    if (force_c > 0 && int64_t(force_c) * kFps3Threads * kFps3MaxPT >= P) C = force_c;
+    const int per_thread = int(ceil_div(P, int64_t(C) * kFps3Threads));
+#define POPS_FPS(PT) return launch_fps_d3<PT>(points, lengths, K, start_idxs, int(N), int(P), int(max_K), C, idx, st)
+    if (per_thread <= 1) POPS_FPS(1);
+    if (per_thread <= 2) POPS_FPS(2);
+    if (per_thread <= 4) POPS_FPS(4);
+    if (per_thread <= 8) POPS_FPS(8);
+    if (per_thread <= 16) POPS_FPS(16);
+    POPS_FPS(32);
+#undef POPS_FPS
   }
   if (workspace_bytes < pops_fps_workspace_bytes(N, P, D, max_K) || !workspace)
     return fail(POPS_ERR_WORKSPACE, "fps: workspace missing or too small");
