@@ -148,6 +148,30 @@ int pops_gather_backward(const float* grad_out, const int64_t* idx, const int64_
                          int64_t N, int64_t M, int64_t U, int64_t L, int64_t K, int mode,
                          float* grad_x, pops_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused chamfer post-processing (additive).  Replaces the ~20 torch kernels per direction that
+ * functions/chamfer.py:114-189 runs after the K=1 search (mask, weights, knn_gather,
+ * cosine_similarity, abs, 1-x, point reduction) and their autograd mirror images.
+ *   dists (N,P1) f32 / idx (N,P1) i64: output of pops_knn_points_idx with K = 1;
+ *   weights (N) f32 or NULL;  xf[f] (N,P1,chans[f]) / yf[f] (N,P2,chans[f]): num_feats <= 8 feature
+ *   pairs (host arrays of device pointers);  point_reduction 0 none | 1 sum | 2 mean | 3 max.
+ *   forward: cham_out (N) [or (N,P1) for none], feat_out (F,N) [or (F,N,P1)], argmax_out (N) for max.
+ *   backward: g_cham / g_feat shaped like the forward outputs; grad_x (N,P1,D), grad_y (N,P2,D),
+ *   grad_xf[f], grad_yf[f] are zero-filled and written by the call (float atomics on the y side).
+ * ------------------------------------------------------------------------------------------- */
+int pops_chamfer_forward(const float* dists, const int64_t* idx, const int64_t* lengths1,
+                         const int64_t* lengths2, const float* weights, int64_t N, int64_t P1,
+                         int64_t P2, int num_feats, const float* const* xf, const float* const* yf,
+                         const int64_t* chans, int point_reduction, int abs_cosine, float* cham_out,
+                         float* feat_out, int64_t* argmax_out, pops_stream_t stream);
+int pops_chamfer_backward(const float* x, const float* y, const int64_t* idx, const int64_t* lengths1,
+                          const int64_t* lengths2, const float* weights, int64_t N, int64_t P1,
+                          int64_t P2, int64_t D, int norm, int num_feats, const float* const* xf,
+                          const float* const* yf, const int64_t* chans, int point_reduction,
+                          int abs_cosine, const float* g_cham, const float* g_feat,
+                          const int64_t* argmax, float* grad_x, float* grad_y, float* const* grad_xf,
+                          float* const* grad_yf, pops_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

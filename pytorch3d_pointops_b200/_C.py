@@ -253,3 +253,81 @@ def gather_backward(grad_out, idx, lengths, M, mode):
                                       K, int(mode), grad_x.data_ptr(), _stream(g))
     _lib.check(st, "gather_backward")
     return grad_x
+
+
+RED = {None: 0, "sum": 1, "mean": 2, "max": 3}
+
+
+def _ptr_array(tensors):
+    import ctypes
+
+    arr = (ctypes.c_void_p * max(len(tensors), 1))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _chan_array(tensors):
+    import ctypes
+
+    arr = (ctypes.c_int64 * max(len(tensors), 1))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.shape[2]
+    return arr
+
+
+def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point_reduction, abs_cosine):
+    """Fused per-direction chamfer post-processing (see include/pointops_b200.h).
+    dists/idx (N,P1) from the K=1 search; xfs/yfs lists of (N,P,C) feature tensors.
+    Returns (cham, feats (F,...) or None, argmax or None)."""
+    lib = _lib.load()
+    dists = _cuda_f32(dists, "dists")
+    idx = _cuda_i64(idx, "idx", dists)
+    N, P1 = dists.shape
+    F = len(xfs)
+    xfs = [_cuda_f32(t, "x_feature") for t in xfs]
+    yfs = [_cuda_f32(t, "y_feature") for t in yfs]
+    red = RED[point_reduction]
+    shape = (N, P1) if red == 0 else (N,)
+    cham = torch.empty(shape, dtype=torch.float32, device=dists.device)
+    feats = torch.empty((F,) + shape, dtype=torch.float32, device=dists.device) if F else None
+    argmax = torch.empty((N,), dtype=torch.int64, device=dists.device) if red == 3 else None
+    if N == 0:
+        return cham, feats, argmax
+    if weights is not None:
+        weights = _cuda_f32(weights, "weights")
+    with torch.cuda.device(dists.device):
+        st = lib.pops_chamfer_forward(dists.data_ptr(), idx.data_ptr(), lengths1.data_ptr(),
+                                      lengths2.data_ptr(), _ptr(weights), N, P1, int(P2), F,
+                                      _ptr_array(xfs), _ptr_array(yfs), _chan_array(xfs), red,
+                                      int(bool(abs_cosine)), cham.data_ptr(), _ptr(feats), _ptr(argmax),
+                                      _stream(dists))
+    _lib.check(st, "chamfer_forward")
+    return cham, feats, argmax
+
+
+def chamfer_backward(x, y, idx, lengths1, lengths2, weights, norm, xfs, yfs, point_reduction, abs_cosine,
+                     g_cham, g_feat, argmax):
+    """Returns (grad_x, grad_y, [grad_xf...], [grad_yf...])."""
+    lib = _lib.load()
+    x = _cuda_f32(x, "x")
+    y = _cuda_f32(y, "y")
+    N, P1, D = x.shape
+    P2 = y.shape[1]
+    F = len(xfs)
+    grad_x = torch.empty_like(x)
+    grad_y = torch.empty_like(y)
+    gxf = [torch.empty_like(t) for t in xfs]
+    gyf = [torch.empty_like(t) for t in yfs]
+    g_cham = _cuda_f32(g_cham, "g_cham")
+    if g_feat is not None:
+        g_feat = _cuda_f32(g_feat, "g_feat")
+    with torch.cuda.device(x.device):
+        st = lib.pops_chamfer_backward(x.data_ptr(), y.data_ptr(), idx.data_ptr(), lengths1.data_ptr(),
+                                       lengths2.data_ptr(), _ptr(weights), N, P1, P2, D, int(norm), F,
+                                       _ptr_array(xfs), _ptr_array(yfs), _chan_array(xfs),
+                                       RED[point_reduction], int(bool(abs_cosine)), g_cham.data_ptr(),
+                                       _ptr(g_feat), _ptr(argmax), grad_x.data_ptr(), grad_y.data_ptr(),
+                                       _ptr_array(gxf), _ptr_array(gyf), _stream(x))
+    _lib.check(st, "chamfer_backward")
+    return grad_x, grad_y, gxf, gyf

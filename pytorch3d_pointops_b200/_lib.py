@@ -36,6 +36,9 @@ SIGNATURES = {
     "pops_padded_to_packed": (c_int, [_P, _P] + [c_int64] * 4 + [_P, _P]),
     "pops_gather": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P, _P]),
     "pops_gather_backward": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P]),
+    "pops_chamfer_forward": (c_int, [_P] * 5 + [c_int64] * 3 + [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "pops_chamfer_backward": (c_int, [_P] * 6 + [c_int64] * 4 + [c_int, c_int, _P, _P, _P, c_int, c_int]
+                              + [_P] * 8),
 }
 
 

@@ -1,16 +1,16 @@
 """chamfer_distance with per-feature cosine losses (reference: functions/chamfer.py:217-365).
 
-Same signature, validation, return structure and numerics contract as the reference.  The
-nearest-neighbour searches run on the K=1 specialisation of the sm_100a KNN kernel; the
-neighbour features are fetched with the fused gather kernel.
+Same signature, validation, return structure and numerics contract as the reference.  Each
+direction is one autograd Function of two fused kernels around the K=1 search of the sm_100a KNN
+kernel (mask, weights, neighbour-feature gather, cosine terms and point reduction in one pass;
+distance and cosine gradients with their index scatters in another).
 """
 from typing import Union
 
 import torch
-import torch.nn.functional as F
 
 from ..structures.point_structure import Pointclouds
-from .knn import _C, _gather_rows, knn_points
+from .. import _C
 
 
 def _validate_chamfer_reduction_inputs(
@@ -60,6 +60,46 @@ def _handle_pointcloud_input(
     return points, lengths, features
 
 
+class _ChamferDirection(torch.autograd.Function):
+    """x -> y half of the chamfer loss as two fused kernels around the K=1 search.
+
+    forward : _C.knn_points_idx (K=1) + _C.chamfer_forward (mask, weights, neighbour-feature
+              gather, cosine terms, point reduction);
+    backward: _C.chamfer_backward (distance gradient to x and scatter to y[idx], cosine chain rule
+              to x features and scatter to y features[idx]).
+    Outputs: cham (N,) [(N,P1) when point_reduction is None], then one tensor per feature.
+    """
+
+    @staticmethod
+    def forward(ctx, x, y, x_lengths, y_lengths, weights, norm, point_reduction, abs_cosine, nfeat,
+                *feats):
+        xfs, yfs = list(feats[:nfeat]), list(feats[nfeat:])
+        idx, dists = _C.knn_points_idx(x, y, x_lengths, y_lengths, norm, 1, -1)
+        N, P1 = x.shape[0], x.shape[1]
+        cham, fo, argmax = _C.chamfer_forward(dists.view(N, P1), idx.view(N, P1), x_lengths, y_lengths,
+                                              weights, y.shape[1], xfs, yfs, point_reduction, abs_cosine)
+        ctx.save_for_backward(x, y, x_lengths, y_lengths, idx, *xfs, *yfs)
+        ctx.weights, ctx.argmax = weights, argmax
+        ctx.cfg = (norm, point_reduction, abs_cosine, nfeat)
+        return (cham,) + tuple(fo[f] for f in range(nfeat))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_cham, *g_feats):
+        norm, point_reduction, abs_cosine, nfeat = ctx.cfg
+        x, y, x_lengths, y_lengths, idx = ctx.saved_tensors[:5]
+        xfs = list(ctx.saved_tensors[5:5 + nfeat])
+        yfs = list(ctx.saved_tensors[5 + nfeat:])
+        N, P1 = x.shape[0], x.shape[1]
+        g_feat = None
+        if nfeat:
+            g_feat = torch.stack([g if g is not None else torch.zeros_like(g_cham) for g in g_feats], 0)
+        gx, gy, gxf, gyf = _C.chamfer_backward(x, y, idx.view(N, P1), x_lengths, y_lengths, ctx.weights,
+                                               norm, xfs, yfs, point_reduction, abs_cosine,
+                                               g_cham.contiguous(), g_feat, ctx.argmax)
+        return (gx, gy, None, None, None, None, None, None, None) + tuple(gxf) + tuple(gyf)
+
+
 def _chamfer_distance_single_direction(
     x, y, x_lengths, y_lengths, x_features, y_features, weights,
     point_reduction: Union[str, None], norm: int, abs_cosine: bool,
@@ -67,7 +107,8 @@ def _chamfer_distance_single_direction(
 ):
     """x -> y half of the loss (reference :85-189): NN distance of every x point, optional
     per-feature 1 - |cos| to the neighbour's feature, masks for ragged clouds, batch weights,
-    and the reduction over points."""
+    and the reduction over points.  Validation as in the reference; the computation itself is
+    `_ChamferDirection`."""
     if feature_names and x_features is not None and y_features is not None:
         for name in feature_names:
             if name not in x_features:
@@ -89,42 +130,19 @@ def _chamfer_distance_single_direction(
         if weights.sum() == 0.0:
             w = weights.view(N, 1)
             return ((x.sum((1, 2)) * w) * 0.0, (x.sum((1, 2)) * w) * 0.0)
-
-    # padded rows already come back as exact zeros from the kernel (rows >= lengths1 are
-    # (0, 0)), so the reference's host-synchronising `is_x_heterogeneous` test is not needed;
-    # the mask is applied unconditionally to the feature terms.
-    x_mask = torch.arange(P1, device=x.device)[None] >= x_lengths[:, None]
-    nn = knn_points(x, y, lengths1=x_lengths, lengths2=y_lengths, norm=norm, K=1)
-    cham_x = nn.dists[..., 0]
-    if weights is not None:
-        cham_x = cham_x * weights.view(N, 1)
-
-    cham_feat = None
-    if with_features:
-        cham_feat = {}
-        for name in feature_names:
-            near = _gather_rows.apply(y_features[name].contiguous(), nn.idx, y_lengths,
-                                      _C.GATHER_KNN, None)[..., 0, :]
-            cos = F.cosine_similarity(x_features[name], near, dim=2, eps=1e-6)
-            cos = torch.abs(cos) if abs_cosine else cos
-            dist = (1 - cos).masked_fill(x_mask, 0.0)
-            if weights is not None:
-                dist = dist * weights.view(N, 1)
-            cham_feat[name] = dist
-
     if point_reduction == "max":
         assert not with_features
-        cham_x = cham_x.max(1).values
-    elif point_reduction is not None:
-        cham_x = cham_x.sum(1)
-        if with_features:
-            cham_feat = {k: v.sum(1) for k, v in cham_feat.items()}
-        if point_reduction == "mean":
-            denom = x_lengths.clamp(min=1)
-            cham_x = cham_x / denom
-            if with_features:
-                cham_feat = {k: v / denom for k, v in cham_feat.items()}
-    return cham_x, cham_feat
+    names = list(feature_names) if with_features else []
+    if len(names) > 8:
+        raise ValueError("at most 8 feature names are supported per call")
+    xfs = [x_features[n].contiguous() for n in names]
+    yfs = [y_features[n].contiguous() for n in names]
+    out = _ChamferDirection.apply(
+        x.contiguous(), y.contiguous(), x_lengths, y_lengths,
+        None if weights is None else weights.detach().float().contiguous(),
+        norm, point_reduction, bool(abs_cosine), len(names), *xfs, *yfs)
+    cham_feat = {n: out[1 + i] for i, n in enumerate(names)} if with_features else None
+    return out[0], cham_feat
 
 
 def _apply_batch_reduction(cham_x, cham_features_x, weights, batch_reduction: Union[str, None]):

@@ -80,8 +80,11 @@ def test_exact_kernels_have_no_fused_multiply_add():
         if "Function :" in line:
             fn = line.split("Function :")[1].strip()
         elif fn and re.search(r"\bFFMA2?\b", line):
-            exact = ("knn_scan_kernelILi" in fn and "ELb0E" in fn) or "knn_generic_kernel" in fn \
-                or "ball_query_generic" in fn or "fps_generic" in fn or "knn_backward" in fn
+            # knn_scan_kernel<DT,NORM,EXP,...>: EXP=false variants scan with the exact distance;
+            # knn_flush_one (every variant) re-evaluates candidates exactly
+            exact = re.search(r"knn_scan_kernelILi\d+ELi\d+ELb0", fn) or "knn_flush_one" in fn \
+                or "knn_generic_kernel" in fn or "ball_query_generic" in fn or "fps_" in fn \
+                or "knn_backward" in fn
             if exact:
                 bad.append(fn)
     assert not bad, sorted(set(bad))
