@@ -190,20 +190,28 @@ def cpu_reference_rate(p, lengths, budget_s: float, workers: int):
     # calibrate on one core: 128 queries of cloud 0
     n, dt = _ref_worker((0, 0, 128, use_ref))
     rate1 = n / max(dt, 1e-6)
-    per_worker = int(max(64, min(P, rate1 * budget_s)))
-    jobs = [((w % B), 0, per_worker, use_ref) for w in range(workers)]
+    per_worker = int(max(64, rate1 * budget_s))          # queries one core finishes in the budget
+    # split into whole-cloud-sized jobs: worker w walks clouds w, w+workers, ...
+    jobs = []
+    for w in range(workers):
+        left, c = per_worker, w
+        while left > 0:
+            q = min(left, P)
+            jobs.append((c % B, 0, q, use_ref))
+            left -= q
+            c += workers
     t0 = time.perf_counter()
     if workers == 1:
-        res = [_ref_worker(jobs[0])]
+        res = [_ref_worker(j) for j in jobs]
     else:
         ctx = mp.get_context("fork")  # workers inherit the tensors and the loaded module
         with ctx.Pool(workers) as pool:
-            res = pool.map(_ref_worker, jobs)
+            res = pool.map(_ref_worker, jobs, chunksize=max(1, len(jobs) // workers))
     wall = time.perf_counter() - t0
     total_q = sum(r[0] for r in res)
     kind = "reference" if use_ref else "port"
-    sample = (f"{workers} worker(s) x {per_worker} queries of one cloud each against the full "
-              f"P2={P} (K={K_NN}, D={D}); native loop is single-threaded per call")
+    sample = (f"{workers} worker process(es) x {per_worker} queries (whole clouds of the batch, each query "
+              f"against the full P2={P}; K={K_NN}, D={D}); the reference's native loop is single-threaded")
     return total_q / wall, kind, sample, wall
 
 
@@ -428,7 +436,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1,0 +1,116 @@
+"""Multi-GPU use of the hot path: shard by cloud, one process per GPU.
+
+Every op of the path is independent per cloud (the outer `for n` of every reference loop, e.g.
+csrc/knn/knn_cpu.cpp:35), so a batch shards across ranks with NO data-path collective:
+each rank runs the single-GPU kernels on its contiguous slice of the batch.  Only two things cross
+NVLink (NCCL through torch.distributed):
+
+* `chamfer_distance_sharded`: one all-reduce (sum) of `1 + len(feature_names)` scalars, so every
+  rank returns the global loss; gradients need no exchange (each rank owns its clouds);
+* `all_gather_clouds`: optional gather of per-cloud outputs (idx, dists, FPS indices) to all ranks.
+
+The reference has no distributed code ("Parallelism strategies ... none"); this is
+new functionality layered on the unchanged single-GPU API.
+"""
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(costs: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) slices of range(len(costs)), one per rank, balancing sum(costs).
+
+    costs[n] ~ work of cloud n (lengths1*lengths2 for search ops, K*lengths for FPS).  Greedy on
+    the prefix sum: rank r ends where the prefix first reaches (r+1)/world of the total.  Uniform
+    costs give the even split N/world (remainder to the first ranks).
+    """
+    n = len(costs)
+    total = float(sum(costs))
+    if n == 0:
+        return [(0, 0)] * world_size
+    if total <= 0:
+        costs, total = [1.0] * n, float(n)
+    prefix, acc = [], 0.0
+    for c in costs:
+        acc += float(c)
+        prefix.append(acc)
+    cuts = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        i = cuts[-1]
+        # number of clouds in the first r shards: the prefix closest to the target
+        while i < n and prefix[i] <= target:
+            i += 1
+        if i < n and i > cuts[-1] and (prefix[i] - target) < (target - prefix[i - 1]):
+            i += 1
+        elif i == cuts[-1] and i < n and (prefix[i] - target) < (target - (prefix[i - 1] if i else 0.0)):
+            i += 1
+        cuts.append(min(i, n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
+def my_slice(n_clouds: int, rank: Optional[int] = None, world_size: Optional[int] = None,
+             costs: Optional[Sequence[float]] = None) -> Tuple[int, int]:
+    """This rank's [lo, hi) slice of a batch of n_clouds."""
+    rank = dist.get_rank() if rank is None else rank
+    world_size = dist.get_world_size() if world_size is None else world_size
+    return shard_bounds(list(costs) if costs is not None else [1.0] * n_clouds, world_size)[rank]
+
+
+def all_gather_clouds(local: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate per-rank tensors along dim 0 (shards may differ in size) on every rank."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    sizes = [torch.zeros((), dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor(local.shape[0], dtype=torch.int64, device=local.device), group=group)
+    sizes = [int(s) for s in sizes]
+    biggest = max(sizes)
+    padded = local.new_zeros((biggest,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+def chamfer_distance_sharded(x, y, x_lengths=None, y_lengths=None, x_features=None, y_features=None,
+                             weights=None, batch_reduction: Optional[str] = "mean",
+                             point_reduction: Optional[str] = "mean", norm: int = 2,
+                             single_directional: bool = False, abs_cosine: bool = True,
+                             feature_names: Optional[list] = None, n_clouds_global: Optional[int] = None,
+                             group=None, _local_fn: Optional[Callable] = None):
+    """`chamfer_distance` over a batch sharded by cloud: every argument is this rank's shard.
+
+    batch_reduction "mean"/"sum": the global reduced loss on every rank (one all-reduce of
+    1 + len(feature_names) scalars; the divisor of "mean" is the global cloud count, or the global
+    sum of weights, as in functions/chamfer.py:203-213).  Gradients flow to the local shard only.
+    batch_reduction None: the local per-cloud results (use `all_gather_clouds` to collect them).
+    `_local_fn` lets tests substitute the single-process implementation.
+    """
+    if _local_fn is None:
+        from .functions.chamfer import chamfer_distance as _local_fn
+    if batch_reduction is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return _local_fn(x, y, x_lengths, y_lengths, x_features, y_features, weights, batch_reduction,
+                         point_reduction, norm, single_directional, abs_cosine, feature_names)
+    loss, feats = _local_fn(x, y, x_lengths, y_lengths, x_features, y_features, weights, "sum",
+                            point_reduction, norm, single_directional, abs_cosine, feature_names)
+    names = sorted(feats) if feats is not None else []
+    local = torch.stack([loss] + [feats[k] for k in names])
+    n_local = x.shape[0] if torch.is_tensor(x) else len(x)
+    div_local = float(n_local) if weights is None else float(weights.sum())
+    packed = torch.cat([local.detach(), local.new_tensor([div_local])])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    total, div = packed[:-1], packed[-1]
+    if batch_reduction == "mean":
+        if weights is None:
+            div = local.new_tensor(float(max(n_clouds_global, 1))) if n_clouds_global is not None else div.clamp(min=1)
+        else:
+            div = torch.where(div == 0, torch.ones_like(div), div)
+    else:
+        div = torch.ones_like(div)
+    # value = global sum / div;  gradient = d(local sum)/div  (other ranks' terms are constants)
+    out = (local + (total - local.detach())) / div
+    out_feats = {k: out[1 + i] for i, k in enumerate(names)} if feats is not None else None
+    return out[0], out_feats
