@@ -26,16 +26,9 @@
 #include <cfloat>
 #include <cstdlib>
 
-#include "common.cuh"
-#include "knn_order.cuh"
+#include "knn_core.cuh"
 
 namespace pops {
-
-constexpr int kGroup = 4;             // points per filter group (one float4 per SoA row)
-constexpr int kChunk = 4;             // groups between candidate-buffer overflow checks
-constexpr int kPadPoints = kGroup * kChunk;  // SoA rows padded to a multiple of this
-constexpr int kSurvCap = 16;           // survivor keys a lane may hold between two merges
-constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
 // ---------------------------------------------------------------------------------------------
 // pack pass
@@ -109,27 +102,14 @@ struct KnnScanParams {
   int64_t* idx;
   float* dists;
   int P1, P2, P2pad, K;
-  // ordered (Morton) variant only
-  const float4* qsorted;   // [N][P1] x,y,z,orig-index bits, Morton order
-  const unsigned* qhome;   // [N][P1] home position of the query in the sorted p2
 };
-
-// k-th element of the "outward from s" visiting order of 0..n-1:  s, s+1, s-1, s+2, ... and, once
-// one side is exhausted, the rest of the other side moving away from s.
-__host__ __device__ __forceinline__ int outward_seq(int k, int s, int n) {
-  const int m = min(s, n - 1 - s);
-  if (k <= 2 * m) return (k & 1) ? s + ((k + 1) >> 1) : s - (k >> 1);
-  return (s - m == 0) ? k : n - 1 - k;
-}
-
-constexpr int kBufCap = 16;  // candidate buffer capacity (groups) per query
 
 // Shared-memory carve-up.  RS = points per tile row (compile time, so tile loads in the hot loop
 // are immediate-offset LDS.128).  ONE tile stage: the TMA refill of a CTA overlaps with the other
 // resident CTA's compute; a single large tile halves the number of forced end-of-tile flushes.
-template <int DT, bool EXP, bool ORD, bool GL, int Q, int THREADS, int RS>
+template <int DT, bool EXP, bool GL, int Q, int THREADS, int RS>
 struct KnnSmem {
-  static constexpr int ROWS = DT + (EXP ? 1 : 0) + (ORD ? 1 : 0);  // ORD: + original-index row
+  static constexpr int ROWS = DT + (EXP ? 1 : 0);
   static constexpr int QPB = Q * THREADS;
   static constexpr size_t tiles_off = 64;
   static constexpr size_t tiles_bytes = size_t(ROWS) * RS * 4 + 64;  // +64: the prefetch over-read
@@ -143,252 +123,11 @@ struct KnnSmem {
   static __host__ __device__ size_t total(int K) { return surv_off(K) + surv_bytes; }
 };
 
-// ---- register sorting networks on 64-bit keys ------------------------------------------------
-__device__ __forceinline__ void ce64(uint64_t& lo, uint64_t& hi) {  // lo <- min, hi <- max
-  const bool sw = hi < lo;
-  const uint64_t a = sw ? hi : lo, b = sw ? lo : hi;
-  lo = a;
-  hi = b;
-}
-
-// Batcher odd-even merge sort of 16 keys: 63 compare-exchanges (pairs generated offline and
-// verified with the 0-1 principle); constexpr tables so that every index resolves statically.
-constexpr int kSort16N = 63;
-__device__ constexpr unsigned char kSort16A[kSort16N] = {0,2,4,6,8,10,12,14,0,1,4,5,8,9,12,13,1,5,9,13,0,1,2,3,8,9,10,11,2,3,10,11,1,3,5,9,11,13,0,1,2,3,4,5,6,7,4,5,6,7,2,3,6,7,10,11,1,3,5,7,9,11,13};
-__device__ constexpr unsigned char kSort16B[kSort16N] = {1,3,5,7,9,11,13,15,2,3,6,7,10,11,14,15,2,6,10,14,4,5,6,7,12,13,14,15,4,5,12,13,2,4,6,10,12,14,8,9,10,11,12,13,14,15,8,9,10,11,4,5,8,9,12,13,2,4,6,8,10,12,14};
-__device__ __forceinline__ void sort16(uint64_t (&v)[16]) {
-#pragma unroll
-  for (int e = 0; e < kSort16N; ++e) ce64(v[kSort16A[e]], v[kSort16B[e]]);
-}
-
-// v is bitonic -> ascending
-template <int N>
-__device__ __forceinline__ void bitonic_merge(uint64_t (&v)[N]) {
-#pragma unroll
-  for (int k = N / 2; k >= 1; k /= 2) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      if ((i & k) == 0) ce64(v[i], v[i + k]);
-    }
-  }
-}
-
-// sorted insertion of one key into the ascending register list (branch-free, all compares
-// against the OLD list, so the KT steps are independent)
-template <int KT>
-__device__ __forceinline__ void insert_network(uint64_t (&Lr)[KT], uint64_t key) {
-  bool lt[KT];
-#pragma unroll
-  for (int k = 0; k < KT; ++k) lt[k] = key < Lr[k];
-#pragma unroll
-  for (int k = KT - 1; k >= 1; --k) Lr[k] = lt[k - 1] ? Lr[k - 1] : (lt[k] ? key : Lr[k]);
-  Lr[0] = lt[0] ? key : Lr[0];
-}
-
-static_assert(kSurvCap == 16, "sort16 assumes 16 survivor slots");
-
-// ---------------------------------------------------------------------------------------------
-// flush: drain ONE query's candidate buffer.  A real (non-inlined) function: it is big, runs
-// rarely, and must exist once, not once per call site and query slot -- the scan loop has to stay
-// resident in the instruction cache.  Called warp-converged and kept converged inside: rare events
-// never sit inside a dense loop.
-//   fill   per buffered group, all 4 points get the exact unfused distance (branch-free, packed
-//          f32x2 sub/mul, scalar adds -- IEEE, never fused); points with d <= dk are appended as
-//          64-bit keys to the lane's survivor column (predicated);
-//   merge  KT > 0: the list (kept in the OUTPUT arrays) is pulled into registers by the lanes that
-//          hold survivors; few survivors -> branch-free insertion network per survivor, many ->
-//          sort network + bitonic merge.  KT == 0 (any K): sorted survivors are merged backward in
-//          place into the shared-memory list.
-// Returns the query's new K-th distance (+inf while the list is not full).
-template <int DT, int NORM, bool EXP, bool ORD, int THREADS, int KT, int RS, int QPB>
-__device__ __noinline__ float knn_flush_one(const float* tile, const unsigned short* cand_col, int c_end,
-                                            uint64_t* L, uint64_t* S, float4 qv, float dkt, int j0,
-                                            int L2, int K, float* od, int64_t* oi) {
-  if (!__any_sync(0xffffffffu, c_end > 0)) return dkt;
-  const float qarr[4] = {qv.x, qv.y, qv.z, qv.w};
-  float q[DT];
-#pragma unroll
-  for (int d = 0; d < DT; ++d) q[d] = qarr[d];
-  constexpr bool GL = KT > 0;
-  constexpr int IDXROW = DT + 1;
-  const float INF = __int_as_float(0x7f800000);
-    int c = 0;
-    for (;;) {
-      if (!__any_sync(0xffffffffu, c < c_end)) break;
-      // ---- fill ----
-      int ns = 0;
-      while (c < c_end && ns <= kSurvCap - kGroup) {
-        const int g = cand_col[c * QPB];
-        ++c;
-        float4 X[DT];
-#pragma unroll
-        for (int d = 0; d < DT; ++d) X[d] = reinterpret_cast<const float4*>(tile + d * RS)[g];
-        float dist[kGroup];
-        if (NORM == 2) {
-          float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int d = 0; d < DT; ++d) {
-            const float2 qd = make_float2(q[d], q[d]);
-            const float2 d01 = __fadd2_rn(qd, make_float2(-X[d].x, -X[d].y));
-            const float2 d23 = __fadd2_rn(qd, make_float2(-X[d].z, -X[d].w));
-            const float2 t01 = __fmul2_rn(d01, d01), t23 = __fmul2_rn(d23, d23);
-            // scalar adds on purpose: ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2
-            // (even with -fmad=false), which would break bit parity with the unfused reference
-            acc01 = d == 0 ? t01 : make_float2(__fadd_rn(acc01.x, t01.x), __fadd_rn(acc01.y, t01.y));
-            acc23 = d == 0 ? t23 : make_float2(__fadd_rn(acc23.x, t23.x), __fadd_rn(acc23.y, t23.y));
-          }
-          dist[0] = acc01.x; dist[1] = acc01.y; dist[2] = acc23.x; dist[3] = acc23.y;
-        } else {
-#pragma unroll
-          for (int i = 0; i < kGroup; ++i) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int d = 0; d < DT; ++d) {
-              const float xv = i == 0 ? X[d].x : (i == 1 ? X[d].y : (i == 2 ? X[d].z : X[d].w));
-              const float term = dist_term<NORM>(q[d], xv);
-              acc = (d == 0) ? term : __fadd_rn(acc, term);
-            }
-            dist[i] = acc;
-          }
-        }
-        const int jg = j0 + g * kGroup;
-        uint4 pix = make_uint4(jg, jg + 1, jg + 2, jg + 3);  // original point indices
-        if (ORD) pix = reinterpret_cast<const uint4*>(tile + IDXROW * RS)[g];
-        const unsigned oix[kGroup] = {pix.x, pix.y, pix.z, pix.w};
-#pragma unroll
-        for (int i = 0; i < kGroup; ++i) {
-          const bool real = ORD ? (oix[i] != kNoPoint) : (jg + i < L2);
-          if (dist[i] <= dkt && real) {
-            S[ns * THREADS] = make_key(dist[i], oix[i]);
-            ++ns;
-          }
-        }
-      }
-      __syncwarp();
-      // ---- merge ----
-      const int ns_max = __reduce_max_sync(0xffffffffu, ns);
-      if (ns_max > 0) {
-        if (KT > 0) {
-          constexpr int KR = KT > 0 ? KT : 1;
-          uint64_t Lr[KR];
-          const bool mine = ns > 0;  // only lanes that hold survivors touch their list
-#pragma unroll
-          for (int k = 0; k < KR; ++k) Lr[k] = kEmptyKey;
-          if (mine) {
-            if (KR >= 4 && (K & 3) == 0) {  // rows are 16-byte aligned: 128-bit loads
-#pragma unroll
-              for (int k4 = 0; k4 < KR / 4; ++k4) {
-                if (k4 * 4 < K) {
-                  const float4 dv = reinterpret_cast<const float4*>(od)[k4];
-                  const longlong2 i01 = reinterpret_cast<const longlong2*>(oi)[k4 * 2];
-                  const longlong2 i23 = reinterpret_cast<const longlong2*>(oi)[k4 * 2 + 1];
-                  Lr[k4 * 4 + 0] = make_key(dv.x, static_cast<uint32_t>(i01.x));
-                  Lr[k4 * 4 + 1] = make_key(dv.y, static_cast<uint32_t>(i01.y));
-                  Lr[k4 * 4 + 2] = make_key(dv.z, static_cast<uint32_t>(i23.x));
-                  Lr[k4 * 4 + 3] = make_key(dv.w, static_cast<uint32_t>(i23.y));
-                }
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < KR; ++k)
-                if (k < K) Lr[k] = make_key(od[k], static_cast<uint32_t>(oi[k]));
-            }
-          }
-          if (ns_max <= 5 || KR < 4) {
-            for (int s2 = 0; s2 < ns_max; ++s2) {
-              const uint64_t key = (s2 < ns) ? S[s2 * THREADS] : kEmptyKey;
-              insert_network<KR>(Lr, key);
-            }
-          } else {
-            uint64_t Sr[kSurvCap];
-#pragma unroll
-            for (int s2 = 0; s2 < kSurvCap; ++s2) Sr[s2] = (s2 < ns) ? S[s2 * THREADS] : kEmptyKey;
-            sort16(Sr);
-            // K smallest of (Lr U Sr): C[i] = min(Lr[i], Sr[KR-1-i]) is bitonic, then merge
-#pragma unroll
-            for (int i = 0; i < KR; ++i) {
-              const int si = KR - 1 - i;
-              if (si < kSurvCap) Lr[i] = (Sr[si] < Lr[i]) ? Sr[si] : Lr[i];
-            }
-            bitonic_merge<KR>(Lr);
-          }
-          if (mine) {
-            if (KR >= 4 && (K & 3) == 0) {
-#pragma unroll
-              for (int k4 = 0; k4 < KR / 4; ++k4) {
-                if (k4 * 4 < K) {
-                  reinterpret_cast<float4*>(od)[k4] =
-                      make_float4(key_dist(Lr[k4 * 4]), key_dist(Lr[k4 * 4 + 1]), key_dist(Lr[k4 * 4 + 2]),
-                                  key_dist(Lr[k4 * 4 + 3]));
-                  reinterpret_cast<longlong2*>(oi)[k4 * 2] =
-                      make_longlong2(static_cast<long long>(Lr[k4 * 4] & 0xFFFFFFFFull),
-                                     static_cast<long long>(Lr[k4 * 4 + 1] & 0xFFFFFFFFull));
-                  reinterpret_cast<longlong2*>(oi)[k4 * 2 + 1] =
-                      make_longlong2(static_cast<long long>(Lr[k4 * 4 + 2] & 0xFFFFFFFFull),
-                                     static_cast<long long>(Lr[k4 * 4 + 3] & 0xFFFFFFFFull));
-                }
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < KR; ++k) {
-                if (k < K) {
-                  od[k] = key_dist(Lr[k]);
-                  oi[k] = static_cast<int64_t>(Lr[k] & 0xFFFFFFFFull);
-                }
-              }
-            }
-            uint64_t worst = kEmptyKey;
-#pragma unroll
-            for (int k = 0; k < KR; ++k)
-              if (k == K - 1) worst = Lr[k];
-            dkt = key_dist(worst);  // +inf while the list is not full
-          }
-        } else if (ns > 0) {
-          for (int a2 = 1; a2 < ns; ++a2) {  // insertion sort of the survivors
-            const uint64_t key = S[a2 * THREADS];
-            int b2 = a2 - 1;
-            while (b2 >= 0) {
-              const uint64_t prev = S[b2 * THREADS];
-              if (prev <= key) break;
-              S[(b2 + 1) * THREADS] = prev;
-              --b2;
-            }
-            S[(b2 + 1) * THREADS] = key;
-          }
-          int r = 0;  // survivors that belong to the K smallest of (list U survivors)
-          while (r < ns && r < K && S[r * THREADS] < L[static_cast<size_t>(K - 1 - r) * QPB]) ++r;
-          int i = K - 1 - r, jj = r - 1, o = K - 1;  // backward in-place merge
-          while (jj >= 0) {
-            const uint64_t sv = S[jj * THREADS];
-            uint64_t lv = 0;
-            if (i >= 0) lv = L[static_cast<size_t>(i) * QPB];
-            if (i >= 0 && lv > sv) {
-              L[static_cast<size_t>(o) * QPB] = lv;
-              --i;
-            } else {
-              L[static_cast<size_t>(o) * QPB] = sv;
-              --jj;
-            }
-            --o;
-          }
-          const uint64_t worst = L[static_cast<size_t>(K - 1) * QPB];
-          if (worst != kEmptyKey) dkt = key_dist(worst);
-        }
-      }
-      __syncwarp();
-    }
-    return dkt;
-}
-
-
-
-template <int DT, int NORM, bool EXP, bool ORD, int Q, int THREADS, int KT, int RS>
+template <int DT, int NORM, bool EXP, int Q, int THREADS, int KT, int RS>
 __global__ void __launch_bounds__(THREADS, (THREADS > 192 ? 1 : ((KT > 0 && KT <= 16) ? 3 : 2)))
 knn_scan_kernel(const KnnScanParams prm) {
-  static_assert(!ORD || (EXP && DT == 3), "the ordered variant is the D=3 L2 kernel");
   constexpr bool GL = KT > 0;  // register-merge variants keep their lists in the output arrays
-  using SM = KnnSmem<DT, EXP, ORD, GL, Q, THREADS, RS>;
-  constexpr int IDXROW = DT + 1;  // ORD: tile row holding the original point indices
+  using SM = KnnSmem<DT, EXP, GL, Q, THREADS, RS>;
   constexpr int ROWS = SM::ROWS;
   constexpr int QPB = SM::QPB;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -408,8 +147,7 @@ knn_scan_kernel(const KnnScanParams prm) {
   if (q_base >= L1 || L2 == 0) {
     const int rows = min(QPB, prm.P1 - q_base);
     for (int e = tid; e < rows * K; e += THREADS) {
-      size_t row = static_cast<size_t>(q_base) + e / K;
-      if (ORD) row = __float_as_uint(prm.qsorted[static_cast<size_t>(n) * prm.P1 + row].w);
+      const size_t row = static_cast<size_t>(q_base) + e / K;
       out_idx[row * K + e % K] = 0;
       out_d[row * K + e % K] = 0.0f;
     }
@@ -425,20 +163,6 @@ knn_scan_kernel(const KnnScanParams prm) {
   const int L2pad = (L2 + kPadPoints - 1) / kPadPoints * kPadPoints;  // <= P2pad
   const int num_tiles = (L2pad + RS - 1) / RS;
   const float* soa_n = prm.soa + static_cast<size_t>(n) * ROWS * P2pad;
-
-  // Thread -> query slots.  ORD: a warp's Q*32 queries are contiguous in Morton order.
-  constexpr int SLOT_STRIDE = ORD ? 32 : THREADS;
-  const int slot0 = ORD ? (tid >> 5) * (Q * 32) + (tid & 31) : tid;
-
-  // ORD: tiles are visited outward from the tile that holds the CTA's own neighbourhood
-  int tile_h = 0, warp_home = 0;
-  if (ORD) {
-    const int nvalid = min(QPB, L1 - q_base);
-    const unsigned* qh = prm.qhome + static_cast<size_t>(n) * prm.P1 + q_base;
-    tile_h = min(static_cast<int>(qh[nvalid >> 1]) / RS, num_tiles - 1);
-    const int wmid = min((tid >> 5) * (Q * 32) + Q * 16, nvalid - 1);
-    warp_home = static_cast<int>(qh[wmid]);
-  }
 
   auto issue_tile = [&](int tile) {
     const int j0 = tile * RS;
@@ -456,7 +180,7 @@ knn_scan_kernel(const KnnScanParams prm) {
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) issue_tile(ORD ? tile_h : 0);
+  if (tid == 0) issue_tile(0);
 
   // ---- per-thread query state ---------------------------------------------------------------
   const float M = __uint_as_float(prm.maxabs_bits[n]);
@@ -469,41 +193,28 @@ knn_scan_kernel(const KnnScanParams prm) {
   float T[Q];       // filter threshold
   float dk[Q];      // current K-th distance (+inf while the list is not full)
   uint32_t cw[Q];   // shared-memory byte address of the next free candidate slot
-  const uint32_t cand_base = smem_u32(cand) + static_cast<uint32_t>(slot0) * 2u;
-  unsigned orow[Q];  // output row (original query index)
+  const uint32_t cand_base = smem_u32(cand) + static_cast<uint32_t>(tid) * 2u;
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
-    const int slot = slot0 + t * SLOT_STRIDE;
+    const int slot = tid + t * THREADS;
     const int qi = q_base + slot;
     const bool valid = qi < L1;
-    float qv[DT];
-    orow[t] = static_cast<unsigned>(qi);
-    if (ORD) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (qi < prm.P1) v = prm.qsorted[static_cast<size_t>(n) * prm.P1 + qi];
-      qv[0] = v.x; qv[1 % DT] = v.y; qv[2 % DT] = v.z;
-      orow[t] = __float_as_uint(v.w);
-    } else {
-#pragma unroll
-      for (int d = 0; d < DT; ++d)
-        qv[d] = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
-    }
     float s = 0.0f;
 #pragma unroll
     for (int d = 0; d < DT; ++d) {
-      const float q = valid ? qv[d] : 0.0f;
+      const float q = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * DT + d] : 0.0f;
       s = fmaf(q, q, s);
       a[t][d] = EXP ? -2.0f * q : q;
     }
     qq[t] = s;
     dk[t] = valid ? INF : -1.0f;
     T[t] = valid ? (EXP ? FLT_MAX : INF) : -INF;
-    cw[t] = cand_base + static_cast<uint32_t>(t) * (SLOT_STRIDE * 2u);
+    cw[t] = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
     if (GL) {
       // empty list = (+inf, 0xFFFFFFFF) in every slot; rows beyond lengths1 are final zeros
       if (qi < prm.P1) {
-        float* od = out_d + static_cast<size_t>(orow[t]) * K;
-        int64_t* oi = out_idx + static_cast<size_t>(orow[t]) * K;
+        float* od = out_d + static_cast<size_t>(qi) * K;
+        int64_t* oi = out_idx + static_cast<size_t>(qi) * K;
         for (int k = 0; k < K; ++k) {
           od[k] = valid ? INF : 0.0f;
           oi[k] = valid ? static_cast<int64_t>(0xFFFFFFFFll) : 0;
@@ -514,10 +225,10 @@ knn_scan_kernel(const KnnScanParams prm) {
     }
   }
 
-  // ---- flush glue: drain query t's candidate buffer (knn_flush_one, defined above) ---------------
+  // ---- flush glue: drain query t's candidate buffer (knn_flush_one, knn_core.cuh) ---------------
   auto flush = [&](int t, const float* tile, int j0) {
-    const int slot = slot0 + t * SLOT_STRIDE;
-    const uint32_t base = cand_base + static_cast<uint32_t>(t) * (SLOT_STRIDE * 2u);
+    const int slot = tid + t * THREADS;
+    const uint32_t base = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
     const int c_end = static_cast<int>((cw[t] - base) / CSTRIDE);
     cw[t] = base;
     float4 qv;  // a = -2q exactly (power-of-two scaling), so q = -a/2 exactly
@@ -525,66 +236,32 @@ knn_scan_kernel(const KnnScanParams prm) {
     qv.y = EXP ? -0.5f * a[t][1 % DT] : a[t][1 % DT];
     qv.z = EXP ? -0.5f * a[t][2 % DT] : a[t][2 % DT];
     qv.w = EXP ? -0.5f * a[t][3 % DT] : a[t][3 % DT];
-    const float dkt = knn_flush_one<DT, NORM, EXP, ORD, THREADS, KT, RS, QPB>(
+    const int qi = q_base + slot;
+    const float dkt = knn_flush_one<DT, NORM, EXP, THREADS, KT, RS, QPB>(
         tile, cand + slot, c_end, GL ? nullptr : lists + slot, surv + tid, qv, dk[t], j0, L2, K,
-        out_d + static_cast<size_t>(orow[t]) * K, out_idx + static_cast<size_t>(orow[t]) * K);
+        out_d + static_cast<size_t>(qi) * K, out_idx + static_cast<size_t>(qi) * K);
     dk[t] = dkt;
     if (dkt >= 0.0f && dkt < INF) T[t] = EXP ? __fadd_rn(__fsub_rn(dkt, qq[t]), E) : dkt;
   };
 
   // ---- main loop over p2 tiles ------------------------------------------------------------------
   const uint32_t cw_limit = cand_base + static_cast<uint32_t>(kBufCap - kChunk) * CSTRIDE;
-  for (int tile_k = 0; tile_k < num_tiles; ++tile_k) {
-    const int tile_i = ORD ? outward_seq(tile_k, tile_h, num_tiles) : tile_k;
+  for (int tile_i = 0; tile_i < num_tiles; ++tile_i) {
     const int j0 = tile_i * RS;
     const int pts = min(RS, L2pad - j0);
     const int ngroups = pts / kGroup;  // multiple of kChunk
     const float* tile = tiles;
-    mbar_wait(&bars[0], tile_k & 1);
+    mbar_wait(&bars[0], tile_i & 1);
 
-    // The tile is scanned in RUNS: contiguous ascending ranges of groups, a multiple of kChunk
-    // long, read with immediate-offset LDS.128; the next group's rows are loaded while the current
-    // group is evaluated (the last prefetch of a run reads one group past it: in-bounds shared
-    // memory, never used).  Non-ORD: one run.  ORD: nearest first at block granularity -- blocks of
-    // kRunGroups groups alternately to the right and to the left of the warp's own position (home
-    // tile), or starting from the edge that faces the home tile (other tiles).
-    // One loop, ONE flush call site (overflow of any lane, or end of tile).
+    // Groups are read with immediate-offset LDS.128; the next group's rows are loaded while the
+    // current group is evaluated (the last prefetch reads one group past the tile: in-bounds shared
+    // memory, never used).  ONE flush call site (overflow of any lane, or end of tile).
     const float4* tp = reinterpret_cast<const float4*>(tile);
-    constexpr int SROWS = DT + (EXP ? 1 : 0);  // rows the scan reads (not the index row)
-    constexpr int kRunGroups = 16;
-    int R = 0, Lc = 0;  // ORD: next block to the right starts at R, next to the left ends at Lc
-    if (ORD) {
-      R = (tile_i == tile_h) ? (min(max((warp_home - j0) / kGroup, 0), ngroups) & ~(kChunk - 1))
-                             : (tile_i > tile_h ? 0 : ngroups);
-      Lc = R;
-    }
-    bool go_right = true;
-    int g = 0, g_end = 0;  // current run [g, g_end)
+    constexpr int SROWS = ROWS;
     float4 Xc[SROWS];
-    for (;;) {
-      if (g >= g_end) {  // start the next run
-        if (ORD) {
-          const bool can_r = R < ngroups, can_l = Lc > 0;
-          if (!can_r && !can_l) break;
-          if ((go_right && can_r) || !can_l) {
-            g = R;
-            g_end = min(R + kRunGroups, ngroups);
-            R = g_end;
-          } else {
-            g_end = Lc;
-            g = max(Lc - kRunGroups, 0);
-            Lc = g;
-          }
-          go_right = !go_right;
-        } else {
-          if (R >= ngroups) break;
-          g = 0;
-          g_end = ngroups;
-          R = ngroups;
-        }
 #pragma unroll
-        for (int r = 0; r < SROWS; ++r) Xc[r] = tp[r * (RS / 4) + g];
-      }
+    for (int r = 0; r < SROWS; ++r) Xc[r] = tp[r * (RS / 4)];
+    for (int g = 0; g < ngroups; g += kChunk) {
 #pragma unroll
       for (int c = 0; c < kChunk; ++c) {
         float4 Xn[SROWS];
@@ -625,22 +302,20 @@ knn_scan_kernel(const KnnScanParams prm) {
 #pragma unroll
         for (int r = 0; r < SROWS; ++r) Xc[r] = Xn[r];
       }
-      g += kChunk;
-      const bool tile_done = (g >= g_end) && (ORD ? (R >= ngroups && Lc <= 0) : true);
       // warp-converged: flush everything when ANY lane's buffer is nearly full, or at tile end
       uint32_t mx = cw[0];
 #pragma unroll
-      for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (SLOT_STRIDE * 2u));
-      if (tile_done || __any_sync(0xffffffffu, mx > cw_limit)) {
+      for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (THREADS * 2u));
+      if (g + kChunk >= ngroups || __any_sync(0xffffffffu, mx > cw_limit)) {
 #pragma unroll
         for (int t = 0; t < Q; ++t) flush(t, tile, j0);
       }
     }
 
     __syncthreads();  // everyone is done reading the tile
-    if (tid == 0 && tile_k + 1 < num_tiles) {
+    if (tid == 0 && tile_i + 1 < num_tiles) {
       fence_proxy_async();
-      issue_tile(ORD ? outward_seq(tile_k + 1, tile_h, num_tiles) : tile_k + 1);
+      issue_tile(tile_i + 1);
     }
   }
 
@@ -651,10 +326,10 @@ knn_scan_kernel(const KnnScanParams prm) {
     if (L2 < K) {
 #pragma unroll
       for (int t = 0; t < Q; ++t) {
-        const int qi = q_base + slot0 + t * SLOT_STRIDE;
+        const int qi = q_base + tid + t * THREADS;
         if (qi >= L1) continue;
-        float* od = out_d + static_cast<size_t>(orow[t]) * K;
-        int64_t* oi = out_idx + static_cast<size_t>(orow[t]) * K;
+        float* od = out_d + static_cast<size_t>(qi) * K;
+        int64_t* oi = out_idx + static_cast<size_t>(qi) * K;
         for (int k = L2; k < K; ++k) {
           od[k] = 0.0f;
           oi[k] = 0;
@@ -666,11 +341,11 @@ knn_scan_kernel(const KnnScanParams prm) {
   // sorted keys -> (idx, dist); empty slots and rows >= L1 are (0, 0)
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
-    const int slot = slot0 + t * SLOT_STRIDE;
+    const int slot = tid + t * THREADS;
     const int qi = q_base + slot;
     if (qi >= prm.P1) continue;
-    int64_t* oi = out_idx + static_cast<size_t>(orow[t]) * K;
-    float* od = out_d + static_cast<size_t>(orow[t]) * K;
+    int64_t* oi = out_idx + static_cast<size_t>(qi) * K;
+    float* od = out_d + static_cast<size_t>(qi) * K;
     for (int k = 0; k < K; ++k) {
       const uint64_t key = lists[static_cast<size_t>(k) * QPB + slot];
       const bool ok = key != kEmptyKey;
@@ -822,13 +497,13 @@ inline int pad_points(int64_t P2) {
 
 inline bool tiled_k_ok(int K) { return K <= 128; }
 
-template <int DT, int NORM, bool EXP, bool ORD, int Q, int KT, int RS, int THREADS = kTiledThreads>
+template <int DT, int NORM, bool EXP, int Q, int KT, int RS, int THREADS = kTiledThreads>
 int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
-  using SM = KnnSmem<DT, EXP, ORD, (KT > 0), Q, THREADS, RS>;
+  using SM = KnnSmem<DT, EXP, (KT > 0), Q, THREADS, RS>;
   constexpr int QPB = Q * THREADS;
   const size_t smem = SM::total(prm.K);
   if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: K too large for the tiled kernel");
-  auto kern = knn_scan_kernel<DT, NORM, EXP, ORD, Q, THREADS, KT, RS>;
+  auto kern = knn_scan_kernel<DT, NORM, EXP, Q, THREADS, KT, RS>;
   POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(ceil_div(prm.P1, QPB)), N);
   profile_begin("knn_scan", st);
@@ -838,12 +513,13 @@ int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
   return POPS_OK;
 }
 
-// D = 3, L2: Morton-ordered clouds + outward scan order (knn_order.cu).  Worth its pre-pass once
-// the cloud spans more than a tile.
-inline bool use_ordered(int64_t P2) {
+// D = 3, L2, K <= 32: Morton-ordered clouds + box-pruned search (knn_order.cu, knn_prune.cu).
+// Worth its pre-pass once the cloud spans more than a few blocks.
+inline bool use_ordered(int64_t P2, int K) {
   static const int force = getenv("POPS_KNN_ORDER") ? atoi(getenv("POPS_KNN_ORDER")) : -1;  // test aid
+  if (K > 32) return false;
   if (force >= 0) return force != 0;
-  return P2 >= 2048;
+  return P2 >= 1024;
 }
 
 int launch_ordered(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
@@ -853,25 +529,13 @@ int launch_ordered(const float* p1, const float* p2, const int64_t* len1, const 
   const bool self_knn = (p1 == p2) && (len1 == len2) && (P1 == P2);
   const int rc = knn_order_prepass(p1, p2, len1, len2, N, P1, P2, self_knn, ob, st);
   if (rc != POPS_OK) return rc;
-  KnnScanParams prm;
-  prm.p1 = p1; prm.soa = ob.soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits;
-  prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = pad_points(P2); prm.K = K;
-  prm.qsorted = ob.qsorted; prm.qhome = ob.qhome;
-  // (Q queries/thread, tile points) by K so that two CTAs share an SM:
-  //   lists K*Q*128*8 B + candidates + survivors + 5-row tile <= ~112 KB;  KT = merge bucket >= K
-  // lists live in the output arrays (KT > 0): shared memory = 5-row tile + candidates + survivors
-  // = 72 KB -> three CTAs per SM
-  if (K == 1) return launch_scan<3, 2, true, true, 4, 1, 2048>(prm, N, st);
-  if (K <= 4) return launch_scan<3, 2, true, true, 4, 4, 2048>(prm, N, st);
-  if (K <= 16) return launch_scan<3, 2, true, true, 4, 16, 2048>(prm, N, st);
-  if (K <= 32) return launch_scan<3, 2, true, true, 4, 32, 2048>(prm, N, st);
-  return launch_scan<3, 2, true, true, 1, 0, 1024>(prm, N, st);
+  return knn_prune_search(ob, len1, len2, N, P1, P2, K, idx, dists, st);
 }
 
 template <int DT, int NORM, bool EXP>
 int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
                  int P1, int P2, int K, int64_t* idx, float* dists, void* ws, cudaStream_t st) {
-  if (EXP && use_ordered(P2)) return launch_ordered(p1, p2, len1, len2, N, P1, P2, K, idx, dists, ws, st);
+  if (EXP && use_ordered(P2, K)) return launch_ordered(p1, p2, len1, len2, N, P1, P2, K, idx, dists, ws, st);
   const int P2pad = pad_points(P2);
   unsigned* maxabs = reinterpret_cast<unsigned*>(ws);
   float* soa = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up(size_t(N) * 4, 256));
@@ -889,17 +553,16 @@ int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const in
   KnnScanParams prm;
   prm.p1 = p1; prm.soa = soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = maxabs;
   prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = P2pad; prm.K = K;
-  prm.qsorted = nullptr; prm.qhome = nullptr;
   if (EXP) {
     // register-merge buckets (KT = next power of two >= K)
-    if (K == 1) return launch_scan<DT, NORM, EXP, false, 4, EXP ? 1 : 0, 2048>(prm, N, st);
-    if (K <= 4) return launch_scan<DT, NORM, EXP, false, 4, EXP ? 4 : 0, 2048>(prm, N, st);
-    if (K <= 16) return launch_scan<DT, NORM, EXP, false, 4, EXP ? 16 : 0, 2048>(prm, N, st);
-    if (K <= 32) return launch_scan<DT, NORM, EXP, false, EXP ? 4 : 1, EXP ? 32 : 0, EXP ? 2048 : 1024>(prm, N, st);
-    return launch_scan<DT, NORM, EXP, false, 1, 0, 1024>(prm, N, st);
+    if (K == 1) return launch_scan<DT, NORM, EXP, 4, EXP ? 1 : 0, 2048>(prm, N, st);
+    if (K <= 4) return launch_scan<DT, NORM, EXP, 4, EXP ? 4 : 0, 2048>(prm, N, st);
+    if (K <= 16) return launch_scan<DT, NORM, EXP, 4, EXP ? 16 : 0, 2048>(prm, N, st);
+    if (K <= 32) return launch_scan<DT, NORM, EXP, EXP ? 4 : 1, EXP ? 32 : 0, EXP ? 2048 : 1024>(prm, N, st);
+    return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
   }
-  if (K <= 12) return launch_scan<DT, NORM, EXP, false, 4, 0, 2048>(prm, N, st);
-  return launch_scan<DT, NORM, EXP, false, 1, 0, 1024>(prm, N, st);
+  if (K <= 12) return launch_scan<DT, NORM, EXP, 4, 0, 2048>(prm, N, st);
+  return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
 }
 
 constexpr int kGenericThreads = 128;

@@ -12,9 +12,10 @@
 //   1. bbox_maxabs_kernel   per cloud: bounding box of the valid p2 points, max |coord| of p1, p2
 //   2. morton_keys_kernel   key = [tensor | cloud | invalid | Morton code], value = index in cloud
 //   3. cub::DeviceRadixSort one sort for every cloud of both tensors
-//   4. gather kernels       p2 -> SoA rows x,y,z,w,orig_idx in sorted order (+ sentinels);
+//   4. gather kernels       p2 -> blocks of 64 sorted points (rows x,y,z,w,orig_idx; + sentinels);
 //                           p1 -> float4 (x,y,z,orig_idx) in sorted order + each query's home
 //                           position in the sorted p2 (binary search of its code)
+//   5. box_kernel           bounding box of every block
 // Results never depend on the order: the exact 64-bit key (dist, ORIGINAL index) decides.
 #include <cub/device/device_radix_sort.cuh>
 
@@ -156,13 +157,17 @@ __global__ void morton_keys_kernel(const float* __restrict__ p1, const float* __
   }
 }
 
+// Sorted p2 in BLOCKS of kBoxPoints points: [n][block][row][kBoxPoints], rows x, y, z, w = |p|^2,
+// original index -- one contiguous 1280-byte piece per block, fetched by a single TMA bulk copy.
+// Padding entries (beyond lengths2, and the tail of the last block): x = y = z = 0, w = +inf,
+// index kNoPoint.
 __global__ void gather_p2_kernel(const float* __restrict__ p2, const int64_t* __restrict__ len2, int P2,
-                                 int P2pad, const unsigned* __restrict__ vals_sorted, bool self_knn,
-                                 float* __restrict__ soa, float4* __restrict__ qsorted,
+                                 int nbox, const unsigned* __restrict__ vals_sorted, bool self_knn,
+                                 float* __restrict__ blocks, float4* __restrict__ qsorted,
                                  unsigned* __restrict__ qhome) {
   const int n = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= P2pad) return;
+  if (j >= nbox * kBoxPoints) return;
   int64_t Ll = len2[n];
   const int L = static_cast<int>(Ll < 0 ? 0 : (Ll > P2 ? P2 : Ll));
   float x = 0.f, y = 0.f, z = 0.f, w = __int_as_float(0x7f800000);
@@ -180,12 +185,12 @@ __global__ void gather_p2_kernel(const float* __restrict__ p2, const int64_t* __
       qhome[static_cast<size_t>(n) * P2 + j] = static_cast<unsigned>(j);
     }
   }
-  float* dst = soa + static_cast<size_t>(n) * 5 * P2pad + j;
+  float* dst = blocks + (static_cast<size_t>(n) * nbox + j / kBoxPoints) * kBlockFloats + (j % kBoxPoints);
   dst[0] = x;
-  dst[static_cast<size_t>(P2pad)] = y;
-  dst[static_cast<size_t>(2) * P2pad] = z;
-  dst[static_cast<size_t>(3) * P2pad] = w;
-  dst[static_cast<size_t>(4) * P2pad] = __uint_as_float(orig);
+  dst[kBoxPoints] = y;
+  dst[2 * kBoxPoints] = z;
+  dst[3 * kBoxPoints] = w;
+  dst[4 * kBoxPoints] = __uint_as_float(orig);
 }
 
 __global__ void gather_p1_kernel(const float* __restrict__ p1, const int64_t* __restrict__ len1,
@@ -220,6 +225,40 @@ __global__ void gather_p1_kernel(const float* __restrict__ p1, const int64_t* __
   qhome[static_cast<size_t>(n) * P1 + j] = home;
 }
 
+// One warp per block: min / max corner of its valid points.  Blocks with no valid point come out
+// as (+inf, -inf) and are never intersected.
+__global__ void box_kernel(const float* __restrict__ blocks, int nbox, float4* __restrict__ boxes) {
+  const int n = blockIdx.y;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= nbox) return;
+  const int lane = threadIdx.x & 31;
+  const float* base = blocks + (static_cast<size_t>(n) * nbox + b) * kBlockFloats;
+  const float INF = __int_as_float(0x7f800000);
+  float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+  for (int i = lane; i < kBoxPoints; i += 32) {
+    if (__float_as_uint(base[4 * kBoxPoints + i]) == kNoPoint) continue;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = base[d * kBoxPoints + i];
+      mn[d] = fminf(mn[d], v);
+      mx[d] = fmaxf(mx[d], v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  }
+  if (lane == 0) {
+    float4* dst = boxes + (static_cast<size_t>(n) * nbox + b) * 2;
+    dst[0] = make_float4(mn[0], mn[1], mn[2], 0.f);
+    dst[1] = make_float4(mx[0], mx[1], mx[2], 0.f);
+  }
+}
+
 size_t cub_temp_bytes_for(int64_t items) {
   size_t bytes = 0;
   unsigned* nul = nullptr;
@@ -230,7 +269,6 @@ size_t cub_temp_bytes_for(int64_t items) {
 }  // namespace
 
 size_t knn_order_carve(void* ws, int64_t N, int64_t P1, int64_t P2, KnnOrderBuffers* out) {
-  const int64_t P2pad = (P2 + 15) / 16 * 16;
   const int64_t items = N * (P1 + P2);
   size_t off = 0;
   char* base = reinterpret_cast<char*>(ws);
@@ -242,9 +280,10 @@ size_t knn_order_carve(void* ws, int64_t N, int64_t P1, int64_t P2, KnnOrderBuff
   KnnOrderBuffers b;
   b.maxabs_bits = reinterpret_cast<unsigned*>(take(size_t(N) * 4));
   b.bbox = reinterpret_cast<float*>(take(size_t(N) * 6 * 4));
-  b.soa = reinterpret_cast<float*>(take(size_t(N) * 5 * P2pad * 4));
+  b.blocks = reinterpret_cast<float*>(take(size_t(N) * knn_order_num_boxes(P2) * kBlockFloats * 4));
   b.qsorted = reinterpret_cast<float4*>(take(size_t(N) * P1 * 16));
   b.qhome = reinterpret_cast<unsigned*>(take(size_t(N) * P1 * 4));
+  b.boxes = reinterpret_cast<float4*>(take(size_t(N) * knn_order_num_boxes(P2) * 32));
   b.keys_in = reinterpret_cast<unsigned*>(take(size_t(items) * 4));
   b.keys_out = reinterpret_cast<unsigned*>(take(size_t(items) * 4));
   b.vals_in = reinterpret_cast<unsigned*>(take(size_t(items) * 4));
@@ -261,7 +300,7 @@ size_t knn_order_workspace_bytes(int64_t N, int64_t P1, int64_t P2) {
 
 int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2,
                       int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st) {
-  const int P2pad = (P2 + 15) / 16 * 16;
+  const int nbox = static_cast<int>(knn_order_num_boxes(P2));
   const KeyLayout kl = key_layout(N, !self_knn);
   bbox_maxabs_kernel<<<N, 1024, 0, st>>>(p1, p2, len1, len2, P1, P2, self_knn, b.bbox, b.maxabs_bits);
   POPS_LAUNCH_OK("bbox_maxabs_kernel");
@@ -277,10 +316,15 @@ int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, con
                                                b.vals_out, static_cast<int>(items), 0, kl.end_bit, st));
   g_launch_count.fetch_add(4, std::memory_order_relaxed);  // cub: histogram + onesweep passes
   {
-    dim3 grid(static_cast<unsigned>(ceil_div(P2pad, 256)), N);
-    gather_p2_kernel<<<grid, 256, 0, st>>>(p2, len2, P2, P2pad, b.vals_out, self_knn, b.soa, b.qsorted,
+    dim3 grid(static_cast<unsigned>(ceil_div(int64_t(nbox) * kBoxPoints, 256)), N);
+    gather_p2_kernel<<<grid, 256, 0, st>>>(p2, len2, P2, nbox, b.vals_out, self_knn, b.blocks, b.qsorted,
                                            b.qhome);
     POPS_LAUNCH_OK("gather_p2_kernel");
+  }
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(nbox, 8)), N);
+    box_kernel<<<grid, 256, 0, st>>>(b.blocks, nbox, b.boxes);
+    POPS_LAUNCH_OK("box_kernel");
   }
   if (!self_knn) {
     dim3 grid(static_cast<unsigned>(ceil_div(P1, 256)), N);

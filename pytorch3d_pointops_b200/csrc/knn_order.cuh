@@ -8,9 +8,10 @@ namespace pops {
 struct KnnOrderBuffers {
   unsigned* maxabs_bits;  // [N]        max |coordinate| over p1 and p2 of the cloud (float bits)
   float* bbox;            // [N][6]     min xyz, max xyz of the valid p2 points
-  float* soa;             // [N][5][P2pad]  x, y, z, w=|p|^2, original index (u32 bits), Morton order
+  float* blocks;          // [N][nbox][5][kBoxPoints]  x, y, z, w=|p|^2, original index (u32 bits), Morton order
   float4* qsorted;        // [N][P1]    x, y, z, original index (u32 bits), Morton order
   unsigned* qhome;        // [N][P1]    position in the sorted p2 where the query's code would go
+  float4* boxes;          // [N][nbox][2]  (min xyz, -), (max xyz, -) of every kBoxPoints sorted p2 points
   // scratch
   unsigned* keys_in;      // [N*(P1+P2)]
   unsigned* keys_out;
@@ -21,6 +22,14 @@ struct KnnOrderBuffers {
 };
 
 constexpr unsigned kNoPoint = 0xFFFFFFFFu;  // "original index" of padding entries
+constexpr int kBoxPoints = 64;               // sorted p2 points per block (one bounding box each)
+constexpr int kBlockFloats = 5 * kBoxPoints; // x, y, z, w, index rows: 1280 bytes per block
+
+// boxes per cloud, padded so that a warp can read 32 boxes of any 2048-point tile in bounds
+inline int64_t knn_order_num_boxes(int64_t P2) {
+  const int64_t nb = (P2 + kBoxPoints - 1) / kBoxPoints;
+  return (nb + 31) / 32 * 32;
+}
 
 size_t knn_order_workspace_bytes(int64_t N, int64_t P1, int64_t P2);
 // Lays the buffers out inside `ws` (256-byte aligned pieces).  Returns bytes used.

@@ -1,0 +1,614 @@
+// D = 3, L2, K <= 32 nearest neighbours over Morton-ordered clouds with exact bounding-box pruning.
+//
+// Same contract as every other KNN path (knn_cpu.cpp:13-69 of the reference: the K
+// lexicographically smallest (dist, idx), dist = the unfused float32 sum), different amount of
+// work: a (query, point) pair is evaluated only if the point's block can still hold a neighbour.
+//
+//   pre-pass (knn_order.cu)   both clouds sorted along a Morton curve; p2 cut into blocks of 64
+//                             points (1280 contiguous bytes: rows x, y, z, w=|p|^2, original index)
+//                             with one bounding box each.
+//   this kernel               one WARP = Q*32 consecutive sorted queries, fully independent of the
+//                             other warps of its CTA (no __syncthreads after start-up).
+//     walk    blocks are visited outward from the warp's own position in the sorted p2.  Lane j of
+//             the warp holds the lower bound between the warp's query box and block j of the
+//             current 32-block chunk; one ballot against the warp's largest K-th distance selects
+//             the blocks still worth reading.  The bound uses the reference's own unfused
+//             operations, and rounding is monotone, so "bound > K-th distance" proves that no
+//             point of the block can enter any list of the warp -- no epsilon (box_lower_bound).
+//     fetch   each surviving block arrives by ONE TMA bulk copy (cp.async.bulk + mbarrier) into the
+//             warp's private ring of 4 slots, up to 3 blocks ahead of the scan.
+//     seed    before the first scan the warp evaluates the exact distances to its first 1-4 blocks
+//             and keeps, per query, the minimum over each of 2 KT interleaved subsets; the KT-th
+//             smallest of those minima bounds the K-th distance from above (KT distinct points are
+//             at least that close).  The filter threshold is therefore tight from the first block
+//             on: a query buffers ~1.5 K candidate points in total instead of ~K ln(P/K).
+//     scan    per group of 4 points and per query: 6 FFMA2 (expanded form w - 2 q.p), min, compare,
+//             predicated append of the group id to the query's candidate buffer -- as in knn.cu.
+//     flush   rare (a query buffers ~K/4 + few groups in total): the buffered groups are re-read from
+//             the sorted blocks in L2 (candidates hold GLOBAL group ids, so the ring can recycle
+//             slots freely), exact unfused distance, 64-bit keys, register sorting networks
+//             (knn_core.cuh); the lists live in the output arrays.
+#include <cfloat>
+#include <cstdlib>
+
+#include "knn_core.cuh"
+
+namespace pops {
+
+namespace {
+
+constexpr int kRingSlots = 4;   // blocks resident per warp
+constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
+constexpr int kPruneBufCap = 24; // candidate groups a query can buffer between flushes
+constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
+constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
+constexpr uint32_t kBlockBytes = kBlockFloats * 4;
+static_assert((kRingSlots & (kRingSlots - 1)) == 0 && kRingSlots <= 32, "slot metadata sits in lanes");
+
+struct KnnPruneParams {
+  const float4* qsorted;
+  const unsigned* qhome;
+  const float* blocks;
+  const float4* boxes;
+  const int64_t* len1;
+  const int64_t* len2;
+  const unsigned* maxabs_bits;
+  int64_t* idx;
+  float* dists;
+  int P1, P2, K, nbox;
+  int prune;  // 0: visit every block (brute force in the same order); measurement aid
+  unsigned long long* stats;  // development counters (POPS_KNN_STATS=1), else nullptr
+};
+
+__device__ unsigned long long g_knn_stats[8];
+
+// CID: candidate id type -- unsigned short while the cloud has at most 65536 groups (262144 points)
+template <int Q, int THREADS, typename CID>
+struct PruneSmem {
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int QPB = Q * THREADS;
+  static constexpr size_t bars_off = 0;
+  static constexpr size_t ring_off = 256;
+  static constexpr size_t ring_bytes = size_t(WARPS) * kRingSlots * kBlockBytes;
+  static constexpr size_t cand_off = ring_off + ring_bytes;
+  static constexpr size_t cand_bytes = size_t(kPruneBufCap) * QPB * sizeof(CID);  // global group ids
+  static constexpr size_t surv_off = (cand_off + cand_bytes + 15) / 16 * 16;
+  static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
+  static constexpr size_t cold_off = surv_off + surv_bytes;
+  static constexpr size_t cold_bytes = size_t(3) * QPB * 4;  // qq, dk, output row per query
+  static constexpr size_t total = cold_off + cold_bytes;
+  static_assert(WARPS * kRingSlots * 8 <= ring_off, "mbarriers overlap the ring");
+};
+
+// Lower bound of the reference distance between ANY query in the box [qlo, qhi] and ANY point in
+// the box [lo, hi].  Same unfused operations in the same order as the reference distance
+// (knn_cpu.cpp:42-50); rounding is monotone, so for every such pair and every axis
+// |fl(q - p)| >= gap, fl(gap^2) <= fl(diff^2), and the rounded sums keep the order: the bound
+// holds exactly.  Empty boxes (+inf, -inf) give +inf.
+__device__ __forceinline__ float box_lower_bound(float4 lo, float4 hi, const float (&qlo)[3],
+                                                 const float (&qhi)[3]) {
+  const float gx = fmaxf(fmaxf(__fsub_rn(lo.x, qhi[0]), __fsub_rn(qlo[0], hi.x)), 0.0f);
+  const float gy = fmaxf(fmaxf(__fsub_rn(lo.y, qhi[1]), __fsub_rn(qlo[1], hi.y)), 0.0f);
+  const float gz = fmaxf(fmaxf(__fsub_rn(lo.z, qhi[2]), __fsub_rn(qlo[2], hi.z)), 0.0f);
+  return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+}
+
+// exact unfused distances of q to the 4 points of one group (packed sub / mul, scalar adds:
+// ptxas fuses packed mul + packed add into FFMA2, which would break bit parity -- knn_core.cuh)
+__device__ __forceinline__ void exact4(float q0, float q1, float q2, float4 X, float4 Y, float4 Z,
+                                       float (&d4)[4]) {
+  const float2 x01 = __fadd2_rn(make_float2(q0, q0), make_float2(-X.x, -X.y));
+  const float2 x23 = __fadd2_rn(make_float2(q0, q0), make_float2(-X.z, -X.w));
+  const float2 y01 = __fadd2_rn(make_float2(q1, q1), make_float2(-Y.x, -Y.y));
+  const float2 y23 = __fadd2_rn(make_float2(q1, q1), make_float2(-Y.z, -Y.w));
+  const float2 z01 = __fadd2_rn(make_float2(q2, q2), make_float2(-Z.x, -Z.y));
+  const float2 z23 = __fadd2_rn(make_float2(q2, q2), make_float2(-Z.z, -Z.w));
+  const float2 xx01 = __fmul2_rn(x01, x01), xx23 = __fmul2_rn(x23, x23);
+  const float2 yy01 = __fmul2_rn(y01, y01), yy23 = __fmul2_rn(y23, y23);
+  const float2 zz01 = __fmul2_rn(z01, z01), zz23 = __fmul2_rn(z23, z23);
+  d4[0] = __fadd_rn(__fadd_rn(xx01.x, yy01.x), zz01.x);
+  d4[1] = __fadd_rn(__fadd_rn(xx01.y, yy01.y), zz01.y);
+  d4[2] = __fadd_rn(__fadd_rn(xx23.x, yy23.x), zz23.x);
+  d4[3] = __fadd_rn(__fadd_rn(xx23.y, yy23.y), zz23.y);
+}
+
+// Batcher odd-even merge sort of v[OFF .. OFF+N) (N a power of two), ascending; fully unrolled, so
+// every index is static and the values stay in registers (63 compare-exchanges for N = 16).
+template <int N, int OFF, int TOTAL>
+__device__ __forceinline__ void sort_floats(float (&v)[TOTAL]) {
+#pragma unroll
+  for (int p = 1; p < N; p *= 2) {
+#pragma unroll
+    for (int k = p; k >= 1; k /= 2) {
+#pragma unroll
+      for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+          if (i <= N - j - k - 1 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+            const float lo = fminf(v[OFF + i + j], v[OFF + i + j + k]);
+            const float hi = fmaxf(v[OFF + i + j], v[OFF + i + j + k]);
+            v[OFF + i + j] = lo;
+            v[OFF + i + j + k] = hi;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Seed bound of one query: exact distances to the `nseed` blocks at the start of the warp's ring;
+// minimum over each of NS interleaved subsets of the points (NS distinct points: the subsets are
+// disjoint), then the KT-th smallest of those minima.  KT distinct points lie within the result,
+// so it bounds the K-th distance (K <= KT) from above.  +inf when fewer than KT subsets hold a
+// valid point.  NS = 2 KT subsets of >= 4 points put the bound near the (1.1 KT)-th nearest seed
+// point.  Not inlined: runs once per query.
+template <int KT>
+__device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q0, float q1, float q2) {
+  constexpr int NS = KT == 1 ? 1 : (KT == 4 ? 16 : 2 * KT);
+  constexpr int UG = NS >= 4 ? NS / 4 : 1;  // groups per unrolled step: subset index stays static
+  static_assert(UG <= kBlockGroups, "a step stays inside one block");
+  const float INF = __int_as_float(0x7f800000);
+  float mins[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) mins[i] = INF;
+  for (int s = 0; s < nseed; ++s) {
+    const float4* tp = ring4 + s * kBlockF4;
+#pragma unroll 1
+    for (int g0 = 0; g0 < kBlockGroups; g0 += UG) {
+#pragma unroll
+      for (int u = 0; u < UG; ++u) {
+        const int g = g0 + u;
+        const float4 W = tp[3 * kBlockGroups + g];
+        float d4[4];
+        exact4(q0, q1, q2, tp[g], tp[kBlockGroups + g], tp[2 * kBlockGroups + g], d4);
+        const float w4[4] = {W.x, W.y, W.z, W.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float dv = (w4[i] == INF) ? INF : d4[i];  // padding entries carry w = +inf
+          float& m = mins[(u * 4 + i) % NS];
+          m = fminf(m, dv);
+        }
+      }
+    }
+  }
+  if (NS == 1) return mins[0];
+  if (NS != 2 * KT) {  // KT = 4: 4th smallest of 16
+    sort_floats<NS, 0, NS>(mins);
+    return mins[KT - 1];
+  }
+  // KT-th smallest of 2 KT values: sort both halves, then max_i min(A[i], B[KT-1-i])
+  constexpr int H = NS / 2;
+  sort_floats<H, 0, NS>(mins);
+  sort_floats<H, H, NS>(mins);
+  float U = fminf(mins[0], mins[H + H - 1]);
+#pragma unroll
+  for (int i = 1; i < H; ++i) U = fmaxf(U, fminf(mins[i], mins[H + H - 1 - i]));
+  return U;
+}
+
+// Drain ONE query's candidate buffer (u32 global group ids, column stride CSTRIDE words).  Not
+// inlined, called warp-converged and kept converged.  The groups are re-read from the sorted
+// blocks (L2), two per step for memory-level parallelism; every point gets the exact distance and
+// points with d <= dkt become 64-bit keys in the lane's survivor column; knn_merge_global folds
+// them into the list.  Returns the tightened bound of the K-th distance.
+template <int KT, int CSTRIDE, int SSTRIDE, typename CID>
+__device__ __noinline__ float prune_flush_one(const float* __restrict__ blocks_n, const CID* cand_col,
+                                              int c_end, uint64_t* S, float q0, float q1, float q2,
+                                              float dkt, int K, float* od, int64_t* oi) {
+  constexpr unsigned FULL = 0xffffffffu;
+  if (!__any_sync(FULL, c_end > 0)) return dkt;
+  int c = 0;
+  for (;;) {
+    if (!__any_sync(FULL, c < c_end)) break;
+    int ns = 0;
+    while (c < c_end && ns <= kSurvCap - 2 * kGroup) {
+      const bool two = c + 1 < c_end;
+      const unsigned ga = cand_col[c * CSTRIDE];
+      const unsigned gb = two ? cand_col[(c + 1) * CSTRIDE] : ga;
+      c += 2;
+      const float* pa = blocks_n + static_cast<size_t>(ga / kBlockGroups) * kBlockFloats + (ga % kBlockGroups) * kGroup;
+      const float* pb = blocks_n + static_cast<size_t>(gb / kBlockGroups) * kBlockFloats + (gb % kBlockGroups) * kGroup;
+      const float4 Xa = *reinterpret_cast<const float4*>(pa);
+      const float4 Ya = *reinterpret_cast<const float4*>(pa + kBoxPoints);
+      const float4 Za = *reinterpret_cast<const float4*>(pa + 2 * kBoxPoints);
+      const uint4 Ia = *reinterpret_cast<const uint4*>(pa + 4 * kBoxPoints);
+      const float4 Xb = *reinterpret_cast<const float4*>(pb);
+      const float4 Yb = *reinterpret_cast<const float4*>(pb + kBoxPoints);
+      const float4 Zb = *reinterpret_cast<const float4*>(pb + 2 * kBoxPoints);
+      const uint4 Ib = *reinterpret_cast<const uint4*>(pb + 4 * kBoxPoints);
+      float da[4], db[4];
+      exact4(q0, q1, q2, Xa, Ya, Za, da);
+      exact4(q0, q1, q2, Xb, Yb, Zb, db);
+      const unsigned ia[4] = {Ia.x, Ia.y, Ia.z, Ia.w}, ib[4] = {Ib.x, Ib.y, Ib.z, Ib.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (da[i] <= dkt && ia[i] != kNoPoint) {
+          S[ns * SSTRIDE] = make_key(da[i], ia[i]);
+          ++ns;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (two && db[i] <= dkt && ib[i] != kNoPoint) {
+          S[ns * SSTRIDE] = make_key(db[i], ib[i]);
+          ++ns;
+        }
+      }
+    }
+    __syncwarp();
+    const int ns_max = __reduce_max_sync(FULL, ns);
+    if (ns_max > 0) dkt = knn_merge_global<KT, SSTRIDE>(S, ns, ns_max, K, od, oi, dkt);
+    __syncwarp();
+  }
+  return dkt;
+}
+
+template <int Q, int KT, int THREADS, typename CID>
+__global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : 8)))
+knn_prune_kernel(const KnnPruneParams prm) {
+  constexpr int QPB = Q * THREADS, S = kRingSlots;
+  constexpr int NSEED = KT <= 4 ? 1 : (KT <= 16 ? 2 : 4);  // >= 4 seed points per tournament subset
+  static_assert(NSEED <= S, "the seed blocks sit in the ring together");
+  using SM = PruneSmem<Q, THREADS, CID>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr unsigned FULL = 0xffffffffu;
+
+  const int n = blockIdx.y;
+  const int q_base = blockIdx.x * QPB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = prm.K;
+  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
+  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
+  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
+  int64_t* out_idx = prm.idx + (static_cast<size_t>(n) * prm.P1) * K;
+  float* out_d = prm.dists + (static_cast<size_t>(n) * prm.P1) * K;
+  const float4* qs = prm.qsorted + static_cast<size_t>(n) * prm.P1;
+  const float INF = __int_as_float(0x7f800000);
+
+  // CTA entirely beyond lengths1[n] (or nothing to search): rows are (0, 0).
+  if (q_base >= L1 || L2 == 0) {
+    const int rows = min(QPB, prm.P1 - q_base);
+    for (int e = tid; e < rows * K; e += THREADS) {
+      const size_t row = __float_as_uint(qs[q_base + e / K].w);
+      out_idx[row * K + e % K] = 0;
+      out_d[row * K + e % K] = 0.0f;
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::bars_off) + warp * S;
+  float* ring = reinterpret_cast<float*>(smem + SM::ring_off) + static_cast<size_t>(warp) * S * kBlockFloats;
+  const float4* ring4 = reinterpret_cast<const float4*>(ring);
+  CID* cand = reinterpret_cast<CID*>(smem + SM::cand_off);
+  uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off);
+  // per-query state the dense loop never touches lives in shared memory, not in registers
+  float* cold_qq = reinterpret_cast<float*>(smem + SM::cold_off);
+  float* cold_dk = cold_qq + QPB;  // upper bound of the final K-th distance (-1: beyond lengths1)
+  unsigned* cold_row = reinterpret_cast<unsigned*>(cold_dk + QPB);  // output row = original query index
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  // ---- per-thread query state ---------------------------------------------------------------
+  const float M = __uint_as_float(prm.maxabs_bits[n]);
+  // E >= 130.2 * 2^-24 * M^2 bounds |filter - reference| (DESIGN.md "filter error bound").
+  const float E = fmaf(M * M, 1.52587890625e-05f /* 2^-16 */, 1e-37f);
+  constexpr uint32_t CB = sizeof(CID);
+  constexpr uint32_t CBYTES = QPB * CB;  // bytes between consecutive entries of one candidate buffer
+  const int slot0 = warp * (Q * 32) + lane;  // a warp's Q*32 queries are contiguous in Morton order
+  const int wq0 = q_base + warp * (Q * 32);
+  float a[Q][3];   // -2 q_d (FFMA2 takes it as a broadcast scalar operand)
+  float T[Q];      // filter threshold
+  uint32_t cw[Q];  // shared-memory byte address of the next free candidate slot
+  const uint32_t cand_base = smem_u32(cand) + static_cast<uint32_t>(slot0) * CB;
+  float wqlo[3] = {INF, INF, INF}, wqhi[3] = {-INF, -INF, -INF};  // box of the warp's valid queries
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    const int slot = slot0 + t * 32;
+    const int qi = q_base + slot;
+    const bool valid = qi < L1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qi < prm.P1) v = qs[qi];
+    const unsigned row = __float_as_uint(v.w);
+    const float qv[3] = {valid ? v.x : 0.0f, valid ? v.y : 0.0f, valid ? v.z : 0.0f};
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      s = fmaf(qv[d], qv[d], s);
+      a[t][d] = -2.0f * qv[d];
+      if (valid) {
+        wqlo[d] = fminf(wqlo[d], qv[d]);
+        wqhi[d] = fmaxf(wqhi[d], qv[d]);
+      }
+    }
+    cold_qq[slot] = s;
+    cold_dk[slot] = valid ? INF : -1.0f;
+    cold_row[slot] = row;
+    T[t] = valid ? FLT_MAX : -INF;
+    cw[t] = cand_base + static_cast<uint32_t>(t) * (32u * CB);
+    // empty list = (+inf, 0xFFFFFFFF) in every slot; rows beyond lengths1 are final zeros
+    if (qi < prm.P1) {
+      float* od = out_d + static_cast<size_t>(row) * K;
+      int64_t* oi = out_idx + static_cast<size_t>(row) * K;
+      for (int k = 0; k < K; ++k) {
+        od[k] = valid ? INF : 0.0f;
+        oi[k] = valid ? static_cast<int64_t>(0xFFFFFFFFll) : 0;
+      }
+    }
+  }
+  if (wq0 >= L1) return;  // no valid query in this warp; warps never meet again
+  if (prm.stats && lane == 0) atomicAdd(prm.stats + 5, 1ull);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      wqlo[d] = fminf(wqlo[d], __shfl_xor_sync(FULL, wqlo[d], o));
+      wqhi[d] = fmaxf(wqhi[d], __shfl_xor_sync(FULL, wqhi[d], o));
+    }
+  }
+  float dkmax = INF;  // largest bound over the warp's valid queries
+
+  // ---- block walk: outward from the warp's home block, 32 blocks (one chunk) per side at a time
+  const int nblk = (L2 + kBoxPoints - 1) / kBoxPoints;
+  const int nchunks = (nblk + 31) >> 5;
+  const int nvalid_w = min(Q * 32, L1 - wq0);
+  const int hb = min(static_cast<int>(prm.qhome[static_cast<size_t>(n) * prm.P1 + wq0 + (nvalid_w >> 1)]) /
+                         kBoxPoints,
+                     nblk - 1);
+  const float4* boxes_n = prm.boxes + static_cast<size_t>(n) * prm.nbox * 2;
+  auto chunk_bounds = [&](int c) -> float {  // lane j: bound for block c*32 + j
+    if (!prm.prune) return 0.0f;
+    const float4* bx = boxes_n + static_cast<size_t>(c * 32 + lane) * 2;  // nbox is a multiple of 32
+    return box_lower_bound(bx[0], bx[1], wqlo, wqhi);
+  };
+  auto valid_mask = [&](int c) -> unsigned {
+    const int left = nblk - (c << 5);
+    return left >= 32 ? FULL : ((1u << left) - 1u);
+  };
+  int chR = hb >> 5, chL = hb >> 5;
+  float lbR = chunk_bounds(chR), lbL = lbR;
+  unsigned pendR = valid_mask(chR) & ~((1u << (hb & 31)) - 1u);
+  unsigned pendL = (1u << (hb & 31)) - 1u;
+  bool go_right = true;
+  float picked_lb = 0.0f;
+  auto pick = [&]() -> int {  // next block whose bound does not exceed dkmax, or -1
+    for (;;) {
+      const bool can_r = chR < nchunks, can_l = chL >= 0;
+      if (!can_r && !can_l) return -1;
+      if ((go_right && can_r) || !can_l) {
+        const unsigned m = pendR & __ballot_sync(FULL, lbR <= dkmax);
+        if (m) {
+          const int b = __ffs(m) - 1;
+          pendR &= ~((2u << b) - 1u);  // skipped blocks stay pruned: dkmax only decreases
+          picked_lb = __shfl_sync(FULL, lbR, b);
+          go_right = false;
+          return (chR << 5) + b;
+        }
+        if (++chR < nchunks) {
+          lbR = chunk_bounds(chR);
+          pendR = valid_mask(chR);
+        }
+      } else {
+        const unsigned m = pendL & __ballot_sync(FULL, lbL <= dkmax);
+        if (m) {
+          const int b = 31 - __clz(m);
+          pendL &= (1u << b) - 1u;
+          picked_lb = __shfl_sync(FULL, lbL, b);
+          go_right = true;
+          return (chL << 5) + b;
+        }
+        if (--chL >= 0) {
+          lbL = chunk_bounds(chL);
+          pendL = FULL;
+        }
+      }
+    }
+  };
+
+  // ---- ring of blocks -----------------------------------------------------------------------------
+  const float* blocks_n = prm.blocks + static_cast<size_t>(n) * prm.nbox * kBlockFloats;
+  float slot_lb = 0.0f;  // lane s: bound of the block in slot s
+  int slot_blk = 0;      // lane s: index of the block in slot s
+  int head = 0, tail = 0;  // blocks issued / scanned
+  auto issue = [&](int b) {
+    const int s = head & (S - 1);
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async();  // the slot's previous contents were read through the generic proxy
+      mbar_arrive_expect_tx(&bars[s], kBlockBytes);
+      tma_bulk_g2s(ring + static_cast<size_t>(s) * kBlockFloats, blocks_n + static_cast<size_t>(b) * kBlockFloats,
+                   kBlockBytes, &bars[s]);
+    }
+    if (lane == s) {
+      slot_lb = picked_lb;
+      slot_blk = b;
+    }
+    ++head;
+    if (prm.stats && lane == 0) atomicAdd(prm.stats + 0, 1ull);
+  };
+
+  // ---- flush glue ------------------------------------------------------------------------------------
+  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(kPruneBufCap - kChunk) * CBYTES;
+  // only_full: drain just the query slots in which some lane's buffer is nearly full
+  auto flush_all = [&](bool only_full) {
+    if (prm.stats && lane == 0) atomicAdd(prm.stats + 2, 1ull);
+    float dm = 0.0f;  // lanes beyond lengths1 carry dk = -1
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const int slot = slot0 + t * 32;
+      const uint32_t base = cand_base + static_cast<uint32_t>(t) * (32u * CB);
+      if (only_full && !__any_sync(FULL, cw[t] > cw_limit + static_cast<uint32_t>(t) * (32u * CB))) {
+        dm = fmaxf(dm, cold_dk[slot]);
+        continue;
+      }
+      const int c_end = static_cast<int>((cw[t] - base) / CBYTES);
+      cw[t] = base;
+      if (prm.stats) {
+        atomicAdd(prm.stats + 3, static_cast<unsigned long long>(c_end));
+        const bool anyc = __any_sync(FULL, c_end > 0);
+        if (lane == 0 && anyc) atomicAdd(prm.stats + 4, 1ull);
+      }
+      const size_t row = cold_row[slot];
+      const float dkt = prune_flush_one<KT, QPB, THREADS, CID>(
+          blocks_n, cand + slot, c_end, surv + tid, -0.5f * a[t][0], -0.5f * a[t][1], -0.5f * a[t][2],
+          cold_dk[slot], K, out_d + row * K, out_idx + row * K);
+      cold_dk[slot] = dkt;
+      if (dkt >= 0.0f && dkt < INF) T[t] = __fadd_rn(__fsub_rn(dkt, cold_qq[slot]), E);
+      dm = fmaxf(dm, dkt);
+    }
+    dkmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(dm)));
+  };
+
+  // ---- seed: upper bound of every query's K-th distance from the first blocks ------------------
+  for (int i = 0; i < NSEED; ++i) {
+    const int b = pick();
+    if (b < 0) break;
+    issue(b);
+  }
+  {
+    const int nseed = head;
+    for (int s = 0; s < nseed; ++s) mbar_wait(&bars[s], 0);
+    float dm = 0.0f;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const int slot = slot0 + t * 32;
+      const float U = seed_bound<KT>(ring4, nseed, -0.5f * a[t][0], -0.5f * a[t][1], -0.5f * a[t][2]);
+      if (cold_dk[slot] >= 0.0f) {
+        cold_dk[slot] = U;  // KT >= K distinct points lie within U
+        if (U < INF) T[t] = __fadd_rn(__fsub_rn(U, cold_qq[slot]), E);
+        dm = fmaxf(dm, U);
+      }
+    }
+    dkmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(dm)));
+  }
+
+  // ---- main loop ---------------------------------------------------------------------------------
+  for (;;) {
+    while (head - tail < kPrefetch) {
+      const int b = pick();
+      if (b < 0) break;
+      issue(b);
+    }
+    if (tail == head) break;
+    const int s = tail & (S - 1);
+    mbar_wait(&bars[s], (tail / S) & 1);
+    if (__shfl_sync(FULL, slot_lb, s) <= dkmax) {  // dkmax may have dropped since the fetch
+      if (prm.stats && lane == 0) atomicAdd(prm.stats + 1, 1ull);
+      const float4* tp = ring4 + s * kBlockF4;
+      const unsigned gid0 = static_cast<unsigned>(__shfl_sync(FULL, slot_blk, s)) * kBlockGroups;
+      float4 Xc[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) Xc[r] = tp[r * kBlockGroups];
+#pragma unroll 1
+      for (int g = 0; g < kBlockGroups; g += kChunk) {
+#pragma unroll
+        for (int c = 0; c < kChunk; ++c) {
+          // next group's rows (the last prefetch of a block reads the index row: in bounds, unused)
+          float4 Xn[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) Xn[r] = tp[r * kBlockGroups + g + c + 1];
+          const unsigned gid = gid0 + g + c;
+#pragma unroll
+          for (int t = 0; t < Q; ++t) {
+            float2 s01 = make_float2(Xc[3].x, Xc[3].y), s23 = make_float2(Xc[3].z, Xc[3].w);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float2 ad = make_float2(a[t][d], a[t][d]);
+              s01 = __ffma2_rn(ad, make_float2(Xc[d].x, Xc[d].y), s01);
+              s23 = __ffma2_rn(ad, make_float2(Xc[d].z, Xc[d].w), s23);
+            }
+            const float m = fminf(fminf(s01.x, s01.y), fminf(s23.x, s23.y));
+            if (m <= T[t]) {  // predicated: one STS + one IADD
+              if (sizeof(CID) == 2)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(cw[t]), "h"(static_cast<unsigned short>(gid)) : "memory");
+              else
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(cw[t]), "r"(gid) : "memory");
+              cw[t] += CBYTES;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) Xc[r] = Xn[r];
+        }
+        uint32_t mx = cw[0];
+#pragma unroll
+        for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (32u * CB));
+        if (__any_sync(FULL, mx > cw_limit)) flush_all(true);
+      }
+    }
+    ++tail;
+  }
+  flush_all(false);
+
+  // the lists ARE the outputs; only slots beyond lengths2 (K > lengths2) still hold the empty
+  // marker and become the reference's (0, 0) padding
+  if (L2 < K) {
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const int slot = slot0 + t * 32;
+      if (cold_dk[slot] < 0.0f) continue;
+      const size_t row = cold_row[slot];
+      for (int k = L2; k < K; ++k) {
+        out_d[row * K + k] = 0.0f;
+        out_idx[row * K + k] = 0;
+      }
+    }
+  }
+}
+
+template <int Q, int KT, int THREADS, typename CID>
+int launch_prune(const KnnPruneParams& prm, int N, cudaStream_t st) {
+  using SM = PruneSmem<Q, THREADS, CID>;
+  auto kern = knn_prune_kernel<Q, KT, THREADS, CID>;
+  POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::total)));
+  dim3 grid(static_cast<unsigned>(ceil_div(prm.P1, SM::QPB)), N);
+  profile_begin("knn_scan", st);
+  kern<<<grid, THREADS, SM::total, st>>>(prm);
+  profile_end("knn_scan", st);
+  POPS_LAUNCH_OK("knn_prune_kernel");
+  return POPS_OK;
+}
+
+template <int Q, typename CID>
+int launch_prune_k(const KnnPruneParams& prm, int N, cudaStream_t st) {
+  constexpr int THREADS = 64;
+  if (prm.K == 1) return launch_prune<Q, 1, THREADS, CID>(prm, N, st);
+  if (prm.K <= 4) return launch_prune<Q, 4, THREADS, CID>(prm, N, st);
+  if (prm.K <= 16) return launch_prune<Q, 16, THREADS, CID>(prm, N, st);
+  return launch_prune<Q, 32, THREADS, CID>(prm, N, st);
+}
+
+}  // namespace
+
+int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64_t* len2, int N, int P1,
+                     int P2, int K, int64_t* idx, float* dists, cudaStream_t st) {
+  static const int prune = getenv("POPS_KNN_PRUNE") ? atoi(getenv("POPS_KNN_PRUNE")) : 1;  // measurement aid
+  static const int q = getenv("POPS_KNN_Q") ? atoi(getenv("POPS_KNN_Q")) : 4;               // tuning aid
+  KnnPruneParams prm;
+  prm.qsorted = ob.qsorted; prm.qhome = ob.qhome; prm.blocks = ob.blocks; prm.boxes = ob.boxes;
+  prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits; prm.idx = idx; prm.dists = dists;
+  prm.P1 = P1; prm.P2 = P2; prm.K = K; prm.nbox = static_cast<int>(knn_order_num_boxes(P2));
+  prm.prune = prune;
+  static const int stats = getenv("POPS_KNN_STATS") ? atoi(getenv("POPS_KNN_STATS")) : 0;
+  prm.stats = nullptr;
+  if (stats) POPS_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&prm.stats), g_knn_stats));
+  const bool narrow = int64_t(prm.nbox) * kBlockGroups <= 65536;
+  if (q == 2) return narrow ? launch_prune_k<2, unsigned short>(prm, N, st) : launch_prune_k<2, unsigned>(prm, N, st);
+  return narrow ? launch_prune_k<4, unsigned short>(prm, N, st) : launch_prune_k<4, unsigned>(prm, N, st);
+}
+
+// development aid: read and reset the counters collected under POPS_KNN_STATS=1
+// [0] blocks fetched, [1] blocks scanned, [2] flush rounds, [3] buffered groups, [4] non-empty
+// per-slot flushes, [5] warps
+}  // namespace pops
+
+extern "C" int pops_knn_debug_stats(unsigned long long* out8) {
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return POPS_ERR_CUDA;
+  if (cudaMemcpyFromSymbol(out8, pops::g_knn_stats, sizeof(zero)) != cudaSuccess) return POPS_ERR_CUDA;
+  if (cudaMemcpyToSymbol(pops::g_knn_stats, zero, sizeof(zero)) != cudaSuccess) return POPS_ERR_CUDA;
+  return POPS_OK;
+}
