@@ -370,6 +370,7 @@ struct KnnGenericParams {
   uint64_t* glists;  // [N][ceil(P1/THREADS)][K][THREADS] when lists live in global memory
   int P1, P2, D, K, TP;
   int lists_in_smem;
+  const unsigned char* flags;  // [N][P1] or nullptr: when set, only flagged queries are (re)computed
 };
 
 template <int NORM, int THREADS>
@@ -383,6 +384,11 @@ knn_generic_kernel(const KnnGenericParams prm) {
   const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
   const int qi = q_base + tid;
   const bool valid = qi < L1;
+  bool wanted = true;
+  if (prm.flags) {  // exact recomputation of the queries the tensor-core path could not certify
+    wanted = qi < prm.P1 && prm.flags[static_cast<size_t>(n) * prm.P1 + qi] != 0;
+    if (!__syncthreads_or(wanted ? 1 : 0)) return;
+  }
 
   float* qsm = reinterpret_cast<float*>(smem);                   // [D][THREADS] (transposed)
   float* tile = qsm + static_cast<size_t>(D) * THREADS;          // [TP][D]
@@ -426,7 +432,7 @@ knn_generic_kernel(const KnnGenericParams prm) {
       }
     }
   }
-  if (qi < prm.P1) {
+  if (qi < prm.P1 && wanted) {
     int64_t* oi = prm.idx + (static_cast<size_t>(n) * prm.P1 + qi) * K;
     float* od = prm.dists + (static_cast<size_t>(n) * prm.P1 + qi) * K;
     for (int k = 0; k < K; ++k) {
@@ -592,7 +598,8 @@ extern "C" size_t pops_knn_workspace_bytes(int64_t N, int64_t P1, int64_t P2, in
   size_t tiled = align_up(size_t(N) * 4, 256) + size_t(N) * (D + 1) * pad_points(P2) * 4;
   if (D == 3 && norm == 2) tiled = std::max(tiled, knn_order_workspace_bytes(N, P1, P2));
   size_t generic = size_t(N) * ceil_div(P1, kGenericThreads) * K * kGenericThreads * 8;
-  (void)norm;
+  // the tensor-core path keeps its own buffers AND may hand flagged queries to the generic kernel
+  if (knn_tc_supported(P1, P2, D, K, norm)) generic = align_up(generic, 256) + knn_tc_workspace_bytes(N, P1, P2);
   return align_up(std::max(tiled, generic), 256) + 256;
 }
 
@@ -637,8 +644,17 @@ extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64
   POPS_TILED(1, 2, false)
   POPS_TILED(1, 1, false)
 #undef POPS_TILED
-  // generic
+  // generic (also the exact recomputation pass behind the tensor-core path)
   KnnGenericParams prm;
+  prm.flags = nullptr;
+  if (knn_tc_supported(P1, P2, D, K, norm)) {
+    const size_t goff = align_up(size_t(N) * ceil_div(P1, kGenericThreads) * K * kGenericThreads * 8, 256);
+    unsigned char* flags = nullptr;
+    const int rc = knn_tc_search(p1, p2, lengths1, lengths2, n, p1n, p2n, int(D), k, idx, dists,
+                                 reinterpret_cast<char*>(workspace) + goff, &flags, st);
+    if (rc != POPS_OK) return rc;
+    prm.flags = flags;
+  }
   prm.p1 = p1; prm.p2 = p2; prm.len1 = lengths1; prm.len2 = lengths2; prm.idx = idx; prm.dists = dists;
   prm.glists = reinterpret_cast<uint64_t*>(workspace);
   prm.P1 = p1n; prm.P2 = p2n; prm.D = int(D); prm.K = k;

@@ -265,4 +265,11 @@ __device__ __noinline__ float knn_flush_one(const float* tile, const unsigned sh
 int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64_t* len2, int N, int P1,
                      int P2, int K, int64_t* idx, float* dists, cudaStream_t st);
 
+// knn_tc.cu: 32 <= D <= 256, L2, K <= 16 on the tensor cores (tcgen05 filter + exact re-rank).
+bool knn_tc_supported(int64_t P1, int64_t P2, int64_t D, int64_t K, int norm);
+size_t knn_tc_workspace_bytes(int64_t N, int64_t P1, int64_t P2);
+int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1,
+                  int P2, int D, int K, int64_t* idx, float* dists, void* ws, unsigned char** flags_out,
+                  cudaStream_t st);
+
 }  // namespace pops

@@ -1,0 +1,649 @@
+// High-dimensional KNN (32 <= D <= 256, L2, K <= 16) on the 5th-generation tensor cores.
+//
+// Contract unchanged (knn_cpu.cpp:13-69 of the reference): the K lexicographically smallest
+// (dist, idx), dist = the reference's unfused float32 sum.  The tensor cores only FILTER:
+//
+//   norms    w_j = |y_j|^2 (fp32) for every p2 point, +inf beyond lengths2; max_j w_j per cloud.
+//   scan     one CTA = 128 queries of one cloud (the 128 TMEM lanes).  The query tile stays in
+//            shared memory; p2 streams through a ring of 16 KB stages (128 points x 32 floats),
+//            both moved by TMA straight from the caller's (N,P,D) tensors with the 128-byte
+//            swizzle -- no repacking pass.  tcgen05.mma kind::tf32 (one elected thread) accumulates
+//            x_i . y_j for 128 x 128 (query, point) pairs into one of four TMEM buffers; four
+//            epilogue warps pull the accumulators back with tcgen05.ld and evaluate
+//                s_ij = w_j - 2 acc_ij   ~   d(x_i, y_j) - |x_i|^2
+//            per pair: one FFMA, one compare, a predicated append of (s, j) when s does not exceed
+//            the query's current threshold.  Thresholds come from the query's APPROXIMATE list: the
+//            32 smallest (s, j) seen so far, kept in global memory (L2) and merged with register
+//            sorting networks when a candidate buffer fills up -- no p2 row is touched outside
+//            the tensor cores during the scan.
+//   rerank   one warp per query: with E >= |s_ij + |x_i|^2 - d_ref(i,j)| (bound below), every true
+//            neighbour has s <= tau = s_(K) + 2E.  The entries of the list within tau (typically
+//            K + a few) get the exact reference distance (same unfused operations, same order),
+//            are sorted by the exact 64-bit key, and the first K are the result.
+//   fallback if the 32nd entry of a list is itself within tau, a needed point may have been
+//            dropped: the query is flagged and recomputed by the exact generic kernel (massive
+//            ties / duplicate-heavy clouds; never on generic data).
+//
+// Error bound.  u = 2^-24.  TF32 operands keep 10 mantissa bits (the low 13 are ignored), so
+// |x^y^ - xy| <= (2^-9 + 2^-20)|xy| per product; fp32 accumulation inside the tensor core is
+// charged D 2^-22 per unit of sum |x_d y_d| (a 4x allowance over round-to-nearest).  With
+// |w~ - |y|^2| <= D u |y|^2, |d_ref - d| <= 2 (D+2) u (|x|^2 + |y|^2), one rounding of the final
+// FFMA, and Cauchy-Schwarz:
+//     E_i = c1 |x_i| M_y + c2 (|x_i|^2 + M_y^2),  M_y = max_j |y_j|,
+//     c1 = 2^-8 (1 + 2^-11 + D 2^-13) + 2^-23,    c2 = (3D + 8) 2^-24,     (+1 % slack)
+// The filter can only add candidates; membership and order are decided by exact keys alone.
+#include <cuda.h>  // CUtensorMap types; cuTensorMapEncodeTiled is fetched at run time (no -lcuda)
+
+#include <cfloat>
+#include <cstdlib>
+
+#include "knn_core.cuh"
+
+namespace pops {
+
+namespace {
+
+constexpr int TC_M = 128;        // queries per CTA = TMEM lanes
+constexpr int TC_N = 128;        // points per tile = TMEM columns per accumulator buffer
+constexpr int TC_KBLK = 32;      // floats per k-block: one 128-byte swizzle span
+constexpr int TC_ABUF = 4;       // accumulator buffers (4 x 128 = all 512 TMEM columns)
+constexpr int TC_LIST = 32;      // K': length of the approximate list (K <= 16)
+constexpr int TC_CAND = 24;      // candidate entries a query buffers between flushes
+constexpr int TC_SUB = 8;        // columns between two buffer-overflow checks
+constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr uint32_t TC_STAGE_BYTES = TC_N * 128;  // 16 KB: 128 rows x 128 bytes
+constexpr int TC_MAX_STAGES = 8;
+static_assert(TC_CAND - TC_SUB >= 16, "a flush round takes 16 candidates");
+
+struct TcParams {
+  const float* w;          // [N][P2pad]
+  const int64_t* len1;
+  const int64_t* len2;
+  uint64_t* lists;         // [N][P1][TC_LIST] ascending keys (sortable(s) << 32 | j)
+  int P1, P2, P2pad;
+  int KB;                  // k-blocks = ceil(D / 32)
+  int nstage;              // stages of the p2 ring
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {  // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 TMEM lanes (this warp's quarter) x 32 consecutive columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile (rows of 128 bytes, 8-row atoms 1024 bytes apart):
+// start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 >> 4 | version 1 |
+// layout SWIZZLE_128B (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
+  const uint64_t addr = (smem_u32(smem_tile) >> 4) & 0x3FFFu;
+  return addr | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N, M
+constexpr uint32_t kTcIdesc =
+    (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TC_N >> 3) << 17) | (uint32_t(TC_M >> 4) << 24);
+
+// order-preserving map float -> uint32 (ascending), and back
+__device__ __forceinline__ uint32_t f2sortable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float sortable2f(uint32_t s) {
+  return __uint_as_float(s ^ ((s >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+// ---------------------------------------------------------------------------------------------
+// norms: one warp per p2 point
+// ---------------------------------------------------------------------------------------------
+__global__ void tc_norm_kernel(const float* __restrict__ p2, const int64_t* __restrict__ len2, int P2,
+                               int P2pad, int D, float* __restrict__ w, unsigned* __restrict__ maxw_bits) {
+  const int n = blockIdx.y;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= P2pad) return;
+  int64_t Ll = len2[n];
+  const int L = static_cast<int>(Ll < 0 ? 0 : (Ll > P2 ? P2 : Ll));
+  float acc = 0.0f;
+  if (j < L) {
+    const float* row = p2 + (static_cast<size_t>(n) * P2 + j) * D;
+    for (int d = lane; d < D; d += 32) acc = fmaf(row[d], row[d], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    w[static_cast<size_t>(n) * P2pad + j] = (j < L) ? acc : __int_as_float(0x7f800000);
+    if (j < L) atomicMax(maxw_bits + n, __float_as_uint(acc));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan
+// ---------------------------------------------------------------------------------------------
+// Merge a lane's candidates (keys at S[0], S[SSTRIDE], ... , `ns` of them, at most 16) into its
+// ascending TC_LIST-entry list in global memory.  Warp-converged; lanes without candidates skip
+// the list traffic.  Returns the list's last key.
+template <int SSTRIDE>
+__device__ __forceinline__ uint64_t tc_merge(const uint64_t* S, int ns, int ns_max, uint64_t* list) {
+  uint64_t Lr[TC_LIST];
+  const bool mine = ns > 0;
+#pragma unroll
+  for (int k = 0; k < TC_LIST; ++k) Lr[k] = kEmptyKey;
+  if (mine) {
+#pragma unroll
+    for (int k2 = 0; k2 < TC_LIST / 2; ++k2) {
+      const ulonglong2 v = reinterpret_cast<const ulonglong2*>(list)[k2];
+      Lr[2 * k2] = v.x;
+      Lr[2 * k2 + 1] = v.y;
+    }
+  }
+  if (ns_max <= 4) {
+    for (int s2 = 0; s2 < ns_max; ++s2) {
+      const uint64_t key = (s2 < ns) ? S[s2 * SSTRIDE] : kEmptyKey;
+      insert_network<TC_LIST>(Lr, key);
+    }
+  } else {
+    uint64_t Sr[kSurvCap];
+#pragma unroll
+    for (int s2 = 0; s2 < kSurvCap; ++s2) Sr[s2] = (s2 < ns) ? S[s2 * SSTRIDE] : kEmptyKey;
+    sort16(Sr);
+    // TC_LIST smallest of (Lr U Sr): C[i] = min(Lr[i], Sr[TC_LIST-1-i]) is bitonic, then merge
+#pragma unroll
+    for (int i = TC_LIST - kSurvCap; i < TC_LIST; ++i) {
+      const int si = TC_LIST - 1 - i;
+      Lr[i] = (Sr[si] < Lr[i]) ? Sr[si] : Lr[i];
+    }
+    bitonic_merge<TC_LIST>(Lr);
+  }
+  if (mine) {
+#pragma unroll
+    for (int k2 = 0; k2 < TC_LIST / 2; ++k2)
+      reinterpret_cast<ulonglong2*>(list)[k2] = make_ulonglong2(Lr[2 * k2], Lr[2 * k2 + 1]);
+  }
+  return Lr[TC_LIST - 1];
+}
+
+// Drain one query's candidate buffer (entries (s bits, j), column stride TC_M) into its list.
+// Not inlined: rare, large.  Returns the new threshold: the 32nd smallest s so far (+inf while
+// the list is not full).
+__device__ __noinline__ float tc_flush(uint2* cand_col, int count, uint64_t* list, float T) {
+  constexpr unsigned FULL = 0xffffffffu;
+  // raw (s, j) -> sortable 64-bit keys, in place
+  for (int c = 0; c < count; ++c) {
+    const uint2 e = cand_col[c * TC_M];
+    cand_col[c * TC_M] = make_uint2(e.y, f2sortable(__uint_as_float(e.x)));  // little endian: lo = j, hi = key(s)
+  }
+  __syncwarp();
+  for (int c0 = 0; __any_sync(FULL, c0 < count); c0 += kSurvCap) {
+    const int ns = max(0, min(kSurvCap, count - c0));
+    const int ns_max = __reduce_max_sync(FULL, ns);
+    const uint64_t last =
+        tc_merge<TC_M>(reinterpret_cast<const uint64_t*>(cand_col) + static_cast<size_t>(c0) * TC_M, ns, ns_max, list);
+    if (ns > 0) T = (last == kEmptyKey) ? __int_as_float(0x7f800000) : sortable2f(static_cast<uint32_t>(last >> 32));
+  }
+  return T;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
+                   const TcParams prm) {
+  extern __shared__ unsigned char smem_raw[];
+  // the 128-byte swizzle needs 1024-byte aligned tiles
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr unsigned FULL = 0xffffffffu;
+  const int n = blockIdx.y;
+  const int q_base = blockIdx.x * TC_M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
+  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
+  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
+  if (q_base >= L1 || L2 == 0) return;  // the rerank kernel writes the (0, 0) rows
+  const int KB = prm.KB, NST = prm.nstage;
+  const int num_tiles = (L2 + TC_N - 1) / TC_N;
+
+  float* sA = reinterpret_cast<float*>(smem);                                  // KB x 16 KB
+  float* sB = reinterpret_cast<float*>(smem + static_cast<size_t>(KB) * TC_STAGE_BYTES);  // NST x 16 KB
+  unsigned char* rest = smem + static_cast<size_t>(KB + NST) * TC_STAGE_BYTES;
+  uint2* cand = reinterpret_cast<uint2*>(rest);                                // TC_CAND x TC_M entries
+  float* sW = reinterpret_cast<float*>(rest + size_t(TC_CAND) * TC_M * 8);     // 2 x TC_N
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 2 * TC_N);
+  uint64_t* full = bars;                       // [TC_MAX_STAGES]  TMA -> MMA
+  uint64_t* empty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * TC_MAX_STAGES;  // [TC_ABUF]        MMA -> epilogue
+  uint64_t* tempty = tfull + TC_ABUF;          // [TC_ABUF]        epilogue -> MMA
+  uint64_t* afull = tempty + TC_ABUF;          // query tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < TC_ABUF; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);  // one arrival per epilogue warp
+    }
+    mbar_init(afull, 1);
+    mbar_fence_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, TC_ABUF * TC_N);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread) =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(afull, static_cast<uint32_t>(KB) * TC_STAGE_BYTES);
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_3d(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4), &map_q, kb * TC_KBLK, q_base, n, afull);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+          tma_load_3d(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4), &map_p, kb * TC_KBLK, t * TC_N, n, &full[s]);
+          if (++s == NST) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      mbar_wait(afull, 0);
+      tc_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int b = t % TC_ABUF;
+        mbar_wait(&tempty[b], ((t / TC_ABUF) & 1) ^ 1);  // the epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * TC_N);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4));
+          const uint64_t bdesc = umma_desc_sw128(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4));
+#pragma unroll
+          for (int k = 0; k < TC_KBLK / 8; ++k)  // K = 8 per tf32 MMA: 32 bytes along the swizzled row
+            umma_tf32(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), kTcIdesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+          if (++s == NST) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull[b]);
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, thread = query row =====
+    const int ew = warp & 3;             // the TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;      // query row inside the tile
+    const int et = (warp - 2) * 32 + lane;  // 0..127: index among the epilogue threads
+    const int qi = q_base + row;
+    const float INF = __int_as_float(0x7f800000);
+    float T = (qi < L1) ? INF : -INF;   // rows beyond lengths1 never buffer anything
+    uint64_t* list = prm.lists + (static_cast<size_t>(n) * prm.P1 + min(qi, prm.P1 - 1)) * TC_LIST;
+    if (qi < L1) {
+#pragma unroll
+      for (int k2 = 0; k2 < TC_LIST / 2; ++k2)
+        reinterpret_cast<ulonglong2*>(list)[k2] = make_ulonglong2(kEmptyKey, kEmptyKey);
+    }
+    uint2* cand_col = cand + row;
+    const uint32_t cand_base = smem_u32(cand_col);
+    uint32_t cw = cand_base;
+    constexpr uint32_t CSTRIDE = TC_M * 8;
+    const uint32_t cw_limit = cand_base + static_cast<uint32_t>(TC_CAND - TC_SUB) * CSTRIDE;
+    const float* w_n = prm.w + static_cast<size_t>(n) * prm.P2pad;
+    sW[et] = w_n[et];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int t = 0; t < num_tiles; ++t) {
+      const int b = t % TC_ABUF;
+      const float* wt = sW + (t & 1) * TC_N;
+      float wnext = 0.0f;
+      if (t + 1 < num_tiles) wnext = w_n[(t + 1) * TC_N + et];
+      mbar_wait(&tfull[b], (t / TC_ABUF) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TC_N);
+#pragma unroll 1
+      for (int c = 0; c < TC_N / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_x32(taddr + static_cast<uint32_t>(c * 32), acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sub = 0; sub < 32 / TC_SUB; ++sub) {
+#pragma unroll
+          for (int i4 = 0; i4 < TC_SUB / 4; ++i4) {
+            const int col = c * 32 + sub * TC_SUB + i4 * 4;
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + col);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float s = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + i]), wv[i]);
+              if (s <= T) {  // predicated: one 64-bit store + one add
+                const uint32_t j = static_cast<uint32_t>(t * TC_N + col + i);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cw), "r"(__float_as_uint(s)), "r"(j) : "memory");
+                cw += CSTRIDE;
+              }
+            }
+          }
+          if (__any_sync(FULL, cw > cw_limit)) {
+            T = tc_flush(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), list, T);
+            cw = cand_base;
+          }
+        }
+      }
+      // accumulator buffer drained
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+      // stage the next tile's norms (all epilogue warps are past their reads of that buffer)
+      sW[((t + 1) & 1) * TC_N + et] = wnext;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (__any_sync(FULL, cw > cand_base)) tc_flush(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), list, T);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_ABUF * TC_N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rerank: one warp per query
+// ---------------------------------------------------------------------------------------------
+struct TcRerankParams {
+  const float* p1;
+  const float* p2;
+  const int64_t* len1;
+  const int64_t* len2;
+  const uint64_t* lists;
+  const unsigned* maxw_bits;
+  int64_t* idx;
+  float* dists;
+  unsigned char* flags;  // [N][P1]: 1 = recompute exactly
+  int P1, P2, D, K;
+};
+
+__global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams prm) {
+  extern __shared__ float sx[];  // [4][D]: the warps' query rows
+  constexpr unsigned FULL = 0xffffffffu;
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int qi = blockIdx.x * 4 + wib;
+  if (qi >= prm.P1) return;
+  const int D = prm.D, K = prm.K;
+  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
+  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
+  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
+  const size_t qrow = static_cast<size_t>(n) * prm.P1 + qi;
+  int64_t* oi = prm.idx + qrow * K;
+  float* od = prm.dists + qrow * K;
+  if (lane == 0) prm.flags[qrow] = 0;
+  if (qi >= L1 || L2 == 0) {
+    for (int k = lane; k < K; k += 32) {
+      oi[k] = 0;
+      od[k] = 0.0f;
+    }
+    return;
+  }
+  // query row -> shared memory, |x|^2
+  float* x = sx + wib * D;
+  const float* xg = prm.p1 + qrow * D;
+  float xx = 0.0f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = xg[d];
+    x[d] = v;
+    xx = fmaf(v, v, xx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) xx += __shfl_xor_sync(FULL, xx, o);
+  __syncwarp();
+
+  const uint64_t key = prm.lists[qrow * TC_LIST + lane];
+  const bool have = key != kEmptyKey;
+  const float s = have ? sortable2f(static_cast<uint32_t>(key >> 32)) : __int_as_float(0x7f800000);
+  const uint32_t j = static_cast<uint32_t>(key & 0xFFFFFFFFull);
+
+  // E (see the header); every factor rounded up, 1 % slack on top
+  const float My2 = __uint_as_float(prm.maxw_bits[n]) * 1.0001f;
+  const float xx_up = xx * 1.0001f;
+  const float c1 = 0.00390625f * (1.0f + 0.00048828125f + static_cast<float>(D) * 0.0001220703125f) + 1.2e-7f;
+  const float c2 = static_cast<float>(3 * D + 8) * 5.9604645e-08f;
+  const float E = 1.01f * (c1 * sqrtf(xx_up * My2) * 1.0001f + c2 * (xx_up + My2));
+  const int kth = min(K, L2);
+  const float sK = __shfl_sync(FULL, s, kth - 1);           // the list is ascending: lane k = (k+1)-th smallest s
+  const float tau = __fadd_ru(sK, __fmul_ru(2.0f, E));
+  const bool active = have && s <= tau;
+  const float s_last = __shfl_sync(FULL, s, TC_LIST - 1);
+  const bool last_have = __shfl_sync(FULL, have ? 1 : 0, TC_LIST - 1) != 0;
+  if (L2 > TC_LIST && last_have && s_last <= tau) {
+    // the list may have dropped a point within tau: exact recomputation (knn_generic_kernel)
+    if (lane == 0) prm.flags[qrow] = 1;
+    return;
+  }
+  // exact reference distance for the active entries: same operations, same order (knn_cpu.cpp:42-50)
+  float dist = 0.0f;
+  if (active) {
+    const float* y = prm.p2 + (static_cast<size_t>(n) * prm.P2 + j) * D;
+    if ((D & 3) == 0) {
+      for (int d = 0; d < D; d += 4) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + d);
+        const float4 xv = *reinterpret_cast<const float4*>(x + d);
+        float df = __fsub_rn(xv.x, yv.x);
+        dist = __fadd_rn(dist, __fmul_rn(df, df));
+        df = __fsub_rn(xv.y, yv.y);
+        dist = __fadd_rn(dist, __fmul_rn(df, df));
+        df = __fsub_rn(xv.z, yv.z);
+        dist = __fadd_rn(dist, __fmul_rn(df, df));
+        df = __fsub_rn(xv.w, yv.w);
+        dist = __fadd_rn(dist, __fmul_rn(df, df));
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        const float df = __fsub_rn(x[d], y[d]);
+        dist = __fadd_rn(dist, __fmul_rn(df, df));
+      }
+    }
+  }
+  uint64_t k2 = active ? make_key(dist, j) : kEmptyKey;
+  // bitonic sort of the 32 keys across the warp, ascending
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const uint64_t other = __shfl_xor_sync(FULL, k2, stride);
+      const bool up = (lane & size) == 0;         // ascending block
+      const bool lower = (lane & stride) == 0;    // this lane keeps the smaller of the pair when ascending
+      const bool take_min = (up == lower);
+      k2 = take_min ? (other < k2 ? other : k2) : (other > k2 ? other : k2);
+    }
+  }
+  if (lane < K) {
+    const bool ok = k2 != kEmptyKey;
+    oi[lane] = ok ? static_cast<int64_t>(k2 & 0xFFFFFFFFull) : 0;
+    od[lane] = ok ? key_dist(k2) : 0.0f;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// (N, P, D) f32 row-major as a 3-D tensor map: box = 32 floats x `rows` points x 1 cloud, 128B swizzle
+int make_map(CUtensorMap* map, const float* base, int64_t N, int64_t P, int64_t D, int rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(POPS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {cuuint64_t(D), cuuint64_t(P), cuuint64_t(N)};
+  const cuuint64_t strides[2] = {cuuint64_t(D) * 4, cuuint64_t(P) * cuuint64_t(D) * 4};
+  const cuuint32_t box[3] = {TC_KBLK, cuuint32_t(rows), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(POPS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+  return POPS_OK;
+}
+
+struct TcLayout {
+  int P2pad;
+  size_t w_off, maxw_off, lists_off, flags_off, total;
+};
+
+TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
+  TcLayout l;
+  l.P2pad = static_cast<int>((P2 + TC_N - 1) / TC_N * TC_N);
+  size_t off = 0;
+  l.maxw_off = off;  off += align_up(size_t(N) * 4, 256);
+  l.w_off = off;     off += align_up(size_t(N) * l.P2pad * 4, 256);
+  l.lists_off = off; off += align_up(size_t(N) * P1 * TC_LIST * 8, 256);
+  l.flags_off = off; off += align_up(size_t(N) * P1, 256);
+  l.total = off;
+  return l;
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+inline size_t tc_smem_fixed(int KB) {
+  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_M * 8 + 2 * TC_N * 4 + (2 * TC_MAX_STAGES + 2 * TC_ABUF + 2) * 8 +
+         1024 /* alignment */;
+}
+
+}  // namespace
+
+bool knn_tc_supported(int64_t P1, int64_t P2, int64_t D, int64_t K, int norm) {
+  static const int force = getenv("POPS_KNN_TC") ? atoi(getenv("POPS_KNN_TC")) : -1;  // test aid
+  if (force == 0) return false;
+  if (norm != 2 || K > 16 || K < 1 || D < 32 || D > 256 || (D & 3) != 0) return false;
+  if (P2 >= (int64_t(1) << 31) - TC_N) return false;
+  const int KB = static_cast<int>((D + TC_KBLK - 1) / TC_KBLK);
+  if (tc_smem_fixed(KB) + 2 * TC_STAGE_BYTES > kSmemLimit) return false;
+  if (force > 0) return true;
+  return P2 >= 512 && P1 >= 64;  // below that the exact generic kernel is as fast
+}
+
+size_t knn_tc_workspace_bytes(int64_t N, int64_t P1, int64_t P2) { return tc_layout(N, P1, P2).total + 256; }
+
+// Runs norms + scan + rerank; on return `*flags_out` (N*P1 bytes, device) marks the queries the
+// caller must recompute with the exact generic kernel.
+int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1,
+                  int P2, int D, int K, int64_t* idx, float* dists, void* ws, unsigned char** flags_out,
+                  cudaStream_t st) {
+  const TcLayout l = tc_layout(N, P1, P2);
+  char* base = reinterpret_cast<char*>(ws);
+  unsigned* maxw = reinterpret_cast<unsigned*>(base + l.maxw_off);
+  float* w = reinterpret_cast<float*>(base + l.w_off);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(base + l.lists_off);
+  unsigned char* flags = reinterpret_cast<unsigned char*>(base + l.flags_off);
+  *flags_out = flags;
+
+  POPS_CUDA_OK(cudaMemsetAsync(maxw, 0, size_t(N) * 4, st));
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(l.P2pad, 8)), N);
+    tc_norm_kernel<<<grid, 256, 0, st>>>(p2, len2, P2, l.P2pad, D, w, maxw);
+    POPS_LAUNCH_OK("tc_norm_kernel");
+  }
+  CUtensorMap map_q, map_p;
+  int rc = make_map(&map_q, p1, N, P1, D, TC_M);
+  if (rc != POPS_OK) return rc;
+  rc = make_map(&map_p, p2, N, P2, D, TC_N);
+  if (rc != POPS_OK) return rc;
+
+  TcParams prm;
+  prm.w = w; prm.len1 = len1; prm.len2 = len2; prm.lists = lists;
+  prm.P1 = P1; prm.P2 = P2; prm.P2pad = l.P2pad;
+  prm.KB = (D + TC_KBLK - 1) / TC_KBLK;
+  const size_t fixed = tc_smem_fixed(prm.KB);
+  prm.nstage = static_cast<int>(std::min<size_t>(TC_MAX_STAGES, (kSmemLimit - fixed) / TC_STAGE_BYTES));
+  const size_t smem = fixed + size_t(prm.nstage) * TC_STAGE_BYTES;
+  POPS_CUDA_OK(cudaFuncSetAttribute(knn_tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(P1, TC_M)), N);
+    profile_begin("knn_tc_scan", st);
+    knn_tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(map_q, map_p, prm);
+    profile_end("knn_tc_scan", st);
+    POPS_LAUNCH_OK("knn_tc_scan_kernel");
+  }
+  TcRerankParams rp;
+  rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.lists = lists; rp.maxw_bits = maxw;
+  rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.P1 = P1; rp.P2 = P2; rp.D = D; rp.K = K;
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(P1, 4)), N);
+    profile_begin("knn_tc_rerank", st);
+    knn_tc_rerank_kernel<<<grid, 128, size_t(4) * D * 4, st>>>(rp);
+    profile_end("knn_tc_rerank", st);
+    POPS_LAUNCH_OK("knn_tc_rerank_kernel");
+  }
+  return POPS_OK;
+}
+
+}  // namespace pops
