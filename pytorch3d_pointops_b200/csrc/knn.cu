@@ -371,6 +371,8 @@ struct KnnGenericParams {
   int P1, P2, D, K, TP;
   int lists_in_smem;
   const unsigned char* flags;  // [N][P1] or nullptr: when set, only flagged queries are (re)computed
+  const unsigned* flag_count;  // with flags: number of flagged queries; this kernel runs only above
+  unsigned flag_limit;         //   flag_limit of them (below, knn_exact_rows_kernel has done the work)
 };
 
 template <int NORM, int THREADS>
@@ -386,6 +388,7 @@ knn_generic_kernel(const KnnGenericParams prm) {
   const bool valid = qi < L1;
   bool wanted = true;
   if (prm.flags) {  // exact recomputation of the queries the tensor-core path could not certify
+    if (*prm.flag_count <= prm.flag_limit) return;
     wanted = qi < prm.P1 && prm.flags[static_cast<size_t>(n) * prm.P1 + qi] != 0;
     if (!__syncthreads_or(wanted ? 1 : 0)) return;
   }
@@ -646,12 +649,13 @@ extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64
 #undef POPS_TILED
   // generic (also the exact recomputation pass behind the tensor-core path)
   KnnGenericParams prm;
-  prm.flags = nullptr;
+  prm.flags = nullptr; prm.flag_count = nullptr; prm.flag_limit = 0;
   if (knn_tc_supported(P1, P2, D, K, norm)) {
     const size_t goff = align_up(size_t(N) * ceil_div(P1, kGenericThreads) * K * kGenericThreads * 8, 256);
     unsigned char* flags = nullptr;
     const int rc = knn_tc_search(p1, p2, lengths1, lengths2, n, p1n, p2n, int(D), k, idx, dists,
-                                 reinterpret_cast<char*>(workspace) + goff, &flags, st);
+                                 reinterpret_cast<char*>(workspace) + goff, &flags, &prm.flag_count,
+                                 &prm.flag_limit, st);
     if (rc != POPS_OK) return rc;
     prm.flags = flags;
   }
@@ -662,6 +666,7 @@ extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64
   generic_layout(int(D), k, &prm.TP, &prm.lists_in_smem, &smem);
   if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: D too large for the generic kernel");
   dim3 grid(static_cast<unsigned>(ceil_div(P1, kGenericThreads)), n);
+  profile_begin("knn_generic", st);
   if (norm == 2) {
     auto kern = knn_generic_kernel<2, kGenericThreads>;
     POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -671,6 +676,7 @@ extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64
     POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     kern<<<grid, kGenericThreads, smem, st>>>(prm);
   }
+  profile_end("knn_generic", st);
   POPS_LAUNCH_OK("knn_generic_kernel");
   return POPS_OK;
 }

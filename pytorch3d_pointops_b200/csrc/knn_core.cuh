@@ -270,6 +270,6 @@ bool knn_tc_supported(int64_t P1, int64_t P2, int64_t D, int64_t K, int norm);
 size_t knn_tc_workspace_bytes(int64_t N, int64_t P1, int64_t P2);
 int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1,
                   int P2, int D, int K, int64_t* idx, float* dists, void* ws, unsigned char** flags_out,
-                  cudaStream_t st);
+                  const unsigned** flag_count_out, unsigned* flag_limit_out, cudaStream_t st);
 
 }  // namespace pops

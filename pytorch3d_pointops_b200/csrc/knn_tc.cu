@@ -63,6 +63,7 @@ struct TcParams {
   int P1, P2, P2pad;
   int KB;                  // k-blocks = ceil(D / 32)
   int nstage;              // stages of the p2 ring
+  int dbg;                 // development: 1 = never buffer a candidate (timing the MMA pipeline alone)
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -73,6 +74,25 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
           "r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// same load, delivered to the same shared-memory offset of every CTA in `mask` (each CTA's own
+// mbarrier at that offset receives the bytes)
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -102,6 +122,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -118,7 +146,17 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Wait for this thread's outstanding tcgen05.ld.  The registers are in/out operands so that no
+// use of them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // K-major, 128-byte-swizzled operand tile (rows of 128 bytes, 8-row atoms 1024 bytes apart):
 // start address >> 4 | LBO (ignored for swizzled K-major) = 1 | SBO = 1024 >> 4 | version 1 |
@@ -231,6 +269,11 @@ __device__ __noinline__ float tc_flush(uint2* cand_col, int count, uint64_t* lis
   return T;
 }
 
+// CL = CTAs per cluster.  The CTAs of a cluster work on CL consecutive query tiles of ONE cloud and
+// walk the same p2 tiles in lock step: each loads 1/CL of every stage and multicasts it to all, so
+// L2 -> shared-memory traffic drops by CL (one CTA per 128 queries streaming all of p2 by itself
+// needs more than the L2 can deliver: measured 5.1 TB/s, 3x the MMA time).
+template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                    const TcParams prm) {
@@ -244,7 +287,11 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   int64_t L1l = prm.len1[n], L2l = prm.len2[n];
   const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
   const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
-  if (q_base >= L1 || L2 == 0) return;  // the rerank kernel writes the (0, 0) rows
+  // the rerank kernel writes the (0, 0) rows.  A CTA without valid queries still has to feed and
+  // release its cluster (L2 is the same for the whole cluster: same cloud).
+  if (L2 == 0 || (CL == 1 && q_base >= L1)) return;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
   const int KB = prm.KB, NST = prm.nstage;
   const int num_tiles = (L2 + TC_N - 1) / TC_N;
 
@@ -264,7 +311,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);  // every CTA of the cluster has consumed the stage
     }
     for (int b = 0; b < TC_ABUF; ++b) {
       mbar_init(&tfull[b], 1);
@@ -277,6 +324,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -290,9 +338,15 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       uint32_t ph = 0;
       for (int t = 0; t < num_tiles; ++t) {
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_sleep(&empty[s], ph ^ 1, 128);
           mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-          tma_load_3d(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4), &map_p, kb * TC_KBLK, t * TC_N, n, &full[s]);
+          if (CL == 1) {
+            tma_load_3d(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4), &map_p, kb * TC_KBLK, t * TC_N, n, &full[s]);
+          } else {  // this CTA's slice of the rows, to every CTA of the cluster
+            constexpr int SL = TC_N / CL;
+            tma_load_3d_mc(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4) + crank * (SL * 32), &map_p, kb * TC_KBLK,
+                           t * TC_N + static_cast<int>(crank) * SL, n, &full[s], kMask);
+          }
           if (++s == NST) {
             s = 0;
             ph ^= 1;
@@ -309,11 +363,11 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       uint32_t ph = 0;
       for (int t = 0; t < num_tiles; ++t) {
         const int b = t % TC_ABUF;
-        mbar_wait(&tempty[b], ((t / TC_ABUF) & 1) ^ 1);  // the epilogue has drained this buffer
+        mbar_wait_sleep(&tempty[b], ((t / TC_ABUF) & 1) ^ 1, 64);  // the epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * TC_N);
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[s], ph);
+          mbar_wait_sleep(&full[s], ph, 32);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4));
           const uint64_t bdesc = umma_desc_sw128(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4));
@@ -321,7 +375,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           for (int k = 0; k < TC_KBLK / 8; ++k)  // K = 8 per tf32 MMA: 32 bytes along the swizzled row
             umma_tf32(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), kTcIdesc,
                       (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+          // the stage may be refilled once these MMAs have read it
+          if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kMask);
           if (++s == NST) {
             s = 0;
             ph ^= 1;
@@ -337,7 +392,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int et = (warp - 2) * 32 + lane;  // 0..127: index among the epilogue threads
     const int qi = q_base + row;
     const float INF = __int_as_float(0x7f800000);
-    float T = (qi < L1) ? INF : -INF;   // rows beyond lengths1 never buffer anything
+    float T = (qi < L1 && !(prm.dbg & 1)) ? INF : -INF;   // rows beyond lengths1 never buffer anything
     uint64_t* list = prm.lists + (static_cast<size_t>(n) * prm.P1 + min(qi, prm.P1 - 1)) * TC_LIST;
     if (qi < L1) {
 #pragma unroll
@@ -360,26 +415,35 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_wait(&tfull[b], (t / TC_ABUF) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TC_N);
-#pragma unroll 1
+      // accumulators come back 32 columns at a time; the next chunk's tcgen05.ld is in flight while
+      // the current one is evaluated
+      uint32_t acc[2][32];
+      tmem_ld_x32(taddr, acc[0]);
+#pragma unroll
       for (int c = 0; c < TC_N / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld_x32(taddr + static_cast<uint32_t>(c * 32), acc);
-        tmem_ld_wait();
+        uint32_t(&cur)[32] = acc[c & 1];
+        tmem_ld_wait(cur);
+        if (c + 1 < TC_N / 32) tmem_ld_x32(taddr + static_cast<uint32_t>((c + 1) * 32), acc[(c + 1) & 1]);
+        float wv[32];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wt + c * 32 + i4 * 4);
+          wv[i4 * 4] = w4.x; wv[i4 * 4 + 1] = w4.y; wv[i4 * 4 + 2] = w4.z; wv[i4 * 4 + 3] = w4.w;
+        }
+        const uint32_t jc = static_cast<uint32_t>(t * TC_N + c * 32);
 #pragma unroll
         for (int sub = 0; sub < 32 / TC_SUB; ++sub) {
+          float sv[TC_SUB];
 #pragma unroll
-          for (int i4 = 0; i4 < TC_SUB / 4; ++i4) {
-            const int col = c * 32 + sub * TC_SUB + i4 * 4;
-            const float4 w4 = *reinterpret_cast<const float4*>(wt + col);
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          for (int i = 0; i < TC_SUB; ++i)
+            sv[i] = fmaf(-2.0f, __uint_as_float(cur[sub * TC_SUB + i]), wv[sub * TC_SUB + i]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float s = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + i]), wv[i]);
-              if (s <= T) {  // predicated: one 64-bit store + one add
-                const uint32_t j = static_cast<uint32_t>(t * TC_N + col + i);
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cw), "r"(__float_as_uint(s)), "r"(j) : "memory");
-                cw += CSTRIDE;
-              }
+          for (int i = 0; i < TC_SUB; ++i) {
+            if (sv[i] <= T) {  // predicated: one 64-bit store + one add (no "memory" clobber: the
+                               // buffer is only read back inside tc_flush, an opaque call)
+              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cw), "r"(__float_as_uint(sv[i])),
+                           "r"(jc + static_cast<uint32_t>(sub * TC_SUB + i)));
+              cw += CSTRIDE;
             }
           }
           if (__any_sync(FULL, cw > cw_limit)) {
@@ -401,6 +465,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still write or signal here
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_ABUF * TC_N);
@@ -410,6 +475,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 // ---------------------------------------------------------------------------------------------
 // rerank: one warp per query
 // ---------------------------------------------------------------------------------------------
+__device__ unsigned g_tc_dbg = 0;
+
 struct TcRerankParams {
   const float* p1;
   const float* p2;
@@ -420,7 +487,9 @@ struct TcRerankParams {
   int64_t* idx;
   float* dists;
   unsigned char* flags;  // [N][P1]: 1 = recompute exactly
+  unsigned* flag_rows;   // compact list of the flagged rows (n * P1 + i); flag_rows[-1] is the counter
   int P1, P2, D, K;
+  int debug;
 };
 
 __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams prm) {
@@ -477,7 +546,12 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
   const bool last_have = __shfl_sync(FULL, have ? 1 : 0, TC_LIST - 1) != 0;
   if (L2 > TC_LIST && last_have && s_last <= tau) {
     // the list may have dropped a point within tau: exact recomputation (knn_generic_kernel)
-    if (lane == 0) prm.flags[qrow] = 1;
+    if (lane == 0) {
+      prm.flags[qrow] = 1;
+      prm.flag_rows[atomicAdd(prm.flag_rows - 1, 1u)] = static_cast<unsigned>(qrow);
+    }
+    if (prm.debug && lane == 0 && atomicAdd(&g_tc_dbg, 1u) < 12u)
+      printf("flag n=%d q=%d sK=%g s_last=%g tau=%g E=%g xx=%g My2=%g kth=%d\n", n, qi, sK, s_last, tau, E, xx, My2, kth);
     return;
   }
   // exact reference distance for the active entries: same operations, same order (knn_cpu.cpp:42-50)
@@ -524,6 +598,82 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// exact recomputation of the flagged queries: one CTA per flagged row, every thread scans a
+// strided share of p2 with the reference arithmetic and keeps its own sorted top-KT in registers;
+// K rounds of block-wide arg-min over the threads' current heads produce the result in order.
+// Rows are few on generic data (a handful per million queries); beyond `limit` rows the dense
+// generic kernel (knn.cu) takes over instead, CTA by CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExactThreads = 256;
+
+template <int KT>
+__global__ void __launch_bounds__(kExactThreads)
+knn_exact_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                      const int64_t* __restrict__ len2, const unsigned* __restrict__ flag_rows, unsigned limit,
+                      int P1, int P2, int D, int K, int64_t* __restrict__ idx, float* __restrict__ dists) {
+  extern __shared__ __align__(16) unsigned char esm[];
+  float* x = reinterpret_cast<float*>(esm);                                   // [D]
+  uint64_t* red = reinterpret_cast<uint64_t*>(esm + align_up(size_t(D) * 4, 16));  // [8] warp minima + [1] winner
+  const unsigned count = flag_rows[-1];
+  if (count > limit) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (unsigned f = blockIdx.x; f < count; f += gridDim.x) {
+    const size_t qrow = flag_rows[f];
+    const int n = static_cast<int>(qrow / P1);
+    int64_t L2l = len2[n];
+    const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > P2 ? P2 : L2l));
+    __syncthreads();
+    for (int d = tid; d < D; d += kExactThreads) x[d] = p1[qrow * D + d];
+    __syncthreads();
+    uint64_t Lr[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) Lr[k] = kEmptyKey;
+    for (int j = tid; j < L2; j += kExactThreads) {
+      const float* y = p2 + (static_cast<size_t>(n) * P2 + j) * D;
+      float dist = 0.0f;
+      for (int d = 0; d < D; ++d) {
+        const float df = __fsub_rn(x[d], y[d]);
+        dist = __fadd_rn(dist, __fmul_rn(df, df));
+      }
+      const uint64_t key = make_key(dist, static_cast<uint32_t>(j));
+      if (key < Lr[KT - 1]) insert_network<KT>(Lr, key);
+    }
+    // K rounds: smallest head wins and its owner pops
+    for (int k = 0; k < K; ++k) {
+      uint64_t m = Lr[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v < m ? v : m;
+      }
+      if (lane == 0) red[warp] = m;
+      __syncthreads();
+      if (warp == 0) {
+        uint64_t v = lane < kExactThreads / 32 ? red[lane] : kEmptyKey;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          const uint64_t u = __shfl_xor_sync(0xffffffffu, v, o);
+          v = u < v ? u : v;
+        }
+        if (lane == 0) red[8] = v;
+      }
+      __syncthreads();
+      const uint64_t win = red[8];
+      if (win != kEmptyKey && Lr[0] == win) {  // keys are unique: exactly one owner
+#pragma unroll
+        for (int q = 0; q + 1 < KT; ++q) Lr[q] = Lr[q + 1];
+        Lr[KT - 1] = kEmptyKey;
+      }
+      if (tid == 0) {
+        idx[qrow * K + k] = win != kEmptyKey ? static_cast<int64_t>(win & 0xFFFFFFFFull) : 0;
+        dists[qrow * K + k] = win != kEmptyKey ? key_dist(win) : 0.0f;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -557,7 +707,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t N, int64_t P, int64_t 
 
 struct TcLayout {
   int P2pad;
-  size_t w_off, maxw_off, lists_off, flags_off, total;
+  size_t w_off, maxw_off, lists_off, flags_off, rows_off, total;
 };
 
 TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
@@ -568,6 +718,7 @@ TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
   l.w_off = off;     off += align_up(size_t(N) * l.P2pad * 4, 256);
   l.lists_off = off; off += align_up(size_t(N) * P1 * TC_LIST * 8, 256);
   l.flags_off = off; off += align_up(size_t(N) * P1, 256);
+  l.rows_off = off;  off += align_up(size_t(N) * P1 * 4 + 256, 256);  // counter lives 4 bytes before the list
   l.total = off;
   return l;
 }
@@ -597,7 +748,7 @@ size_t knn_tc_workspace_bytes(int64_t N, int64_t P1, int64_t P2) { return tc_lay
 // caller must recompute with the exact generic kernel.
 int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1,
                   int P2, int D, int K, int64_t* idx, float* dists, void* ws, unsigned char** flags_out,
-                  cudaStream_t st) {
+                  const unsigned** flag_count_out, unsigned* flag_limit_out, cudaStream_t st) {
   const TcLayout l = tc_layout(N, P1, P2);
   char* base = reinterpret_cast<char*>(ws);
   unsigned* maxw = reinterpret_cast<unsigned*>(base + l.maxw_off);
@@ -605,6 +756,11 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   uint64_t* lists = reinterpret_cast<uint64_t*>(base + l.lists_off);
   unsigned char* flags = reinterpret_cast<unsigned char*>(base + l.flags_off);
   *flags_out = flags;
+  unsigned* flag_rows = reinterpret_cast<unsigned*>(base + l.rows_off + 256);
+  *flag_count_out = flag_rows - 1;
+  const unsigned limit = 4096;  // flagged rows the per-row kernel takes; more -> dense generic kernel
+  *flag_limit_out = limit;
+  POPS_CUDA_OK(cudaMemsetAsync(flag_rows - 1, 0, 4, st));
 
   POPS_CUDA_OK(cudaMemsetAsync(maxw, 0, size_t(N) * 4, st));
   {
@@ -612,36 +768,65 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
     tc_norm_kernel<<<grid, 256, 0, st>>>(p2, len2, P2, l.P2pad, D, w, maxw);
     POPS_LAUNCH_OK("tc_norm_kernel");
   }
+  static const int cl_env = getenv("POPS_TC_CLUSTER") ? atoi(getenv("POPS_TC_CLUSTER")) : 4;  // tuning aid
+  const int64_t qtiles = ceil_div(P1, TC_M);
+  const int CL = (cl_env >= 4 && qtiles >= 4) ? 4 : ((cl_env >= 2 && qtiles >= 2) ? 2 : 1);
   CUtensorMap map_q, map_p;
   int rc = make_map(&map_q, p1, N, P1, D, TC_M);
   if (rc != POPS_OK) return rc;
-  rc = make_map(&map_p, p2, N, P2, D, TC_N);
+  rc = make_map(&map_p, p2, N, P2, D, TC_N / CL);
   if (rc != POPS_OK) return rc;
 
   TcParams prm;
   prm.w = w; prm.len1 = len1; prm.len2 = len2; prm.lists = lists;
   prm.P1 = P1; prm.P2 = P2; prm.P2pad = l.P2pad;
   prm.KB = (D + TC_KBLK - 1) / TC_KBLK;
+  prm.dbg = getenv("POPS_TC_DBG") ? atoi(getenv("POPS_TC_DBG")) : 0;
   const size_t fixed = tc_smem_fixed(prm.KB);
   prm.nstage = static_cast<int>(std::min<size_t>(TC_MAX_STAGES, (kSmemLimit - fixed) / TC_STAGE_BYTES));
   const size_t smem = fixed + size_t(prm.nstage) * TC_STAGE_BYTES;
-  POPS_CUDA_OK(cudaFuncSetAttribute(knn_tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   {
-    dim3 grid(static_cast<unsigned>(ceil_div(P1, TC_M)), N);
+    void (*kern)(const CUtensorMap, const CUtensorMap, const TcParams) =
+        CL == 4 ? knn_tc_scan_kernel<4> : (CL == 2 ? knn_tc_scan_kernel<2> : knn_tc_scan_kernel<1>);
+    POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(ceil_div(qtiles, CL) * CL), N);  // whole clusters; spare CTAs see no query
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     profile_begin("knn_tc_scan", st);
-    knn_tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(map_q, map_p, prm);
+    POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_q, map_p, prm));
     profile_end("knn_tc_scan", st);
     POPS_LAUNCH_OK("knn_tc_scan_kernel");
   }
   TcRerankParams rp;
   rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.lists = lists; rp.maxw_bits = maxw;
-  rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.P1 = P1; rp.P2 = P2; rp.D = D; rp.K = K;
+  rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.flag_rows = flag_rows; rp.P1 = P1; rp.P2 = P2; rp.D = D; rp.K = K;
+  rp.debug = getenv("POPS_KNN_STATS") ? 1 : 0;
   {
     dim3 grid(static_cast<unsigned>(ceil_div(P1, 4)), N);
     profile_begin("knn_tc_rerank", st);
     knn_tc_rerank_kernel<<<grid, 128, size_t(4) * D * 4, st>>>(rp);
     profile_end("knn_tc_rerank", st);
     POPS_LAUNCH_OK("knn_tc_rerank_kernel");
+  }
+  {
+    const size_t esmem = align_up(size_t(D) * 4, 16) + 9 * 8;
+    const int grid = num_sms() * 2;
+    profile_begin("knn_exact_rows", st);
+    if (K <= 4)
+      knn_exact_rows_kernel<4><<<grid, kExactThreads, esmem, st>>>(p1, p2, len2, flag_rows, limit, P1, P2, D, K, idx, dists);
+    else
+      knn_exact_rows_kernel<16><<<grid, kExactThreads, esmem, st>>>(p1, p2, len2, flag_rows, limit, P1, P2, D, K, idx, dists);
+    profile_end("knn_exact_rows", st);
+    POPS_LAUNCH_OK("knn_exact_rows_kernel");
   }
   return POPS_OK;
 }
