@@ -100,23 +100,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// same, for single-thread roles that share a scheduler with working warps: sleep between polls so
-// the spin does not eat issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(ns);
-  }
+// same, for single-thread roles that share a scheduler with working warps: the suspend-time hint
+// lets the hardware park the thread until the phase completes (or the hint expires) instead of
+// burning issue slots in a polling loop
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "PARK_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra PARK_DONE;\n\t"
+      "bra PARK_LOOP;\n\t"
+      "PARK_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 // 1-D bulk global->shared copy completing on an mbarrier.  dst/src 16-byte aligned, bytes % 16 == 0.
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,

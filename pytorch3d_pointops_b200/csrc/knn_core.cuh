@@ -60,6 +60,31 @@ __device__ __forceinline__ void insert_network(uint64_t (&Lr)[KT], uint64_t key)
 
 static_assert(kSurvCap == 16, "sort16 assumes 16 survivor slots");
 
+// Batcher odd-even merge sort of v[OFF .. OFF+N) (N a power of two), ascending; fully unrolled, so
+// every index is static and the values stay in registers (63 compare-exchanges for N = 16).
+template <int N, int OFF, int TOTAL>
+__device__ __forceinline__ void sort_floats(float (&v)[TOTAL]) {
+#pragma unroll
+  for (int p = 1; p < N; p *= 2) {
+#pragma unroll
+    for (int k = p; k >= 1; k /= 2) {
+#pragma unroll
+      for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+          if (i <= N - j - k - 1 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+            const float lo = fminf(v[OFF + i + j], v[OFF + i + j + k]);
+            const float hi = fmaxf(v[OFF + i + j], v[OFF + i + j + k]);
+            v[OFF + i + j] = lo;
+            v[OFF + i + j + k] = hi;
+          }
+        }
+      }
+    }
+  }
+}
+
+
 // Merge one lane's `ns` survivor keys (column S, stride SSTRIDE) into its ascending K-list kept in
 // the OUTPUT arrays (od, oi); warp-converged, `ns_max` = the largest ns in the warp.  Few
 // survivors -> branch-free insertion network per survivor; many -> sort network + bitonic merge.

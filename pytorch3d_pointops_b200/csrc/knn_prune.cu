@@ -112,30 +112,6 @@ __device__ __forceinline__ void exact4(float q0, float q1, float q2, float4 X, f
   d4[3] = __fadd_rn(__fadd_rn(xx23.y, yy23.y), zz23.y);
 }
 
-// Batcher odd-even merge sort of v[OFF .. OFF+N) (N a power of two), ascending; fully unrolled, so
-// every index is static and the values stay in registers (63 compare-exchanges for N = 16).
-template <int N, int OFF, int TOTAL>
-__device__ __forceinline__ void sort_floats(float (&v)[TOTAL]) {
-#pragma unroll
-  for (int p = 1; p < N; p *= 2) {
-#pragma unroll
-    for (int k = p; k >= 1; k /= 2) {
-#pragma unroll
-      for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
-#pragma unroll
-        for (int i = 0; i < k; ++i) {
-          if (i <= N - j - k - 1 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-            const float lo = fminf(v[OFF + i + j], v[OFF + i + j + k]);
-            const float hi = fmaxf(v[OFF + i + j], v[OFF + i + j + k]);
-            v[OFF + i + j] = lo;
-            v[OFF + i + j + k] = hi;
-          }
-        }
-      }
-    }
-  }
-}
-
 // Seed bound of one query: exact distances to the `nseed` blocks at the start of the warp's ring;
 // minimum over each of NS interleaved subsets of the points (NS distinct points: the subsets are
 // disjoint), then the KT-th smallest of those minima.  KT distinct points lie within the result,

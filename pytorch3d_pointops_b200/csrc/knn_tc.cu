@@ -11,18 +11,23 @@
 //            x_i . y_j for 128 x 128 (query, point) pairs into one of four TMEM buffers; four
 //            epilogue warps pull the accumulators back with tcgen05.ld and evaluate
 //                s_ij = w_j - 2 acc_ij   ~   d(x_i, y_j) - |x_i|^2
-//            per pair: one FFMA, one compare, a predicated append of (s, j) when s does not exceed
-//            the query's current threshold.  Thresholds come from the query's APPROXIMATE list: the
-//            32 smallest (s, j) seen so far, kept in global memory (L2) and merged with register
-//            sorting networks when a candidate buffer fills up -- no p2 row is touched outside
-//            the tensor cores during the scan.
-//   rerank   one warp per query: with E >= |s_ij + |x_i|^2 - d_ref(i,j)| (bound below), every true
-//            neighbour has s <= tau = s_(K) + 2E.  The entries of the list within tau (typically
+//            per pair: one FFMA, one min into a register tournament (32 running minima over
+//            disjoint subsets of the columns), and -- only when some lane of the warp has a hit --
+//            a predicated append of (s, j) when s <= threshold.  The threshold is
+//            (16th smallest of the 32 minima) + 2E: 16 distinct points lie within that minimum, so
+//            it bounds the final K-th smallest s from above at any time, and every point the
+//            re-rank can need satisfies s <= s_(K) + 2E.  It is refreshed on a geometric schedule.
+//            Candidates are staged in shared memory and spilled, re-filtered with the current
+//            threshold, to a per-query array in global memory: no sorting, no list upkeep and no
+//            p2 row touched outside the tensor cores during the scan.
+//   rerank   one warp per query: the 32 smallest (s, j) among the query's candidates (bitonic
+//            networks over warp shuffles); with E >= |s_ij + |x_i|^2 - d_ref(i,j)| (bound below)
+//            every true neighbour has s <= tau = s_(K) + 2E.  The entries within tau (typically
 //            K + a few) get the exact reference distance (same unfused operations, same order),
 //            are sorted by the exact 64-bit key, and the first K are the result.
-//   fallback if the 32nd entry of a list is itself within tau, a needed point may have been
-//            dropped: the query is flagged and recomputed by the exact generic kernel (massive
-//            ties / duplicate-heavy clouds; never on generic data).
+//   fallback if the 32nd smallest s is itself within tau, or a candidate array overflowed, the
+//            query is recomputed exactly (knn_exact_rows_kernel; the dense generic kernel when
+//            there are thousands): massive ties / duplicate-heavy clouds, adversarial orders.
 //
 // Error bound.  u = 2^-24.  TF32 operands keep 10 mantissa bits (the low 13 are ignored), so
 // |x^y^ - xy| <= (2^-9 + 2^-20)|xy| per product; fp32 accumulation inside the tensor core is
@@ -47,20 +52,26 @@ constexpr int TC_M = 128;        // queries per CTA = TMEM lanes
 constexpr int TC_N = 128;        // points per tile = TMEM columns per accumulator buffer
 constexpr int TC_KBLK = 32;      // floats per k-block: one 128-byte swizzle span
 constexpr int TC_ABUF = 4;       // accumulator buffers (4 x 128 = all 512 TMEM columns)
-constexpr int TC_LIST = 32;      // K': length of the approximate list (K <= 16)
-constexpr int TC_CAND = 24;      // candidate entries a query buffers between flushes
-constexpr int TC_SUB = 8;        // columns between two buffer-overflow checks
-constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int TC_LIST = 32;      // the re-rank keeps the 32 smallest s of a query (K <= 16)
+constexpr int TC_GCAP = 256;     // candidates a (query, column half) can hold in global memory
+constexpr int TC_TOUR = 32;      // tournament minima per thread; threshold = their 16th smallest
+constexpr int TC_CAND = 24;      // candidate entries a thread stages in shared memory between flushes
+constexpr int TC_SUB = 8;        // columns between two staging-overflow checks
+constexpr int TC_HALVES = 2;      // epilogue warps per TMEM lane quarter: each takes half of a tile's columns
+constexpr int TC_THREADS = 64 + 128 * TC_HALVES;  // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue
+constexpr int TC_CSTRIDE = TC_M * TC_HALVES;      // candidate entries between two slots of one buffer
 constexpr uint32_t TC_STAGE_BYTES = TC_N * 128;  // 16 KB: 128 rows x 128 bytes
 constexpr int TC_MAX_STAGES = 8;
-static_assert(TC_CAND - TC_SUB >= 16, "a flush round takes 16 candidates");
 
 struct TcParams {
   const float* w;          // [N][P2pad]
   const int64_t* len1;
   const int64_t* len2;
-  uint64_t* lists;         // [N][P1][TC_LIST] ascending keys (sortable(s) << 32 | j)
-  int P1, P2, P2pad;
+  const float* xq;         // [N][P1pad] |x_i|^2
+  const unsigned* maxw_bits;  // [N] max_j w_j (float bits)
+  uint2* cands;            // [N][P1][TC_HALVES][TC_GCAP] (s bits, j)
+  unsigned* counts;        // [N][P1][TC_HALVES] entries used; bit 31 = overflowed
+  int P1, P2, P2pad, P1pad, D;
   int KB;                  // k-blocks = ceil(D / 32)
   int nstage;              // stages of the p2 ring
   int dbg;                 // development: 1 = never buffer a candidate (timing the MMA pipeline alone)
@@ -205,68 +216,43 @@ __global__ void tc_norm_kernel(const float* __restrict__ p2, const int64_t* __re
 // ---------------------------------------------------------------------------------------------
 // scan
 // ---------------------------------------------------------------------------------------------
-// Merge a lane's candidates (keys at S[0], S[SSTRIDE], ... , `ns` of them, at most 16) into its
-// ascending TC_LIST-entry list in global memory.  Warp-converged; lanes without candidates skip
-// the list traffic.  Returns the list's last key.
-template <int SSTRIDE>
-__device__ __forceinline__ uint64_t tc_merge(const uint64_t* S, int ns, int ns_max, uint64_t* list) {
-  uint64_t Lr[TC_LIST];
-  const bool mine = ns > 0;
-#pragma unroll
-  for (int k = 0; k < TC_LIST; ++k) Lr[k] = kEmptyKey;
-  if (mine) {
-#pragma unroll
-    for (int k2 = 0; k2 < TC_LIST / 2; ++k2) {
-      const ulonglong2 v = reinterpret_cast<const ulonglong2*>(list)[k2];
-      Lr[2 * k2] = v.x;
-      Lr[2 * k2 + 1] = v.y;
-    }
-  }
-  if (ns_max <= 4) {
-    for (int s2 = 0; s2 < ns_max; ++s2) {
-      const uint64_t key = (s2 < ns) ? S[s2 * SSTRIDE] : kEmptyKey;
-      insert_network<TC_LIST>(Lr, key);
-    }
-  } else {
-    uint64_t Sr[kSurvCap];
-#pragma unroll
-    for (int s2 = 0; s2 < kSurvCap; ++s2) Sr[s2] = (s2 < ns) ? S[s2 * SSTRIDE] : kEmptyKey;
-    sort16(Sr);
-    // TC_LIST smallest of (Lr U Sr): C[i] = min(Lr[i], Sr[TC_LIST-1-i]) is bitonic, then merge
-#pragma unroll
-    for (int i = TC_LIST - kSurvCap; i < TC_LIST; ++i) {
-      const int si = TC_LIST - 1 - i;
-      Lr[i] = (Sr[si] < Lr[i]) ? Sr[si] : Lr[i];
-    }
-    bitonic_merge<TC_LIST>(Lr);
-  }
-  if (mine) {
-#pragma unroll
-    for (int k2 = 0; k2 < TC_LIST / 2; ++k2)
-      reinterpret_cast<ulonglong2*>(list)[k2] = make_ulonglong2(Lr[2 * k2], Lr[2 * k2 + 1]);
-  }
-  return Lr[TC_LIST - 1];
+// E (see the header) from |x|^2 and max_j |y_j|^2; every factor rounded up, 1 % slack on top.
+// The scan and the re-rank call this with identical arguments, so they agree bit for bit.
+__device__ __forceinline__ float tc_error_bound(float xx, float maxw, int D) {
+  const float My2 = maxw * 1.0001f;
+  const float xx_up = xx * 1.0001f;
+  const float c1 = 0.00390625f * (1.0f + 0.00048828125f + static_cast<float>(D) * 0.0001220703125f) + 1.2e-7f;
+  const float c2 = static_cast<float>(3 * D + 8) * 5.9604645e-08f;
+  return 1.01f * (c1 * sqrtf(xx_up * My2) * 1.0001f + c2 * (xx_up + My2));
 }
 
-// Drain one query's candidate buffer (entries (s bits, j), column stride TC_M) into its list.
-// Not inlined: rare, large.  Returns the new threshold: the 32nd smallest s so far (+inf while
-// the list is not full).
-__device__ __noinline__ float tc_flush(uint2* cand_col, int count, uint64_t* list, float T) {
-  constexpr unsigned FULL = 0xffffffffu;
-  // raw (s, j) -> sortable 64-bit keys, in place
-  for (int c = 0; c < count; ++c) {
-    const uint2 e = cand_col[c * TC_M];
-    cand_col[c * TC_M] = make_uint2(e.y, f2sortable(__uint_as_float(e.x)));  // little endian: lo = j, hi = key(s)
+// Spill one thread's staged candidates (column stride TC_CSTRIDE) to its array in global memory,
+// keeping only those still within the current threshold.  When the array is full it is first
+// compacted against the threshold; if that does not help the overflow bit is set and the query
+// will be recomputed exactly.  Not inlined: rare.  Returns the new count.
+__device__ __noinline__ unsigned tc_flush_stage(const uint2* cand_col, int staged, float T, uint2* garr,
+                                                unsigned gcount) {
+  for (int c = 0; c < staged; ++c) {
+    const uint2 e = cand_col[c * TC_CSTRIDE];
+    if (!(__uint_as_float(e.x) <= T)) continue;
+    unsigned cnt = gcount & 0x7fffffffu;
+    if (cnt == TC_GCAP) {
+      unsigned wpos = 0;
+      for (unsigned r = 0; r < TC_GCAP; ++r) {
+        const uint2 g = garr[r];
+        if (__uint_as_float(g.x) <= T) garr[wpos++] = g;
+      }
+      cnt = wpos;
+      gcount = (gcount & 0x80000000u) | cnt;
+      if (cnt > TC_GCAP - 32) {  // still (nearly) full: give up on this query
+        gcount |= 0x80000000u;
+        if (cnt == TC_GCAP) continue;
+      }
+    }
+    garr[cnt] = e;
+    gcount = (gcount & 0x80000000u) | (cnt + 1);
   }
-  __syncwarp();
-  for (int c0 = 0; __any_sync(FULL, c0 < count); c0 += kSurvCap) {
-    const int ns = max(0, min(kSurvCap, count - c0));
-    const int ns_max = __reduce_max_sync(FULL, ns);
-    const uint64_t last =
-        tc_merge<TC_M>(reinterpret_cast<const uint64_t*>(cand_col) + static_cast<size_t>(c0) * TC_M, ns, ns_max, list);
-    if (ns > 0) T = (last == kEmptyKey) ? __int_as_float(0x7f800000) : sortable2f(static_cast<uint32_t>(last >> 32));
-  }
-  return T;
+  return gcount;
 }
 
 // CL = CTAs per cluster.  The CTAs of a cluster work on CL consecutive query tiles of ONE cloud and
@@ -298,9 +284,11 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   float* sA = reinterpret_cast<float*>(smem);                                  // KB x 16 KB
   float* sB = reinterpret_cast<float*>(smem + static_cast<size_t>(KB) * TC_STAGE_BYTES);  // NST x 16 KB
   unsigned char* rest = smem + static_cast<size_t>(KB + NST) * TC_STAGE_BYTES;
-  uint2* cand = reinterpret_cast<uint2*>(rest);                                // TC_CAND x TC_M entries
-  float* sW = reinterpret_cast<float*>(rest + size_t(TC_CAND) * TC_M * 8);     // 2 x TC_N
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 2 * TC_N);
+  uint2* cand = reinterpret_cast<uint2*>(rest);                                // TC_CAND x TC_CSTRIDE staged (s, j)
+  float* sX = reinterpret_cast<float*>(rest + size_t(TC_CAND) * TC_CSTRIDE * 8);  // TC_TOUR x TC_M: minima exchange
+  float* sW = sX + TC_TOUR * TC_M;                                             // 2 x TC_N norms
+  float* sT = sW + 2 * TC_N;                                                   // TC_M tournament bounds
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + TC_M);
   uint64_t* full = bars;                       // [TC_MAX_STAGES]  TMA -> MMA
   uint64_t* empty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]  MMA -> TMA
   uint64_t* tfull = bars + 2 * TC_MAX_STAGES;  // [TC_ABUF]        MMA -> epilogue
@@ -315,7 +303,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     for (int b = 0; b < TC_ABUF; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty[b], 4 * TC_HALVES);  // one arrival per epilogue warp
     }
     mbar_init(afull, 1);
     mbar_fence_init();
@@ -338,7 +326,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       uint32_t ph = 0;
       for (int t = 0; t < num_tiles; ++t) {
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_sleep(&empty[s], ph ^ 1, 128);
+          mbar_wait_parked(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
           if (CL == 1) {
             tma_load_3d(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4), &map_p, kb * TC_KBLK, t * TC_N, n, &full[s]);
@@ -363,11 +351,11 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       uint32_t ph = 0;
       for (int t = 0; t < num_tiles; ++t) {
         const int b = t % TC_ABUF;
-        mbar_wait_sleep(&tempty[b], ((t / TC_ABUF) & 1) ^ 1, 64);  // the epilogue has drained this buffer
+        mbar_wait_parked(&tempty[b], ((t / TC_ABUF) & 1) ^ 1);  // the epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * TC_N);
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_sleep(&full[s], ph, 32);
+          mbar_wait_parked(&full[s], ph);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4));
           const uint64_t bdesc = umma_desc_sw128(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4));
@@ -386,69 +374,82 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   } else {
-    // ===== epilogue: 4 warps, thread = query row =====
-    const int ew = warp & 3;             // the TMEM lane quarter this warp may read
-    const int row = ew * 32 + lane;      // query row inside the tile
-    const int et = (warp - 2) * 32 + lane;  // 0..127: index among the epilogue threads
+    // ===== epilogue: 4 x TC_HALVES warps.  Thread = (query row, half of every tile's columns) =====
+    const int ew = warp & 3;                 // the TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;        // which half of the columns
+    const int row = ew * 32 + lane;          // query row inside the tile
+    const int et = (warp - 2) * 32 + lane;   // index among the epilogue threads
     const int qi = q_base + row;
     const float INF = __int_as_float(0x7f800000);
-    float T = (qi < L1 && !(prm.dbg & 1)) ? INF : -INF;   // rows beyond lengths1 never buffer anything
-    uint64_t* list = prm.lists + (static_cast<size_t>(n) * prm.P1 + min(qi, prm.P1 - 1)) * TC_LIST;
-    if (qi < L1) {
+    constexpr int HC = TC_N / TC_HALVES;     // columns per half
+    static_assert(HC % 32 == 0 && TC_TOUR == 32, "column c of a chunk feeds tournament slot c");
+    const bool live = qi < L1 && !(prm.dbg & 1);
+    const size_t qrow = static_cast<size_t>(n) * prm.P1 + min(qi, prm.P1 - 1);
+    const float E2 = 2.0f * tc_error_bound(prm.xq[static_cast<size_t>(n) * prm.P1pad + min(qi, prm.P1pad - 1)],
+                                           __uint_as_float(prm.maxw_bits[n]), prm.D);
+    float mins[TC_TOUR];   // running minima of s over 32 disjoint subsets of this thread's columns
 #pragma unroll
-      for (int k2 = 0; k2 < TC_LIST / 2; ++k2)
-        reinterpret_cast<ulonglong2*>(list)[k2] = make_ulonglong2(kEmptyKey, kEmptyKey);
-    }
-    uint2* cand_col = cand + row;
+    for (int i = 0; i < TC_TOUR; ++i) mins[i] = INF;
+    float T = live ? INF : -INF;   // append threshold; rows beyond lengths1 never buffer anything
+    uint2* garr = prm.cands + (qrow * TC_HALVES + half) * TC_GCAP;
+    unsigned gcount = 0;
+    uint2* cand_col = cand + half * TC_M + row;
     const uint32_t cand_base = smem_u32(cand_col);
     uint32_t cw = cand_base;
-    constexpr uint32_t CSTRIDE = TC_M * 8;
+    constexpr uint32_t CSTRIDE = TC_CSTRIDE * 8;
     const uint32_t cw_limit = cand_base + static_cast<uint32_t>(TC_CAND - TC_SUB) * CSTRIDE;
     const float* w_n = prm.w + static_cast<size_t>(n) * prm.P2pad;
-    sW[et] = w_n[et];
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const uint32_t sW_addr = smem_u32(sW);
+    if (et < TC_N) sW[et] = w_n[et];
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
     for (int t = 0; t < num_tiles; ++t) {
       const int b = t % TC_ABUF;
-      const float* wt = sW + (t & 1) * TC_N;
+      const uint32_t wt = sW_addr + static_cast<uint32_t>(((t & 1) * TC_N + half * HC) * 4);
       float wnext = 0.0f;
-      if (t + 1 < num_tiles) wnext = w_n[(t + 1) * TC_N + et];
-      mbar_wait(&tfull[b], (t / TC_ABUF) & 1);
+      if (et < TC_N && t + 1 < num_tiles) wnext = w_n[(t + 1) * TC_N + et];
+      mbar_wait_parked(&tfull[b], (t / TC_ABUF) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TC_N);
-      // accumulators come back 32 columns at a time; the next chunk's tcgen05.ld is in flight while
-      // the current one is evaluated
-      uint32_t acc[2][32];
-      tmem_ld_x32(taddr, acc[0]);
-#pragma unroll
-      for (int c = 0; c < TC_N / 32; ++c) {
-        uint32_t(&cur)[32] = acc[c & 1];
-        tmem_ld_wait(cur);
-        if (c + 1 < TC_N / 32) tmem_ld_x32(taddr + static_cast<uint32_t>((c + 1) * 32), acc[(c + 1) & 1]);
-        float wv[32];
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wt + c * 32 + i4 * 4);
-          wv[i4 * 4] = w4.x; wv[i4 * 4 + 1] = w4.y; wv[i4 * 4 + 2] = w4.z; wv[i4 * 4 + 3] = w4.w;
-        }
-        const uint32_t jc = static_cast<uint32_t>(t * TC_N + c * 32);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TC_N + half * HC);
+#pragma unroll 1
+      for (int c = 0; c < HC / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_x32(taddr + static_cast<uint32_t>(c * 32), acc);
+        tmem_ld_wait(acc);
+        const uint32_t jc = static_cast<uint32_t>(t * TC_N + half * HC + c * 32);
 #pragma unroll
         for (int sub = 0; sub < 32 / TC_SUB; ++sub) {
           float sv[TC_SUB];
 #pragma unroll
-          for (int i = 0; i < TC_SUB; ++i)
-            sv[i] = fmaf(-2.0f, __uint_as_float(cur[sub * TC_SUB + i]), wv[sub * TC_SUB + i]);
-#pragma unroll
-          for (int i = 0; i < TC_SUB; ++i) {
-            if (sv[i] <= T) {  // predicated: one 64-bit store + one add (no "memory" clobber: the
-                               // buffer is only read back inside tc_flush, an opaque call)
-              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cw), "r"(__float_as_uint(sv[i])),
-                           "r"(jc + static_cast<uint32_t>(sub * TC_SUB + i)));
-              cw += CSTRIDE;
-            }
+          for (int i4 = 0; i4 < TC_SUB / 4; ++i4) {
+            float w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3)
+                         : "r"(wt + static_cast<uint32_t>((c * 32 + sub * TC_SUB + i4 * 4) * 4)));
+            sv[i4 * 4 + 0] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 0]), w0);
+            sv[i4 * 4 + 1] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 1]), w1);
+            sv[i4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 2]), w2);
+            sv[i4 * 4 + 3] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 3]), w3);
           }
-          if (__any_sync(FULL, cw > cw_limit)) {
-            T = tc_flush(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), list, T);
-            cw = cand_base;
+          float m = fminf(sv[0], sv[1]);
+#pragma unroll
+          for (int i = 2; i < TC_SUB; ++i) m = fminf(m, sv[i]);
+#pragma unroll
+          for (int i = 0; i < TC_SUB; ++i) mins[sub * TC_SUB + i] = fminf(mins[sub * TC_SUB + i], sv[i]);
+          // the append code is skipped unless some lane has a hit among these columns
+          if (__any_sync(FULL, m <= T)) {
+#pragma unroll
+            for (int i = 0; i < TC_SUB; ++i) {
+              if (sv[i] <= T) {  // predicated: one 64-bit store + one add (no "memory" clobber: the
+                                 // buffer is only read back inside tc_flush_stage, an opaque call)
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cw), "r"(__float_as_uint(sv[i])),
+                             "r"(jc + static_cast<uint32_t>(sub * TC_SUB + i)));
+                cw += CSTRIDE;
+              }
+            }
+            if (__any_sync(FULL, cw > cw_limit)) {
+              gcount = tc_flush_stage(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), T, garr, gcount);
+              cw = cand_base;
+            }
           }
         }
       }
@@ -456,11 +457,40 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
+      // refresh the threshold: after tiles 1, 2, 3, 4, 6, 8, 12, 16, ... and then every 16th.  The
+      // two threads of a row (one per column half) pool their minima slot by slot -- slot i then
+      // covers the union of both slot-i subsets, still 32 disjoint subsets of everything the row
+      // has seen -- and half 0 takes the 16th smallest of the pooled 32.
+      const int v = t + 1;
+      const bool pow2 = (v & (v - 1)) == 0;
+      const bool pow2x3 = (v % 3 == 0) && (((v / 3) & ((v / 3) - 1)) == 0);
+      const bool refresh = v < 64 ? (pow2 || pow2x3) : (v & 15) == 0;
+      if (refresh) {
+        if (half != 0) {
+#pragma unroll
+          for (int i = 0; i < TC_TOUR; ++i) sX[i * TC_M + row] = mins[i];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
+        if (half == 0) {
+          // 16th smallest of the 32 pooled minima: sort both halves, then max_i min(A[i], B[15-i])
+          float tmp[TC_TOUR];
+#pragma unroll
+          for (int i = 0; i < TC_TOUR; ++i) tmp[i] = fminf(mins[i], sX[i * TC_M + row]);
+          sort_floats<16, 0, TC_TOUR>(tmp);
+          sort_floats<16, 16, TC_TOUR>(tmp);
+          float U = fminf(tmp[0], tmp[31]);
+#pragma unroll
+          for (int i = 1; i < 16; ++i) U = fmaxf(U, fminf(tmp[i], tmp[31 - i]));
+          sT[row] = U;
+        }
+      }
       // stage the next tile's norms (all epilogue warps are past their reads of that buffer)
-      sW[((t + 1) & 1) * TC_N + et] = wnext;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < TC_N) sW[((t + 1) & 1) * TC_N + et] = wnext;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
+      if (live && refresh) T = __fadd_ru(sT[row], E2);  // +inf while fewer than 16 points have been seen
     }
-    if (__any_sync(FULL, cw > cand_base)) tc_flush(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), list, T);
+    gcount = tc_flush_stage(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), T, garr, gcount);
+    if (qi < L1) prm.counts[qrow * TC_HALVES + half] = gcount;
   }
 
   tc_fence_before();
@@ -482,13 +512,15 @@ struct TcRerankParams {
   const float* p2;
   const int64_t* len1;
   const int64_t* len2;
-  const uint64_t* lists;
+  const uint2* cands;     // [N][P1][TC_HALVES][TC_GCAP]
+  const unsigned* counts; // [N][P1][TC_HALVES]
+  const float* xq;        // [N][P1pad]
   const unsigned* maxw_bits;
   int64_t* idx;
   float* dists;
   unsigned char* flags;  // [N][P1]: 1 = recompute exactly
   unsigned* flag_rows;   // compact list of the flagged rows (n * P1 + i); flag_rows[-1] is the counter
-  int P1, P2, D, K;
+  int P1, P2, P1pad, D, K;
   int debug;
 };
 
@@ -514,50 +546,83 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
     }
     return;
   }
-  // query row -> shared memory, |x|^2
+  // query row -> shared memory
   float* x = sx + wib * D;
   const float* xg = prm.p1 + qrow * D;
-  float xx = 0.0f;
-  for (int d = lane; d < D; d += 32) {
-    const float v = xg[d];
-    x[d] = v;
-    xx = fmaf(v, v, xx);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) xx += __shfl_xor_sync(FULL, xx, o);
+  for (int d = lane; d < D; d += 32) x[d] = xg[d];
   __syncwarp();
+  const float E = tc_error_bound(prm.xq[static_cast<size_t>(n) * prm.P1pad + qi], __uint_as_float(prm.maxw_bits[n]), D);
 
-  const uint64_t key = prm.lists[qrow * TC_LIST + lane];
-  const bool have = key != kEmptyKey;
-  const float s = have ? sortable2f(static_cast<uint32_t>(key >> 32)) : __int_as_float(0x7f800000);
-  const uint32_t j = static_cast<uint32_t>(key & 0xFFFFFFFFull);
-
-  // E (see the header); every factor rounded up, 1 % slack on top
-  const float My2 = __uint_as_float(prm.maxw_bits[n]) * 1.0001f;
-  const float xx_up = xx * 1.0001f;
-  const float c1 = 0.00390625f * (1.0f + 0.00048828125f + static_cast<float>(D) * 0.0001220703125f) + 1.2e-7f;
-  const float c2 = static_cast<float>(3 * D + 8) * 5.9604645e-08f;
-  const float E = 1.01f * (c1 * sqrtf(xx_up * My2) * 1.0001f + c2 * (xx_up + My2));
+  // the 32 smallest (s, j) among the query's candidates, ascending along the lanes: every chunk of
+  // 32 candidates is sorted (bitonic network over shuffles); min(run[i], chunk[31-i]) holds the 32
+  // smallest of both as a bitonic sequence, which one merge pass sorts
+  auto sort32 = [&](uint64_t v) -> uint64_t {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const uint64_t other = __shfl_xor_sync(FULL, v, stride);
+        const bool up = (lane & size) == 0;
+        const bool lower = (lane & stride) == 0;
+        v = (up == lower) ? (other < v ? other : v) : (other > v ? other : v);
+      }
+    }
+    return v;
+  };
+  auto merge32 = [&](uint64_t v) -> uint64_t {  // v bitonic -> ascending
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+      const uint64_t other = __shfl_xor_sync(FULL, v, stride);
+      v = (lane & stride) == 0 ? (other < v ? other : v) : (other > v ? other : v);
+    }
+    return v;
+  };
+  uint64_t run = kEmptyKey;
+  bool unsure = false;
+  unsigned total = 0;
+  for (int h = 0; h < TC_HALVES; ++h) {
+    const unsigned raw = prm.counts[qrow * TC_HALVES + h];
+    unsure = unsure || (raw >> 31) != 0;  // the candidate array overflowed
+    const unsigned cnt = raw & 0x7fffffffu;
+    const uint2* arr = prm.cands + (qrow * TC_HALVES + h) * TC_GCAP;
+    for (unsigned c0 = 0; c0 < cnt; c0 += 32) {
+      uint64_t key = kEmptyKey;
+      if (c0 + lane < cnt) {
+        const uint2 e = arr[c0 + lane];
+        key = (static_cast<uint64_t>(f2sortable(__uint_as_float(e.x))) << 32) | e.y;
+      }
+      key = sort32(key);
+      const uint64_t rev = __shfl_sync(FULL, key, 31 - lane);
+      run = merge32(rev < run ? rev : run);
+    }
+    total += cnt;
+  }
+  const bool have = run != kEmptyKey;
+  const float s = have ? sortable2f(static_cast<uint32_t>(run >> 32)) : __int_as_float(0x7f800000);
+  const uint32_t j = static_cast<uint32_t>(run & 0xFFFFFFFFull);
   const int kth = min(K, L2);
-  const float sK = __shfl_sync(FULL, s, kth - 1);           // the list is ascending: lane k = (k+1)-th smallest s
+  const float sK = __shfl_sync(FULL, s, kth - 1);  // lane k holds the (k+1)-th smallest s
   const float tau = __fadd_ru(sK, __fmul_ru(2.0f, E));
-  const bool active = have && s <= tau;
-  const float s_last = __shfl_sync(FULL, s, TC_LIST - 1);
-  const bool last_have = __shfl_sync(FULL, have ? 1 : 0, TC_LIST - 1) != 0;
-  if (L2 > TC_LIST && last_have && s_last <= tau) {
-    // the list may have dropped a point within tau: exact recomputation (knn_generic_kernel)
+  {
+    const float s_last = __shfl_sync(FULL, s, TC_LIST - 1);
+    // more than 32 candidates and the 32nd is still within tau: the band is not fully visible here
+    unsure = unsure || (total > TC_LIST && s_last <= tau);
+  }
+  if (unsure) {
     if (lane == 0) {
       prm.flags[qrow] = 1;
       prm.flag_rows[atomicAdd(prm.flag_rows - 1, 1u)] = static_cast<unsigned>(qrow);
     }
     if (prm.debug && lane == 0 && atomicAdd(&g_tc_dbg, 1u) < 12u)
-      printf("flag n=%d q=%d sK=%g s_last=%g tau=%g E=%g xx=%g My2=%g kth=%d\n", n, qi, sK, s_last, tau, E, xx, My2, kth);
+      printf("flag n=%d q=%d sK=%g tau=%g E=%g total=%u kth=%d\n", n, qi, sK, tau, E, total, kth);
     return;
   }
-  // exact reference distance for the active entries: same operations, same order (knn_cpu.cpp:42-50)
-  float dist = 0.0f;
-  if (active) {
+  if (prm.debug && lane == 0 && (qrow & 0xFFFF) == 0) printf("row %d: %u candidates\n", static_cast<int>(qrow), total);
+  // exact reference distance for the entries within tau: same operations, same order (knn_cpu.cpp:42-50)
+  uint64_t k2 = kEmptyKey;
+  if (have && s <= tau) {
     const float* y = prm.p2 + (static_cast<size_t>(n) * prm.P2 + j) * D;
+    float dist = 0.0f;
     if ((D & 3) == 0) {
       for (int d = 0; d < D; d += 4) {
         const float4 yv = *reinterpret_cast<const float4*>(y + d);
@@ -577,20 +642,9 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
         dist = __fadd_rn(dist, __fmul_rn(df, df));
       }
     }
+    k2 = make_key(dist, j);
   }
-  uint64_t k2 = active ? make_key(dist, j) : kEmptyKey;
-  // bitonic sort of the 32 keys across the warp, ascending
-#pragma unroll
-  for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const uint64_t other = __shfl_xor_sync(FULL, k2, stride);
-      const bool up = (lane & size) == 0;         // ascending block
-      const bool lower = (lane & stride) == 0;    // this lane keeps the smaller of the pair when ascending
-      const bool take_min = (up == lower);
-      k2 = take_min ? (other < k2 ? other : k2) : (other > k2 ? other : k2);
-    }
-  }
+  k2 = sort32(k2);
   if (lane < K) {
     const bool ok = k2 != kEmptyKey;
     oi[lane] = ok ? static_cast<int64_t>(k2 & 0xFFFFFFFFull) : 0;
@@ -605,7 +659,7 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
 // Rows are few on generic data (a handful per million queries); beyond `limit` rows the dense
 // generic kernel (knn.cu) takes over instead, CTA by CTA.
 // ---------------------------------------------------------------------------------------------
-constexpr int kExactThreads = 256;
+constexpr int kExactThreads = 1024;
 
 template <int KT>
 __global__ void __launch_bounds__(kExactThreads)
@@ -614,7 +668,8 @@ knn_exact_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2
                       int P1, int P2, int D, int K, int64_t* __restrict__ idx, float* __restrict__ dists) {
   extern __shared__ __align__(16) unsigned char esm[];
   float* x = reinterpret_cast<float*>(esm);                                   // [D]
-  uint64_t* red = reinterpret_cast<uint64_t*>(esm + align_up(size_t(D) * 4, 16));  // [8] warp minima + [1] winner
+  uint64_t* red = reinterpret_cast<uint64_t*>(esm + align_up(size_t(D) * 4, 16));  // [32] warp minima + [1] winner
+  float* tile = reinterpret_cast<float*>(red + 34) + (threadIdx.x >> 5) * (32 * 33);       // per warp: 32 x 33
   const unsigned count = flag_rows[-1];
   if (count > limit) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -629,15 +684,31 @@ knn_exact_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2
     uint64_t Lr[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) Lr[k] = kEmptyKey;
-    for (int j = tid; j < L2; j += kExactThreads) {
-      const float* y = p2 + (static_cast<size_t>(n) * P2 + j) * D;
+    // a warp takes 32 points at a time: rows are read coalesced into a padded tile, then every
+    // lane sums its own point in dimension order (the reference's order)
+    const float* yb = p2 + static_cast<size_t>(n) * P2 * D;
+    for (int base = warp * 32; base < L2; base += (kExactThreads / 32) * 32) {
       float dist = 0.0f;
-      for (int d = 0; d < D; ++d) {
-        const float df = __fsub_rn(x[d], y[d]);
-        dist = __fadd_rn(dist, __fmul_rn(df, df));
+      for (int d0 = 0; d0 < D; d0 += 32) {
+        const int dn = min(32, D - d0);
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          float v = 0.0f;
+          if (base + r < L2 && lane < dn) v = yb[static_cast<size_t>(base + r) * D + d0 + lane];
+          tile[r * 33 + lane] = v;
+        }
+        __syncwarp();
+        for (int dd = 0; dd < dn; ++dd) {
+          const float df = __fsub_rn(x[d0 + dd], tile[lane * 33 + dd]);
+          dist = __fadd_rn(dist, __fmul_rn(df, df));
+        }
+        __syncwarp();
       }
-      const uint64_t key = make_key(dist, static_cast<uint32_t>(j));
-      if (key < Lr[KT - 1]) insert_network<KT>(Lr, key);
+      const int j = base + lane;
+      if (j < L2) {
+        const uint64_t key = make_key(dist, static_cast<uint32_t>(j));
+        if (key < Lr[KT - 1]) insert_network<KT>(Lr, key);
+      }
     }
     // K rounds: smallest head wins and its owner pops
     for (int k = 0; k < K; ++k) {
@@ -652,14 +723,14 @@ knn_exact_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2
       if (warp == 0) {
         uint64_t v = lane < kExactThreads / 32 ? red[lane] : kEmptyKey;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = 16; o > 0; o >>= 1) {
           const uint64_t u = __shfl_xor_sync(0xffffffffu, v, o);
           v = u < v ? u : v;
         }
-        if (lane == 0) red[8] = v;
+        if (lane == 0) red[32] = v;
       }
       __syncthreads();
-      const uint64_t win = red[8];
+      const uint64_t win = red[32];
       if (win != kEmptyKey && Lr[0] == win) {  // keys are unique: exactly one owner
 #pragma unroll
         for (int q = 0; q + 1 < KT; ++q) Lr[q] = Lr[q + 1];
@@ -707,16 +778,21 @@ int make_map(CUtensorMap* map, const float* base, int64_t N, int64_t P, int64_t 
 
 struct TcLayout {
   int P2pad;
-  size_t w_off, maxw_off, lists_off, flags_off, rows_off, total;
+  int P1pad;
+  size_t w_off, xq_off, maxw_off, maxq_off, cands_off, counts_off, flags_off, rows_off, total;
 };
 
 TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
   TcLayout l;
   l.P2pad = static_cast<int>((P2 + TC_N - 1) / TC_N * TC_N);
   size_t off = 0;
+  l.P1pad = static_cast<int>((P1 + TC_M - 1) / TC_M * TC_M);
   l.maxw_off = off;  off += align_up(size_t(N) * 4, 256);
+  l.maxq_off = off;  off += align_up(size_t(N) * 4, 256);
   l.w_off = off;     off += align_up(size_t(N) * l.P2pad * 4, 256);
-  l.lists_off = off; off += align_up(size_t(N) * P1 * TC_LIST * 8, 256);
+  l.xq_off = off;    off += align_up(size_t(N) * l.P1pad * 4, 256);
+  l.cands_off = off; off += align_up(size_t(N) * P1 * TC_HALVES * TC_GCAP * 8, 256);
+  l.counts_off = off; off += align_up(size_t(N) * P1 * TC_HALVES * 4, 256);
   l.flags_off = off; off += align_up(size_t(N) * P1, 256);
   l.rows_off = off;  off += align_up(size_t(N) * P1 * 4 + 256, 256);  // counter lives 4 bytes before the list
   l.total = off;
@@ -725,7 +801,8 @@ TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 inline size_t tc_smem_fixed(int KB) {
-  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_M * 8 + 2 * TC_N * 4 + (2 * TC_MAX_STAGES + 2 * TC_ABUF + 2) * 8 +
+  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_CSTRIDE * 8 + size_t(TC_TOUR) * TC_M * 4 + 2 * TC_N * 4 + TC_M * 4 +
+         (2 * TC_MAX_STAGES + 2 * TC_ABUF + 2) * 8 +
          1024 /* alignment */;
 }
 
@@ -753,7 +830,10 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   char* base = reinterpret_cast<char*>(ws);
   unsigned* maxw = reinterpret_cast<unsigned*>(base + l.maxw_off);
   float* w = reinterpret_cast<float*>(base + l.w_off);
-  uint64_t* lists = reinterpret_cast<uint64_t*>(base + l.lists_off);
+  unsigned* maxq = reinterpret_cast<unsigned*>(base + l.maxq_off);
+  float* xq = reinterpret_cast<float*>(base + l.xq_off);
+  uint2* cands = reinterpret_cast<uint2*>(base + l.cands_off);
+  unsigned* counts = reinterpret_cast<unsigned*>(base + l.counts_off);
   unsigned char* flags = reinterpret_cast<unsigned char*>(base + l.flags_off);
   *flags_out = flags;
   unsigned* flag_rows = reinterpret_cast<unsigned*>(base + l.rows_off + 256);
@@ -763,9 +843,13 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   POPS_CUDA_OK(cudaMemsetAsync(flag_rows - 1, 0, 4, st));
 
   POPS_CUDA_OK(cudaMemsetAsync(maxw, 0, size_t(N) * 4, st));
+  POPS_CUDA_OK(cudaMemsetAsync(maxq, 0, size_t(N) * 4, st));
   {
     dim3 grid(static_cast<unsigned>(ceil_div(l.P2pad, 8)), N);
     tc_norm_kernel<<<grid, 256, 0, st>>>(p2, len2, P2, l.P2pad, D, w, maxw);
+    POPS_LAUNCH_OK("tc_norm_kernel");
+    dim3 gridq(static_cast<unsigned>(ceil_div(l.P1pad, 8)), N);
+    tc_norm_kernel<<<gridq, 256, 0, st>>>(p1, len1, P1, l.P1pad, D, xq, maxq);
     POPS_LAUNCH_OK("tc_norm_kernel");
   }
   static const int cl_env = getenv("POPS_TC_CLUSTER") ? atoi(getenv("POPS_TC_CLUSTER")) : 4;  // tuning aid
@@ -778,8 +862,8 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   if (rc != POPS_OK) return rc;
 
   TcParams prm;
-  prm.w = w; prm.len1 = len1; prm.len2 = len2; prm.lists = lists;
-  prm.P1 = P1; prm.P2 = P2; prm.P2pad = l.P2pad;
+  prm.w = w; prm.len1 = len1; prm.len2 = len2; prm.xq = xq; prm.maxw_bits = maxw; prm.cands = cands; prm.counts = counts;
+  prm.P1 = P1; prm.P2 = P2; prm.P2pad = l.P2pad; prm.P1pad = l.P1pad; prm.D = D;
   prm.KB = (D + TC_KBLK - 1) / TC_KBLK;
   prm.dbg = getenv("POPS_TC_DBG") ? atoi(getenv("POPS_TC_DBG")) : 0;
   const size_t fixed = tc_smem_fixed(prm.KB);
@@ -807,8 +891,8 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
     POPS_LAUNCH_OK("knn_tc_scan_kernel");
   }
   TcRerankParams rp;
-  rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.lists = lists; rp.maxw_bits = maxw;
-  rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.flag_rows = flag_rows; rp.P1 = P1; rp.P2 = P2; rp.D = D; rp.K = K;
+  rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.cands = cands; rp.counts = counts; rp.xq = xq; rp.maxw_bits = maxw;
+  rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.flag_rows = flag_rows; rp.P1 = P1; rp.P2 = P2; rp.P1pad = l.P1pad; rp.D = D; rp.K = K;
   rp.debug = getenv("POPS_KNN_STATS") ? 1 : 0;
   {
     dim3 grid(static_cast<unsigned>(ceil_div(P1, 4)), N);
@@ -818,8 +902,10 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
     POPS_LAUNCH_OK("knn_tc_rerank_kernel");
   }
   {
-    const size_t esmem = align_up(size_t(D) * 4, 16) + 9 * 8;
-    const int grid = num_sms() * 2;
+    const size_t esmem = align_up(size_t(D) * 4, 16) + 34 * 8 + size_t(kExactThreads / 32) * 32 * 33 * 4;
+    POPS_CUDA_OK(cudaFuncSetAttribute(knn_exact_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esmem)));
+    POPS_CUDA_OK(cudaFuncSetAttribute(knn_exact_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esmem)));
+    const int grid = num_sms();
     profile_begin("knn_exact_rows", st);
     if (K <= 4)
       knn_exact_rows_kernel<4><<<grid, kExactThreads, esmem, st>>>(p1, p2, len2, flag_rows, limit, P1, P2, D, K, idx, dists);
