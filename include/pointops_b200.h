@@ -47,10 +47,24 @@ const char* pops_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 int64_t pops_launch_count(void);
 
+/* Tuning / measurement knobs, also readable from the environment as POPS_<NAME> (upper case):
+ *   knn_order   -1 auto | 0 never | 1 always use the Morton-ordered, box-pruned D=3 search
+ *   knn_prune   1 | 0: visit every block (brute force in the same order; bench.py uses it to report
+ *               the evaluation rate of the scan loop next to the pruned time)
+ *   knn_q       queries per thread of the pruned search (4 | 2)
+ *   knn_stats   1: collect block / flush counters (pops_knn_debug_stats)
+ *   knn_tc      -1 auto | 0 never | 1 whenever the shape allows: tensor-core path for 32 <= D <= 256
+ *   tc_cluster  CTAs that share every p2 stage by TMA multicast (1 | 2 | 4) */
+void pops_set_option(const char* name, int value);
+/* Development counters of the pruned D=3 search, read and reset (needs knn_stats = 1):
+ * [0] blocks fetched, [1] blocks scanned, [2] flush rounds, [3] buffered groups, [4] non-empty
+ * per-slot flushes, [5] warps. */
+int pops_knn_debug_stats(unsigned long long* out8);
+
 /* Optional per-kernel timing (bench.py "roofline"): while enabled, the library brackets its
  * dominant kernels with CUDA events on the launching stream.  pops_profile_read synchronises
- * those events and returns, for the named kernel ("knn_scan", "fps", "ball_query", "gather",
- * "knn_backward", "chamfer"), the number of launches seen since the last reset and their total
+ * those events and returns, for the named kernel ("knn_scan", "knn_tc_scan", "knn_tc_rerank",
+ * "knn_exact_rows", "knn_generic", "fps", "ball_query", "gather", "knn_backward", "chamfer"), the number of launches seen since the last reset and their total
  * device time in milliseconds.  Off by default; costs two event records per launch when on. */
 void pops_profile_enable(int on);
 void pops_profile_reset(void);

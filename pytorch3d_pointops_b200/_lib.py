@@ -20,6 +20,8 @@ SIGNATURES = {
     "pops_build_info": (c_char_p, []),
     "pops_last_error": (c_char_p, []),
     "pops_launch_count": (c_int64, []),
+    "pops_set_option": (None, [c_char_p, c_int]),
+    "pops_knn_debug_stats": (c_int, [_P]),
     "pops_profile_enable": (None, [c_int]),
     "pops_profile_reset": (None, []),
     "pops_profile_read": (c_int, [c_char_p, _P, _P]),

@@ -1,5 +1,8 @@
 // Library-level plumbing of libpointops_b200.so: error string, build info, launch counter.
+#include <cctype>
+#include <cstdlib>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -10,6 +13,24 @@ std::string& last_error_ref() {
   return err;
 }
 std::atomic<int64_t> g_launch_count{0};
+
+// ---- options ------------------------------------------------------------------------------------
+namespace {
+std::mutex g_opt_mu;
+std::vector<std::pair<std::string, int>> g_opts;
+}  // namespace
+
+int get_option(const char* name, int dflt) {
+  {
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    for (auto& kv : g_opts)
+      if (kv.first == name) return kv.second;
+  }
+  std::string env = "POPS_";
+  for (const char* c = name; *c; ++c) env.push_back(static_cast<char>(toupper(*c)));
+  const char* v = getenv(env.c_str());
+  return v ? atoi(v) : dflt;
+}
 
 // ---- optional per-kernel timing ---------------------------------------------------------------
 namespace {
@@ -43,6 +64,16 @@ void profile_end(const char* kernel, cudaStream_t st) {
     }
 }
 }  // namespace pops
+
+extern "C" void pops_set_option(const char* name, int value) {
+  std::lock_guard<std::mutex> lk(pops::g_opt_mu);
+  for (auto& kv : pops::g_opts)
+    if (kv.first == name) {
+      kv.second = value;
+      return;
+    }
+  pops::g_opts.emplace_back(name, value);
+}
 
 extern "C" void pops_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(pops::g_prof_mu);

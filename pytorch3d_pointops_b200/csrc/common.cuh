@@ -43,6 +43,10 @@ inline int fail(int code, const std::string& msg) {
       return ::pops::fail(POPS_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// tuning / measurement knobs (api.cu): value set through pops_set_option, else the environment
+// variable POPS_<NAME>, else `dflt`.  Read at every call, so tests and bench.py can flip them.
+int get_option(const char* name, int dflt);
+
 // per-kernel timing (api.cu); no-ops unless pops_profile_enable(1)
 void profile_begin(const char* kernel, cudaStream_t st);
 void profile_end(const char* kernel, cudaStream_t st);

@@ -525,7 +525,7 @@ int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
 // D = 3, L2, K <= 32: Morton-ordered clouds + box-pruned search (knn_order.cu, knn_prune.cu).
 // Worth its pre-pass once the cloud spans more than a few blocks.
 inline bool use_ordered(int64_t P2, int K) {
-  static const int force = getenv("POPS_KNN_ORDER") ? atoi(getenv("POPS_KNN_ORDER")) : -1;  // test aid
+  const int force = get_option("knn_order", -1);  // test aid
   if (K > 32) return false;
   if (force >= 0) return force != 0;
   return P2 >= 1024;

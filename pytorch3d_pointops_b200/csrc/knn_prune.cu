@@ -561,14 +561,14 @@ int launch_prune_k(const KnnPruneParams& prm, int N, cudaStream_t st) {
 
 int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64_t* len2, int N, int P1,
                      int P2, int K, int64_t* idx, float* dists, cudaStream_t st) {
-  static const int prune = getenv("POPS_KNN_PRUNE") ? atoi(getenv("POPS_KNN_PRUNE")) : 1;  // measurement aid
-  static const int q = getenv("POPS_KNN_Q") ? atoi(getenv("POPS_KNN_Q")) : 4;               // tuning aid
+  const int prune = get_option("knn_prune", 1);  // 0: visit every block (measurement aid)
+  const int q = get_option("knn_q", 4);          // queries per thread (tuning aid)
   KnnPruneParams prm;
   prm.qsorted = ob.qsorted; prm.qhome = ob.qhome; prm.blocks = ob.blocks; prm.boxes = ob.boxes;
   prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits; prm.idx = idx; prm.dists = dists;
   prm.P1 = P1; prm.P2 = P2; prm.K = K; prm.nbox = static_cast<int>(knn_order_num_boxes(P2));
   prm.prune = prune;
-  static const int stats = getenv("POPS_KNN_STATS") ? atoi(getenv("POPS_KNN_STATS")) : 0;
+  const int stats = get_option("knn_stats", 0);
   prm.stats = nullptr;
   if (stats) POPS_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&prm.stats), g_knn_stats));
   const bool narrow = int64_t(prm.nbox) * kBlockGroups <= 65536;

@@ -809,7 +809,7 @@ inline size_t tc_smem_fixed(int KB) {
 }  // namespace
 
 bool knn_tc_supported(int64_t P1, int64_t P2, int64_t D, int64_t K, int norm) {
-  static const int force = getenv("POPS_KNN_TC") ? atoi(getenv("POPS_KNN_TC")) : -1;  // test aid
+  const int force = get_option("knn_tc", -1);  // test aid: 0 = never, 1 = whenever the shape allows
   if (force == 0) return false;
   if (norm != 2 || K > 16 || K < 1 || D < 32 || D > 256 || (D & 3) != 0) return false;
   if (P2 >= (int64_t(1) << 31) - TC_N) return false;
@@ -852,7 +852,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
     tc_norm_kernel<<<gridq, 256, 0, st>>>(p1, len1, P1, l.P1pad, D, xq, maxq);
     POPS_LAUNCH_OK("tc_norm_kernel");
   }
-  static const int cl_env = getenv("POPS_TC_CLUSTER") ? atoi(getenv("POPS_TC_CLUSTER")) : 4;  // tuning aid
+  const int cl_env = get_option("tc_cluster", 1);  // CTAs sharing every p2 stage by TMA multicast (tuning aid)
   const int64_t qtiles = ceil_div(P1, TC_M);
   const int CL = (cl_env >= 4 && qtiles >= 4) ? 4 : ((cl_env >= 2 && qtiles >= 2) ? 2 : 1);
   CUtensorMap map_q, map_p;
@@ -865,7 +865,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   prm.w = w; prm.len1 = len1; prm.len2 = len2; prm.xq = xq; prm.maxw_bits = maxw; prm.cands = cands; prm.counts = counts;
   prm.P1 = P1; prm.P2 = P2; prm.P2pad = l.P2pad; prm.P1pad = l.P1pad; prm.D = D;
   prm.KB = (D + TC_KBLK - 1) / TC_KBLK;
-  prm.dbg = getenv("POPS_TC_DBG") ? atoi(getenv("POPS_TC_DBG")) : 0;
+  prm.dbg = get_option("tc_dbg", 0);
   const size_t fixed = tc_smem_fixed(prm.KB);
   prm.nstage = static_cast<int>(std::min<size_t>(TC_MAX_STAGES, (kSmemLimit - fixed) / TC_STAGE_BYTES));
   const size_t smem = fixed + size_t(prm.nstage) * TC_STAGE_BYTES;
@@ -893,7 +893,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   TcRerankParams rp;
   rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.cands = cands; rp.counts = counts; rp.xq = xq; rp.maxw_bits = maxw;
   rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.flag_rows = flag_rows; rp.P1 = P1; rp.P2 = P2; rp.P1pad = l.P1pad; rp.D = D; rp.K = K;
-  rp.debug = getenv("POPS_KNN_STATS") ? 1 : 0;
+  rp.debug = get_option("knn_stats", 0);
   {
     dim3 grid(static_cast<unsigned>(ceil_div(P1, 4)), N);
     profile_begin("knn_tc_rerank", st);
