@@ -71,6 +71,7 @@ struct TcParams {
   const unsigned* maxw_bits;  // [N] max_j w_j (float bits)
   uint2* cands;            // [N][P1][TC_HALVES][TC_GCAP] (s bits, j)
   unsigned* counts;        // [N][P1][TC_HALVES] entries used; bit 31 = overflowed
+  float* tfin;             // [N][P1] final append threshold: nothing above it can be needed
   int P1, P2, P2pad, P1pad, D;
   int KB;                  // k-blocks = ceil(D / 32)
   int nstage;              // stages of the p2 ring
@@ -286,8 +287,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   unsigned char* rest = smem + static_cast<size_t>(KB + NST) * TC_STAGE_BYTES;
   uint2* cand = reinterpret_cast<uint2*>(rest);                                // TC_CAND x TC_CSTRIDE staged (s, j)
   float* sX = reinterpret_cast<float*>(rest + size_t(TC_CAND) * TC_CSTRIDE * 8);  // TC_TOUR x TC_M: minima exchange
-  float* sW = sX + TC_TOUR * TC_M;                                             // 2 x TC_N norms
-  float* sT = sW + 2 * TC_N;                                                   // TC_M tournament bounds
+  float* sW = sX + TC_TOUR * TC_M;                                             // per epilogue warp: 2 x TC_N/TC_HALVES norms
+  float* sT = sW + 4 * TC_HALVES * 2 * (TC_N / TC_HALVES);                                                   // TC_M tournament bounds
   uint64_t* bars = reinterpret_cast<uint64_t*>(sT + TC_M);
   uint64_t* full = bars;                       // [TC_MAX_STAGES]  TMA -> MMA
   uint64_t* empty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]  MMA -> TMA
@@ -378,7 +379,6 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int ew = warp & 3;                 // the TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;        // which half of the columns
     const int row = ew * 32 + lane;          // query row inside the tile
-    const int et = (warp - 2) * 32 + lane;   // index among the epilogue threads
     const int qi = q_base + row;
     const float INF = __int_as_float(0x7f800000);
     constexpr int HC = TC_N / TC_HALVES;     // columns per half
@@ -398,15 +398,19 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint32_t cw = cand_base;
     constexpr uint32_t CSTRIDE = TC_CSTRIDE * 8;
     const uint32_t cw_limit = cand_base + static_cast<uint32_t>(TC_CAND - TC_SUB) * CSTRIDE;
-    const float* w_n = prm.w + static_cast<size_t>(n) * prm.P2pad;
-    const uint32_t sW_addr = smem_u32(sW);
-    if (et < TC_N) sW[et] = w_n[et];
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
+    // every warp stages the norms of ITS columns of the next tile in a private double buffer: no
+    // CTA-wide barrier per tile
+    static_assert(HC == 64, "two norms per lane");
+    const float* w_n = prm.w + static_cast<size_t>(n) * prm.P2pad + half * HC;
+    float* sWw = sW + (warp - 2) * 2 * HC;
+    const uint32_t sW_addr = smem_u32(sWw);
+    *reinterpret_cast<float2*>(sWw + 2 * lane) = *reinterpret_cast<const float2*>(w_n + 2 * lane);
+    __syncwarp();
     for (int t = 0; t < num_tiles; ++t) {
       const int b = t % TC_ABUF;
-      const uint32_t wt = sW_addr + static_cast<uint32_t>(((t & 1) * TC_N + half * HC) * 4);
-      float wnext = 0.0f;
-      if (et < TC_N && t + 1 < num_tiles) wnext = w_n[(t + 1) * TC_N + et];
+      const uint32_t wt = sW_addr + static_cast<uint32_t>((t & 1) * HC * 4);
+      float2 wnext = make_float2(0.0f, 0.0f);
+      if (t + 1 < num_tiles) wnext = *reinterpret_cast<const float2*>(w_n + (t + 1) * TC_N + 2 * lane);
       mbar_wait_parked(&tfull[b], (t / TC_ABUF) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TC_N + half * HC);
@@ -484,13 +488,19 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           sT[row] = U;
         }
       }
-      // stage the next tile's norms (all epilogue warps are past their reads of that buffer)
-      if (et < TC_N) sW[((t + 1) & 1) * TC_N + et] = wnext;
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
-      if (live && refresh) T = __fadd_ru(sT[row], E2);  // +inf while fewer than 16 points have been seen
+      // stage the next tile's norms (the warp is past its reads of that buffer)
+      *reinterpret_cast<float2*>(sWw + ((t + 1) & 1) * HC + 2 * lane) = wnext;
+      __syncwarp();
+      if (refresh) {
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
+        if (live) T = __fadd_ru(sT[row], E2);  // +inf while fewer than 16 points have been seen
+      }
     }
     gcount = tc_flush_stage(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), T, garr, gcount);
-    if (qi < L1) prm.counts[qrow * TC_HALVES + half] = gcount;
+    if (qi < L1) {
+      prm.counts[qrow * TC_HALVES + half] = gcount;
+      if (half == 0) prm.tfin[qrow] = T;
+    }
   }
 
   tc_fence_before();
@@ -514,6 +524,7 @@ struct TcRerankParams {
   const int64_t* len2;
   const uint2* cands;     // [N][P1][TC_HALVES][TC_GCAP]
   const unsigned* counts; // [N][P1][TC_HALVES]
+  const float* tfin;      // [N][P1]
   const float* xq;        // [N][P1pad]
   const unsigned* maxw_bits;
   int64_t* idx;
@@ -577,25 +588,50 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
     }
     return v;
   };
+  // Only candidates within the scan's FINAL threshold can matter (tau <= that threshold); they are
+  // compacted through a small per-warp queue so that the sorting networks run on full chunks.
+  __shared__ uint64_t qbuf_all[4][64];
+  uint64_t* qbuf = qbuf_all[wib];
+  const float Tfin = prm.tfin[qrow];
+  const unsigned lt_mask = (1u << lane) - 1u;
   uint64_t run = kEmptyKey;
   bool unsure = false;
-  unsigned total = 0;
+  unsigned total = 0, fill = 0;
   for (int h = 0; h < TC_HALVES; ++h) {
     const unsigned raw = prm.counts[qrow * TC_HALVES + h];
     unsure = unsure || (raw >> 31) != 0;  // the candidate array overflowed
     const unsigned cnt = raw & 0x7fffffffu;
     const uint2* arr = prm.cands + (qrow * TC_HALVES + h) * TC_GCAP;
     for (unsigned c0 = 0; c0 < cnt; c0 += 32) {
+      bool pass = false;
       uint64_t key = kEmptyKey;
       if (c0 + lane < cnt) {
         const uint2 e = arr[c0 + lane];
+        pass = __uint_as_float(e.x) <= Tfin;
         key = (static_cast<uint64_t>(f2sortable(__uint_as_float(e.x))) << 32) | e.y;
       }
-      key = sort32(key);
-      const uint64_t rev = __shfl_sync(FULL, key, 31 - lane);
-      run = merge32(rev < run ? rev : run);
+      const unsigned m = __ballot_sync(FULL, pass);
+      if (pass) qbuf[fill + __popc(m & lt_mask)] = key;
+      fill += __popc(m);
+      __syncwarp();
+      if (fill >= 32) {
+        uint64_t k = sort32(qbuf[lane]);
+        const uint64_t rev = __shfl_sync(FULL, k, 31 - lane);
+        run = merge32(rev < run ? rev : run);
+        const uint64_t tail = qbuf[32 + lane];
+        __syncwarp();
+        qbuf[lane] = tail;
+        fill -= 32;
+        total += 32;
+        __syncwarp();
+      }
     }
-    total += cnt;
+  }
+  if (fill > 0) {
+    uint64_t k = sort32(lane < fill ? qbuf[lane] : kEmptyKey);
+    const uint64_t rev = __shfl_sync(FULL, k, 31 - lane);
+    run = merge32(rev < run ? rev : run);
+    total += fill;
   }
   const bool have = run != kEmptyKey;
   const float s = have ? sortable2f(static_cast<uint32_t>(run >> 32)) : __int_as_float(0x7f800000);
@@ -691,12 +727,14 @@ knn_exact_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2
       float dist = 0.0f;
       for (int d0 = 0; d0 < D; d0 += 32) {
         const int dn = min(32, D - d0);
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          float v = 0.0f;
-          if (base + r < L2 && lane < dn) v = yb[static_cast<size_t>(base + r) * D + d0 + lane];
-          tile[r * 33 + lane] = v;
+        float v[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {  // 32 independent coalesced loads in flight
+          v[r] = 0.0f;
+          if (base + r < L2 && lane < dn) v[r] = yb[static_cast<size_t>(base + r) * D + d0 + lane];
         }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tile[r * 33 + lane] = v[r];
         __syncwarp();
         for (int dd = 0; dd < dn; ++dd) {
           const float df = __fsub_rn(x[d0 + dd], tile[lane * 33 + dd]);
@@ -779,7 +817,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t N, int64_t P, int64_t 
 struct TcLayout {
   int P2pad;
   int P1pad;
-  size_t w_off, xq_off, maxw_off, maxq_off, cands_off, counts_off, flags_off, rows_off, total;
+  size_t w_off, xq_off, maxw_off, maxq_off, cands_off, counts_off, tfin_off, flags_off, rows_off, total;
 };
 
 TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
@@ -793,6 +831,7 @@ TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
   l.xq_off = off;    off += align_up(size_t(N) * l.P1pad * 4, 256);
   l.cands_off = off; off += align_up(size_t(N) * P1 * TC_HALVES * TC_GCAP * 8, 256);
   l.counts_off = off; off += align_up(size_t(N) * P1 * TC_HALVES * 4, 256);
+  l.tfin_off = off;  off += align_up(size_t(N) * P1 * 4, 256);
   l.flags_off = off; off += align_up(size_t(N) * P1, 256);
   l.rows_off = off;  off += align_up(size_t(N) * P1 * 4 + 256, 256);  // counter lives 4 bytes before the list
   l.total = off;
@@ -801,7 +840,7 @@ TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 inline size_t tc_smem_fixed(int KB) {
-  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_CSTRIDE * 8 + size_t(TC_TOUR) * TC_M * 4 + 2 * TC_N * 4 + TC_M * 4 +
+  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_CSTRIDE * 8 + size_t(TC_TOUR) * TC_M * 4 + 4 * 2 * TC_N * 4 + TC_M * 4 +
          (2 * TC_MAX_STAGES + 2 * TC_ABUF + 2) * 8 +
          1024 /* alignment */;
 }
@@ -834,6 +873,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   float* xq = reinterpret_cast<float*>(base + l.xq_off);
   uint2* cands = reinterpret_cast<uint2*>(base + l.cands_off);
   unsigned* counts = reinterpret_cast<unsigned*>(base + l.counts_off);
+  float* tfin = reinterpret_cast<float*>(base + l.tfin_off);
   unsigned char* flags = reinterpret_cast<unsigned char*>(base + l.flags_off);
   *flags_out = flags;
   unsigned* flag_rows = reinterpret_cast<unsigned*>(base + l.rows_off + 256);
@@ -862,7 +902,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   if (rc != POPS_OK) return rc;
 
   TcParams prm;
-  prm.w = w; prm.len1 = len1; prm.len2 = len2; prm.xq = xq; prm.maxw_bits = maxw; prm.cands = cands; prm.counts = counts;
+  prm.w = w; prm.len1 = len1; prm.len2 = len2; prm.xq = xq; prm.maxw_bits = maxw; prm.cands = cands; prm.counts = counts; prm.tfin = tfin;
   prm.P1 = P1; prm.P2 = P2; prm.P2pad = l.P2pad; prm.P1pad = l.P1pad; prm.D = D;
   prm.KB = (D + TC_KBLK - 1) / TC_KBLK;
   prm.dbg = get_option("tc_dbg", 0);
@@ -891,7 +931,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
     POPS_LAUNCH_OK("knn_tc_scan_kernel");
   }
   TcRerankParams rp;
-  rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.cands = cands; rp.counts = counts; rp.xq = xq; rp.maxw_bits = maxw;
+  rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.cands = cands; rp.counts = counts; rp.tfin = tfin; rp.xq = xq; rp.maxw_bits = maxw;
   rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.flag_rows = flag_rows; rp.P1 = P1; rp.P2 = P2; rp.P1pad = l.P1pad; rp.D = D; rp.K = K;
   rp.debug = get_option("knn_stats", 0);
   {

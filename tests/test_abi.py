@@ -60,6 +60,10 @@ def test_sass_is_blackwell_native():
     assert "sm_100a" in out
     assert "UBLKCP" in out, "TMA bulk copy (cp.async.bulk) missing from SASS"
     assert "FFMA2" in out, "packed FP32 FMA missing from SASS"
+    # tensor-core KNN (csrc/knn_tc.cu): tcgen05.mma / tcgen05.ld / TMA tensor loads
+    assert re.search(r"\bUTC[A-Z]*MMA\b", out), "tcgen05.mma missing from SASS"
+    assert "LDTM" in out, "tcgen05.ld missing from SASS"
+    assert "UTMALDG" in out, "cp.async.bulk.tensor missing from SASS"
 
 
 def test_exact_kernels_have_no_fused_multiply_add():
@@ -84,7 +88,10 @@ def test_exact_kernels_have_no_fused_multiply_add():
             # knn_flush_one (every variant) re-evaluates candidates exactly
             exact = re.search(r"knn_scan_kernelILi\d+ELi\d+ELb0", fn) or "knn_flush_one" in fn \
                 or "knn_generic_kernel" in fn or "ball_query_generic" in fn or "fps_" in fn \
-                or "knn_backward" in fn
+                or "knn_backward" in fn or "prune_flush_one" in fn or "seed_bound" in fn \
+                or "knn_exact_rows_kernel" in fn
+            # (knn_tc_rerank_kernel is not listed: its sqrtf() for the error bound lowers to FFMA;
+            #  its distance uses __fsub_rn/__fmul_rn/__fadd_rn, which are never contracted)
             if exact:
                 bad.append(fn)
     assert not bad, sorted(set(bad))
