@@ -97,6 +97,55 @@ __device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
       : "memory");
 }
+// CTA-pair (cta_group::2) forms.  Shared-memory addresses of a barrier "in the leader" are obtained
+// with mapa (rank 0 of the 2-CTA cluster).
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t smem_addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(0));
+  return r;
+}
+// TMA load into THIS CTA's shared memory, bytes credited to the barrier at `bar_cluster_addr`
+// (a shared::cluster address: the leader's barrier)
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {  // one warp of EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A . B^T over the pair: M = 256 (128 rows per CTA), N = 256 (128 rows of B
+// from each CTA's shared memory); issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -180,6 +229,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N, M
 constexpr uint32_t kTcIdesc =
     (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TC_N >> 3) << 17) | (uint32_t(TC_M >> 4) << 24);
+constexpr uint32_t kTcIdescPair =  // cta_group::2: M = 256, N = 256
+    (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(256 >> 3) << 17) | (uint32_t(256 >> 4) << 24);
 
 // order-preserving map float -> uint32 (ascending), and back
 __device__ __forceinline__ uint32_t f2sortable(float f) {
@@ -260,7 +311,12 @@ __device__ __noinline__ unsigned tc_flush_stage(const uint2* cand_col, int stage
 // walk the same p2 tiles in lock step: each loads 1/CL of every stage and multicasts it to all, so
 // L2 -> shared-memory traffic drops by CL (one CTA per 128 queries streaming all of p2 by itself
 // needs more than the L2 can deliver: measured 5.1 TB/s, 3x the MMA time).
-template <int CL>
+// PAIR: the two CTAs of a cluster form a cta_group::2 pair.  One tcgen05.mma of the leader covers
+// 256 queries x 256 points: every CTA supplies its 128 query rows and 128 of the 256 p2 rows of a
+// tile from its own shared memory and receives the accumulators of ITS queries (128 lanes x 256
+// columns).  Per SM the MMA then reads 64 B/clk of shared memory instead of 128 and TMA writes 32
+// instead of 64 -- the single-CTA form is bound by exactly that bandwidth.
+template <int CL, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_p,
                    const TcParams prm) {
@@ -276,11 +332,20 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
   // the rerank kernel writes the (0, 0) rows.  A CTA without valid queries still has to feed and
   // release its cluster (L2 is the same for the whole cluster: same cloud).
-  if (L2 == 0 || (CL == 1 && q_base >= L1)) return;
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  static_assert(!PAIR || CL == 1, "the pair shares p2 through the MMA, not through multicast");
+  if (L2 == 0 || (CL == 1 && !PAIR && q_base >= L1)) return;
+  const uint32_t crank = (CL > 1 || PAIR) ? cluster_ctarank() : 0;
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
+  constexpr int TN = PAIR ? 2 * TC_N : TC_N;   // accumulator columns (= points) per tile
+  constexpr int ABUF = 512 / TN;               // accumulator buffers: all 512 TMEM columns
+  const bool leader = crank == 0;
   const int KB = prm.KB, NST = prm.nstage;
-  const int num_tiles = (L2 + TC_N - 1) / TC_N;
+  const int num_tiles = (L2 + TN - 1) / TN;
+  // Seed pass: the first tiles are evaluated twice -- first for the tournament only (no candidate
+  // is staged), so that the real pass starts with a finite threshold instead of buffering the first
+  // few hundred points of every query.  Sequence of tiles for all roles: 0..S-1, then 0..num_tiles-1.
+  const int S_seed = num_tiles >= 16 ? 4 : 0;
+  const int seq_tiles = S_seed + num_tiles;
 
   float* sA = reinterpret_cast<float*>(smem);                                  // KB x 16 KB
   float* sB = reinterpret_cast<float*>(smem + static_cast<size_t>(KB) * TC_STAGE_BYTES);  // NST x 16 KB
@@ -288,7 +353,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint2* cand = reinterpret_cast<uint2*>(rest);                                // TC_CAND x TC_CSTRIDE staged (s, j)
   float* sX = reinterpret_cast<float*>(rest + size_t(TC_CAND) * TC_CSTRIDE * 8);  // TC_TOUR x TC_M: minima exchange
   float* sW = sX + TC_TOUR * TC_M;                                             // per epilogue warp: 2 x TC_N/TC_HALVES norms
-  float* sT = sW + 4 * TC_HALVES * 2 * (TC_N / TC_HALVES);                                                   // TC_M tournament bounds
+  float* sT = sW + 4 * TC_HALVES * 2 * (2 * TC_N / TC_HALVES);                 // TC_M tournament bounds
   uint64_t* bars = reinterpret_cast<uint64_t*>(sT + TC_M);
   uint64_t* full = bars;                       // [TC_MAX_STAGES]  TMA -> MMA
   uint64_t* empty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]  MMA -> TMA
@@ -302,32 +367,50 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CL);  // every CTA of the cluster has consumed the stage
     }
-    for (int b = 0; b < TC_ABUF; ++b) {
+    for (int b = 0; b < ABUF; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4 * TC_HALVES);  // one arrival per epilogue warp
+      mbar_init(&tempty[b], 4 * TC_HALVES * (PAIR ? 2 : 1));  // one arrival per epilogue warp (of both CTAs)
     }
     mbar_init(afull, 1);
     mbar_fence_init();
   } else if (warp == 1) {
-    tmem_alloc(tmem_slot, TC_ABUF * TC_N);
+    if (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast
+  if (CL > 1 || PAIR) cluster_sync_all();  // peers' barriers are initialised before anything arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===== TMA producer (one thread) =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(afull, static_cast<uint32_t>(KB) * TC_STAGE_BYTES);
-      for (int kb = 0; kb < KB; ++kb)
-        tma_load_3d(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4), &map_q, kb * TC_KBLK, q_base, n, afull);
+      // PAIR: the MMA issuer lives in the leader, so every load of either CTA is credited to the
+      // LEADER's barriers, which expect the bytes of both
+      if (!PAIR || leader) mbar_arrive_expect_tx(afull, static_cast<uint32_t>(KB) * TC_STAGE_BYTES * (PAIR ? 2 : 1));
+      const uint32_t afull_l = PAIR ? mapa_rank0(smem_u32(afull)) : 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        if (PAIR)
+          tma_load_3d_pair(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4), &map_q, kb * TC_KBLK, q_base, n, afull_l);
+        else
+          tma_load_3d(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4), &map_q, kb * TC_KBLK, q_base, n, afull);
+      }
       int s = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < num_tiles; ++t) {
+      for (int tt = 0; tt < seq_tiles; ++tt) {
+        const int t = tt < S_seed ? tt : tt - S_seed;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_parked(&empty[s], ph ^ 1);
+          if (PAIR) {  // this CTA's 128 of the tile's 256 rows
+            if (leader) mbar_arrive_expect_tx(&full[s], 2 * TC_STAGE_BYTES);
+            tma_load_3d_pair(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4), &map_p, kb * TC_KBLK,
+                             t * TN + static_cast<int>(crank) * TC_N, n, mapa_rank0(smem_u32(&full[s])));
+            if (++s == NST) {
+              s = 0;
+              ph ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
           if (CL == 1) {
             tma_load_3d(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4), &map_p, kb * TC_KBLK, t * TC_N, n, &full[s]);
@@ -345,33 +428,40 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    if (lane == 0 && (!PAIR || leader)) {
       mbar_wait(afull, 0);
       tc_fence_after();
       int s = 0;
       uint32_t ph = 0;
-      for (int t = 0; t < num_tiles; ++t) {
-        const int b = t % TC_ABUF;
-        mbar_wait_parked(&tempty[b], ((t / TC_ABUF) & 1) ^ 1);  // the epilogue has drained this buffer
+      for (int t = 0; t < seq_tiles; ++t) {  // t: position in the sequence (buffers rotate with it)
+        const int b = t % ABUF;
+        mbar_wait_parked(&tempty[b], ((t / ABUF) & 1) ^ 1);  // the epilogue(s) drained this buffer
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * TC_N);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * TN);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_parked(&full[s], ph);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(sA + static_cast<size_t>(kb) * (TC_STAGE_BYTES / 4));
           const uint64_t bdesc = umma_desc_sw128(sB + static_cast<size_t>(s) * (TC_STAGE_BYTES / 4));
 #pragma unroll
-          for (int k = 0; k < TC_KBLK / 8; ++k)  // K = 8 per tf32 MMA: 32 bytes along the swizzled row
-            umma_tf32(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), kTcIdesc,
-                      (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TC_KBLK / 8; ++k) {  // K = 8 per tf32 MMA: 32 bytes along the swizzled row
+            if (PAIR)
+              umma_tf32_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                             kTcIdescPair, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_tf32(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), kTcIdesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          }
           // the stage may be refilled once these MMAs have read it
-          if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kMask);
+          if (PAIR) umma_commit_pair(&empty[s]);
+          else if (CL == 1) umma_commit(&empty[s]);
+          else umma_commit_mc(&empty[s], kMask);
           if (++s == NST) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tfull[b]);
+        if (PAIR) umma_commit_pair(&tfull[b]); else umma_commit(&tfull[b]);
       }
     }
   } else {
@@ -381,7 +471,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int row = ew * 32 + lane;          // query row inside the tile
     const int qi = q_base + row;
     const float INF = __int_as_float(0x7f800000);
-    constexpr int HC = TC_N / TC_HALVES;     // columns per half
+    constexpr int HC = TN / TC_HALVES;       // columns per half
     static_assert(HC % 32 == 0 && TC_TOUR == 32, "column c of a chunk feeds tournament slot c");
     const bool live = qi < L1 && !(prm.dbg & 1);
     const size_t qrow = static_cast<size_t>(n) * prm.P1 + min(qi, prm.P1 - 1);
@@ -400,52 +490,69 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t cw_limit = cand_base + static_cast<uint32_t>(TC_CAND - TC_SUB) * CSTRIDE;
     // every warp stages the norms of ITS columns of the next tile in a private double buffer: no
     // CTA-wide barrier per tile
-    static_assert(HC == 64, "two norms per lane");
+    constexpr int WPL = HC / 32;  // norms per lane: 2 or 4
     const float* w_n = prm.w + static_cast<size_t>(n) * prm.P2pad + half * HC;
     float* sWw = sW + (warp - 2) * 2 * HC;
     const uint32_t sW_addr = smem_u32(sWw);
-    *reinterpret_cast<float2*>(sWw + 2 * lane) = *reinterpret_cast<const float2*>(w_n + 2 * lane);
+    const uint32_t tempty_l = PAIR ? mapa_rank0(smem_u32(tempty)) : 0;  // the leader's tempty[0]
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) sWw[WPL * lane + i] = w_n[WPL * lane + i];
     __syncwarp();
-    for (int t = 0; t < num_tiles; ++t) {
-      const int b = t % TC_ABUF;
-      const uint32_t wt = sW_addr + static_cast<uint32_t>((t & 1) * HC * 4);
-      float2 wnext = make_float2(0.0f, 0.0f);
-      if (t + 1 < num_tiles) wnext = *reinterpret_cast<const float2*>(w_n + (t + 1) * TC_N + 2 * lane);
-      mbar_wait_parked(&tfull[b], (t / TC_ABUF) & 1);
+    for (int tt = 0; tt < seq_tiles; ++tt) {
+      const bool seeding = tt < S_seed;
+      const int t = seeding ? tt : tt - S_seed;                                // the tile
+      const int tn = (tt + 1 < S_seed) ? tt + 1 : tt + 1 - S_seed;             // the next tile of the sequence
+      const int b = tt % ABUF;
+      const uint32_t wt = sW_addr + static_cast<uint32_t>((tt & 1) * HC * 4);
+      float wnext[WPL];
+#pragma unroll
+      for (int i = 0; i < WPL; ++i) wnext[i] = (tt + 1 < seq_tiles) ? w_n[tn * TN + WPL * lane + i] : 0.0f;
+      mbar_wait_parked(&tfull[b], (tt / ABUF) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TC_N + half * HC);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TN + half * HC);
 #pragma unroll 1
-      for (int c = 0; c < HC / 32; ++c) {
+      for (int c = 0; c < ((prm.dbg & 2) ? 0 : HC / 32); ++c) {  // dbg 2: drain nothing (MMA / TMA pipeline alone)
         uint32_t acc[32];
         tmem_ld_x32(taddr + static_cast<uint32_t>(c * 32), acc);
         tmem_ld_wait(acc);
-        const uint32_t jc = static_cast<uint32_t>(t * TC_N + half * HC + c * 32);
+        if (prm.dbg & 4) {  // dbg 4: read the accumulators, evaluate nothing
+          if (acc[0] == 0x12345678u && acc[31] == 0x9abcdef0u) T = 0.0f;
+          continue;
+        }
+        const uint32_t jc = static_cast<uint32_t>(t * TN + half * HC + c * 32);
+        // straight-line part first (32 independent columns: norms, s, tournament), hit tests after
+        float sv[32];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3)
+                       : "r"(wt + static_cast<uint32_t>((c * 32 + i4 * 4) * 4)));
+          sv[i4 * 4 + 0] = fmaf(-2.0f, __uint_as_float(acc[i4 * 4 + 0]), w0);
+          sv[i4 * 4 + 1] = fmaf(-2.0f, __uint_as_float(acc[i4 * 4 + 1]), w1);
+          sv[i4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(acc[i4 * 4 + 2]), w2);
+          sv[i4 * 4 + 3] = fmaf(-2.0f, __uint_as_float(acc[i4 * 4 + 3]), w3);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mins[i] = fminf(mins[i], sv[i]);
+        float m8[32 / TC_SUB];
 #pragma unroll
         for (int sub = 0; sub < 32 / TC_SUB; ++sub) {
-          float sv[TC_SUB];
+          float m = fminf(sv[sub * TC_SUB], sv[sub * TC_SUB + 1]);
 #pragma unroll
-          for (int i4 = 0; i4 < TC_SUB / 4; ++i4) {
-            float w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3)
-                         : "r"(wt + static_cast<uint32_t>((c * 32 + sub * TC_SUB + i4 * 4) * 4)));
-            sv[i4 * 4 + 0] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 0]), w0);
-            sv[i4 * 4 + 1] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 1]), w1);
-            sv[i4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 2]), w2);
-            sv[i4 * 4 + 3] = fmaf(-2.0f, __uint_as_float(acc[sub * TC_SUB + i4 * 4 + 3]), w3);
-          }
-          float m = fminf(sv[0], sv[1]);
+          for (int i = 2; i < TC_SUB; ++i) m = fminf(m, sv[sub * TC_SUB + i]);
+          m8[sub] = m;
+        }
+        // the append code is skipped unless some lane has a hit among the columns (never while seeding)
+        if (!seeding && __any_sync(FULL, fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])) <= T)) {
 #pragma unroll
-          for (int i = 2; i < TC_SUB; ++i) m = fminf(m, sv[i]);
-#pragma unroll
-          for (int i = 0; i < TC_SUB; ++i) mins[sub * TC_SUB + i] = fminf(mins[sub * TC_SUB + i], sv[i]);
-          // the append code is skipped unless some lane has a hit among these columns
-          if (__any_sync(FULL, m <= T)) {
+          for (int sub = 0; sub < 32 / TC_SUB; ++sub) {
+            if (!__any_sync(FULL, m8[sub] <= T)) continue;
 #pragma unroll
             for (int i = 0; i < TC_SUB; ++i) {
-              if (sv[i] <= T) {  // predicated: one 64-bit store + one add (no "memory" clobber: the
-                                 // buffer is only read back inside tc_flush_stage, an opaque call)
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cw), "r"(__float_as_uint(sv[i])),
+              if (sv[sub * TC_SUB + i] <= T) {  // predicated: one 64-bit store + one add (no "memory" clobber:
+                                                // the buffer is only read back inside tc_flush_stage, an opaque call)
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cw), "r"(__float_as_uint(sv[sub * TC_SUB + i])),
                              "r"(jc + static_cast<uint32_t>(sub * TC_SUB + i)));
                 cw += CSTRIDE;
               }
@@ -460,7 +567,9 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       // accumulator buffer drained
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[b]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(tempty_l + static_cast<uint32_t>(b * 8)); else mbar_arrive(&tempty[b]);
+      }
       // refresh the threshold: after tiles 1, 2, 3, 4, 6, 8, 12, 16, ... and then every 16th.  The
       // two threads of a row (one per column half) pool their minima slot by slot -- slot i then
       // covers the union of both slot-i subsets, still 32 disjoint subsets of everything the row
@@ -468,7 +577,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const int v = t + 1;
       const bool pow2 = (v & (v - 1)) == 0;
       const bool pow2x3 = (v % 3 == 0) && (((v / 3) & ((v / 3) - 1)) == 0);
-      const bool refresh = v < 64 ? (pow2 || pow2x3) : (v & 15) == 0;
+      const bool refresh = seeding ? (tt == S_seed - 1) : (v < 64 ? (pow2 || pow2x3) : (v & 15) == 0);
       if (refresh) {
         if (half != 0) {
 #pragma unroll
@@ -489,7 +598,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
       }
       // stage the next tile's norms (the warp is past its reads of that buffer)
-      *reinterpret_cast<float2*>(sWw + ((t + 1) & 1) * HC + 2 * lane) = wnext;
+#pragma unroll
+      for (int i = 0; i < WPL; ++i) sWw[((tt + 1) & 1) * HC + WPL * lane + i] = wnext[i];
       __syncwarp();
       if (refresh) {
         asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
@@ -505,10 +615,10 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still write or signal here
+  if (CL > 1 || PAIR) cluster_sync_all();  // nobody leaves while a peer may still write or signal here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_ABUF * TC_N);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -653,7 +763,9 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
       printf("flag n=%d q=%d sK=%g tau=%g E=%g total=%u kth=%d\n", n, qi, sK, tau, E, total, kth);
     return;
   }
-  if (prm.debug && lane == 0 && (qrow & 0xFFFF) == 0) printf("row %d: %u candidates\n", static_cast<int>(qrow), total);
+  if (prm.debug && lane == 0 && (qrow & 0xFFFF) == 0)
+    printf("row %d: %u candidates within the final threshold of %u + %u appended\n", static_cast<int>(qrow), total,
+           prm.counts[qrow * TC_HALVES] & 0x7fffffffu, prm.counts[qrow * TC_HALVES + 1] & 0x7fffffffu);
   // exact reference distance for the entries within tau: same operations, same order (knn_cpu.cpp:42-50)
   uint64_t k2 = kEmptyKey;
   if (have && s <= tau) {
@@ -822,7 +934,7 @@ struct TcLayout {
 
 TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
   TcLayout l;
-  l.P2pad = static_cast<int>((P2 + TC_N - 1) / TC_N * TC_N);
+  l.P2pad = static_cast<int>((P2 + 2 * TC_N - 1) / (2 * TC_N) * (2 * TC_N));  // whole 256-point tiles
   size_t off = 0;
   l.P1pad = static_cast<int>((P1 + TC_M - 1) / TC_M * TC_M);
   l.maxw_off = off;  off += align_up(size_t(N) * 4, 256);
@@ -840,7 +952,7 @@ TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 inline size_t tc_smem_fixed(int KB) {
-  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_CSTRIDE * 8 + size_t(TC_TOUR) * TC_M * 4 + 4 * 2 * TC_N * 4 + TC_M * 4 +
+  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_CSTRIDE * 8 + size_t(TC_TOUR) * TC_M * 4 + 4 * 2 * 2 * TC_N * 4 + TC_M * 4 +
          (2 * TC_MAX_STAGES + 2 * TC_ABUF + 2) * 8 +
          1024 /* alignment */;
 }
@@ -894,7 +1006,8 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   }
   const int cl_env = get_option("tc_cluster", 1);  // CTAs sharing every p2 stage by TMA multicast (tuning aid)
   const int64_t qtiles = ceil_div(P1, TC_M);
-  const int CL = (cl_env >= 4 && qtiles >= 4) ? 4 : ((cl_env >= 2 && qtiles >= 2) ? 2 : 1);
+  const bool pair = get_option("tc_pair", 1) != 0 && qtiles >= 2;  // cta_group::2 pairs
+  const int CL = pair ? 1 : ((cl_env >= 4 && qtiles >= 4) ? 4 : ((cl_env >= 2 && qtiles >= 2) ? 2 : 1));
   CUtensorMap map_q, map_p;
   int rc = make_map(&map_q, p1, N, P1, D, TC_M);
   if (rc != POPS_OK) return rc;
@@ -911,16 +1024,19 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   const size_t smem = fixed + size_t(prm.nstage) * TC_STAGE_BYTES;
   {
     void (*kern)(const CUtensorMap, const CUtensorMap, const TcParams) =
-        CL == 4 ? knn_tc_scan_kernel<4> : (CL == 2 ? knn_tc_scan_kernel<2> : knn_tc_scan_kernel<1>);
+        pair ? knn_tc_scan_kernel<1, true>
+             : (CL == 4 ? knn_tc_scan_kernel<4, false>
+                        : (CL == 2 ? knn_tc_scan_kernel<2, false> : knn_tc_scan_kernel<1, false>));
+    const int cdim = pair ? 2 : CL;
     POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(ceil_div(qtiles, CL) * CL), N);  // whole clusters; spare CTAs see no query
+    cfg.gridDim = dim3(static_cast<unsigned>(ceil_div(qtiles, cdim) * cdim), N);  // whole clusters; spare CTAs see no query
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = cdim;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
