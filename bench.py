@@ -368,12 +368,21 @@ def run_ours(args, rank, world, local_rank):
     out_i_pin = torch.empty((B, P, K_NN), dtype=torch.int64).pin_memory()
     len_pin = len_host.pin_memory()
 
-    def step_e2e():
+    def step_e2e_serial():
         pd = p_pin.to(dev, non_blocking=True)
         ld = len_pin.to(dev, non_blocking=True)
         r = knn_points(pd, pd, ld, ld, K=K_NN)
         out_d_pin.copy_(r.dists, non_blocking=True)
         out_i_pin.copy_(r.idx, non_blocking=True)
+
+    from pytorch3d_pointops_b200.host import HostKnn
+
+    host_knn = HostKnn(B, P, P, D, K_NN, dev, slices=3)
+
+    def step_e2e():
+        # host-in / host-out API: the batch streams through the GPU in 3 slices of clouds (one CUDA graph), so the
+        # H2D of slice i+1 and the D2H of slice i-1 overlap the search of slice i
+        host_knn(p_pin, None, len_pin)
 
     for _ in range(2):
         step_e2e()
@@ -396,6 +405,18 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = queries_per_step * world * e2e_steps / (e2e_ms * 1e-3)
     h2d = p_pin.numel() * 4 + len_pin.numel() * 8
     d2h = out_d_pin.numel() * 4 + out_i_pin.numel() * 8
+    # the plain call sequence a user of the reference API writes (no overlap), for comparison
+    for _ in range(2):
+        step_e2e_serial()
+    torch.cuda.synchronize(dev)
+    s_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    for a, b in s_evs:
+        flush.zero_()
+        a.record()
+        step_e2e_serial()
+        b.record()
+    torch.cuda.synchronize(dev)
+    e2e_serial_ms = float(sum(a.elapsed_time(b) for a, b in s_evs)) / e2e_steps
 
     # ---- secondary: chamfer fwd+bwd (configs[1]) ---------------------------------------------------
     ch = {k: v.to(dev) for k, v in make_chamfer_inputs(rank).items()}
@@ -523,7 +544,10 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps,
-                "what": "pinned host p -> H2D -> knn_points -> D2H of dists+idx into pinned host"},
+                "what": "pytorch3d_pointops_b200.host.HostKnn: pinned host clouds -> H2D -> knn_points_idx -> D2H of "
+                        "dists+idx into pinned host, 3 slices of clouds pipelined over 3 streams, replayed as one CUDA graph",
+                "serial_ms_per_step": e2e_serial_ms,
+                "serial_what": "p.to(device) -> knn_points -> copy_ of dists+idx to pinned host on one stream"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "secondary": {"metric": "chamfer_pairs_per_sec", "value": chamfer_pairs, "unit": "cloud-pairs/s",

@@ -216,3 +216,27 @@ def test_no_cuda_errors_and_streams():
     s.synchronize()
     assert torch.equal(out.idx, ref.idx) and torch.equal(out.dists, ref.dists)
     torch.cuda.synchronize()
+
+
+def test_host_pipeline_matches_device_call():
+    """host.HostKnn (sliced, three streams) returns exactly what one knn_points_idx call returns."""
+    from pytorch3d_pointops_b200.host import HostKnn
+
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(9)
+    N, P, K = 7, 3000, 8
+    p = torch.rand(N, P, 3, generator=gen).pin_memory()
+    L = torch.randint(1, P + 1, (N,), generator=gen).pin_memory()
+    hk = HostKnn(N, P, P, 3, K, DEV, slices=3)
+    for _ in range(2):  # second call reuses the staging
+        d, i = hk(p, None, L)
+        torch.cuda.synchronize()
+        ri, rd = _C.knn_points_idx(p.to(DEV), p.to(DEV), L.to(DEV), L.to(DEV), 2, K, -1)
+        assert torch.equal(i, ri.cpu()) and torch.equal(d, rd.cpu())
+    q = torch.rand(N, 500, 3, generator=gen).pin_memory()
+    hk2 = HostKnn(N, 500, P, 3, K, DEV, slices=4)
+    d, i = hk2(q, p, None, L)
+    torch.cuda.synchronize()
+    L1 = torch.full((N,), 500, device=DEV)
+    ri, rd = _C.knn_points_idx(q.to(DEV), p.to(DEV), L1, L.to(DEV), 2, K, -1)
+    assert torch.equal(i, ri.cpu()) and torch.equal(d, rd.cpu())
