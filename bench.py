@@ -453,6 +453,7 @@ def run_ours(args, rank, world, local_rank):
         c_ms = float(t.item())
     chamfer_pairs = 32 * world * c_steps / (c_ms * 1e-3)
 
+    sms_early = torch.cuda.get_device_properties(dev).multi_processor_count
     # ---- secondary: high-D feature KNN on the tensor cores (configs[4]: D=128, K=16, B=16, P=32768;
     #      clouds shard 16/world per rank) ----------------------------------------------------------
     highdim = None
@@ -503,6 +504,73 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_flop_per_launch": gemm_flop},
         }
         del xh
+
+    # ---- secondary: FPS (configs[2]: K=1024 from P=65536, B=64 sharded over 8 GPUs -> 64/8 per
+    #      rank at world<=8) and ball query + gather (configs[3]: K=32, r=0.1, B=128, P=16384) ------
+    others = {}
+    if not args.no_highdim:
+        from pytorch3d_pointops_b200.functions import ball_query, sample_farthest_points
+
+        peaks_o, _ = load_peaks()
+        Bf = 8  # configs[2]: 64 clouds over 8 GPUs = 8 per rank
+        gf = torch.Generator().manual_seed(2 + rank)
+        pf = torch.rand(Bf, 65536, 3, generator=gf).to(dev)
+        for _ in range(2):
+            sample_farthest_points(pf, K=1024)
+        torch.cuda.synchronize(dev)
+        f_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        barrier()
+        for a, b in f_evs:
+            a.record()
+            sample_farthest_points(pf, K=1024)
+            b.record()
+        torch.cuda.synchronize(dev)
+        f_ms = float(sum(a.elapsed_time(b) for a, b in f_evs)) / len(f_evs)
+        f_bytes = Bf * 1023 * 65536 * (4 * 3 + 8)  # re-read points + r/w min-dist per iteration
+        others["secondary_fps"] = {
+            "metric": "fps_samples_per_sec", "value": Bf * 1024 * world / (f_ms * 1e-3), "unit": "samples/s",
+            "ms_per_step": f_ms, "us_per_iteration": f_ms * 1e3 / 1023,
+            "workload": f"sample_farthest_points K=1024 from P=65536, {Bf} clouds per rank (configs[2]: 64 clouds over 8 GPUs)",
+            "roofline": {"kernel": "fps_d3_kernel (cluster per cloud, points in registers)", "bound": "hbm",
+                         "achieved": f_bytes / (f_ms * 1e-3) / 1e9, "peak": float(peaks_o.get("hbm_gbs", 6650.0)),
+                         "unit": "GB/s", "frac": f_bytes / (f_ms * 1e-3) / 1e9 / float(peaks_o.get("hbm_gbs", 6650.0)),
+                         "note": "ALGORITHMIC bytes of the streaming formulation; the kernel keeps the cloud "
+                                 "on chip and reads it from HBM once, so this is a latency-bound kernel"}}
+        del pf
+        Bb = max(1, 128 // world)
+        gb = torch.Generator().manual_seed(3 + rank)
+        pb = torch.rand(Bb, 16384, 3, generator=gb).to(dev)
+        for _ in range(2):
+            rb = ball_query(pb, pb, K=32, radius=0.1)
+        torch.cuda.synchronize(dev)
+        b_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        lib.pops_profile_reset()
+        lib.pops_profile_enable(1)
+        barrier()
+        for a, b in b_evs:
+            a.record()
+            rb = ball_query(pb, pb, K=32, radius=0.1)
+            b.record()
+        torch.cuda.synchronize(dev)
+        lib.pops_profile_enable(0)
+        b_ms = float(sum(a.elapsed_time(b) for a, b in b_evs)) / len(b_evs)
+        bq_ms, _ = kernel_ms(b"ball_query")
+        lib.pops_profile_reset()
+        last = rb.idx[..., -1]
+        scanned = torch.where(last >= 0, last + 1, torch.full_like(last, 16384)).sum().item()
+        others["secondary_ball_query"] = {
+            "metric": "ball_query_queries_per_sec", "value": Bb * 16384 * world / (b_ms * 1e-3), "unit": UNIT,
+            "ms_per_step": b_ms, "kernel_ms": bq_ms,
+            "workload": f"ball_query K=32 r=0.1 return_nn=True (masked gather), B={Bb * world} ({Bb}/rank) P=16384 (configs[3])",
+            "roofline": {"kernel": "ball_query_d3_kernel", "bound": "fp32",
+                         "achieved": 9.0 * scanned / (bq_ms * 1e-3) / 1e12 if bq_ms > 0 else None,
+                         "peak": sms_early * 128 * 2 * float(peaks_o.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12,
+                         "unit": "TFLOP/s",
+                         "note": "3*D flop per point the reference's sequential scan visits (idx[q,K-1]+1, or "
+                                 "lengths2 when the ball holds fewer than K points), SURVEY 8(d)"}}
+        rl = others["secondary_ball_query"]["roofline"]
+        rl["frac"] = rl["achieved"] / rl["peak"] if rl["achieved"] else None
+        del pb, rb
 
     # ---- roofline of the dominant kernel (knn_scan) -----------------------------------------------
     peaks, peak_src = load_peaks()
@@ -557,6 +625,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if highdim is not None:
         line["secondary_highdim"] = highdim
+    line.update(others)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, kind, sample, wall = cpu_reference_rate(p_host, len_host, budget_s=12.0, workers=1)

@@ -143,6 +143,16 @@ int pops_padded_to_packed(const float* padded, const int64_t* first_idxs, int64_
                           pops_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * sample_pdf.  Replaces _C.sample_pdf (ext.cpp:27; sample_pdf.h:58-78; sample_pdf_cpu.cpp:24-142):
+ * inverse-CDF sampling of B piecewise-constant densities.  bins (B,n_bins+1) f32 bin edges,
+ * weights (B,n_bins) f32 >= 0, outputs (B,n_samples) f32: on entry uniform numbers in [0,1], on
+ * return the samples -- IN PLACE, like the reference (which also bumps the tensor's autograd
+ * version; the Python glue does that).  Same float operations as the reference CPU path.
+ * ------------------------------------------------------------------------------------------- */
+int pops_sample_pdf(const float* bins, const float* weights, float* outputs, int64_t B,
+                    int64_t n_bins, int64_t n_samples, float eps, pops_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused row gather.  Replaces the torch expand+gather+mask of knn_gather (functions/knn.py:200-250)
  * and masked_gather (functions/utils.py:20-65).
  *   x (N,M,U) f32, idx (N,L,K) i64 -> out (N,L,K,U) f32.

@@ -96,6 +96,31 @@ def knn_points_backward(p1, p2, lengths1, lengths2, idx, norm, grad_dists):
     return g1, g2
 
 
+def sample_pdf_(bins, weights, outputs, eps):
+    """_C.sample_pdf on CPU (sample_pdf_cpu.cpp:24-142): in place on `outputs` (B, n_samples)."""
+    bins = bins.detach().cpu().float().contiguous()
+    weights = weights.detach().cpu().float().contiguous()
+    assert outputs.dtype == torch.float32 and outputs.is_contiguous() and outputs.device.type == "cpu"
+    B, n_bins = weights.shape
+    st = lib().oracle_sample_pdf(_f(bins), _f(weights), _f(outputs), _i64(B), _i64(n_bins), _i64(outputs.shape[1]),
+                                 ctypes.c_float(eps))
+    assert st == 0
+    return outputs
+
+
+def sample_pdf(bins, weights, n_samples, det=False, eps=1e-5, u=None):
+    """functions/sample_pdf.py:14-66.  `u` (optional) supplies the uniform numbers so that both
+    sides of a comparison draw the same ones."""
+    n_bins = weights.shape[-1]
+    batch_shape = bins.shape[:-1]
+    if det:
+        out = torch.linspace(0.0, 1.0, n_samples, dtype=torch.float32).expand(batch_shape + (n_samples,)).contiguous()
+    else:
+        out = (u if u is not None else torch.rand(batch_shape + (n_samples,))).detach().cpu().float().clone().contiguous()
+    sample_pdf_(bins.reshape(-1, n_bins + 1), weights.reshape(-1, n_bins), out.view(-1, n_samples), eps)
+    return out
+
+
 def ball_query_idx(p1, p2, lengths1=None, lengths2=None, K=500, radius=0.2, q0=0, q1=-1,
                    threads=1):
     """_C.ball_query on CPU (ball_query_cpu.cpp:12-54).  Returns (idx, dists)."""

@@ -16,6 +16,7 @@ _SUBMODULES = [
     "functions.ball_query",
     "functions.chamfer",
     "functions.sample_farthest_points",
+    "functions.sample_pdf",
     "functions.packed_to_padded",
     "functions.utils",
     "structures",

@@ -7,7 +7,8 @@ Inputs must be CUDA tensors: there is no CPU path (the reference's CPU loops sur
 test oracle).  Outputs are fresh tensors on the inputs' device; kernels are enqueued on the
 current stream of that device and the call returns without synchronising (knn.cu:330-331).
 
-Extra, additive entry points used by functions/*.py: `gather`, `gather_backward`.
+Extra, additive entry points used by functions/*.py: `gather`, `gather_backward`, the fused
+chamfer pieces.
 """
 from __future__ import annotations
 
@@ -331,3 +332,31 @@ def chamfer_backward(x, y, idx, lengths1, lengths2, weights, norm, xfs, yfs, poi
                                        _ptr_array(gxf), _ptr_array(gyf), _stream(x))
     _lib.check(st, "chamfer_backward")
     return grad_x, grad_y, gxf, gyf
+
+
+def sample_pdf(bins, weights, outputs, eps):
+    """sample_pdf.h:58-78: bins (B,n_bins+1), weights (B,n_bins), outputs (B,n_samples) float32;
+    `outputs` holds uniform numbers on entry and the samples on return (in place; its autograd
+    version is bumped like torch::autograd::increment_version in sample_pdf_cpu.cpp:141)."""
+    bins = _cuda_f32(bins, "bins")
+    weights = _cuda_f32(weights, "weights")
+    _same_device(bins, weights, "bins and weights")
+    _same_device(bins, outputs, "bins and outputs")
+    if not outputs.is_cuda or outputs.dtype != torch.float32:
+        raise RuntimeError("outputs must be a float32 CUDA tensor.")
+    if not outputs.is_contiguous():
+        raise RuntimeError("outputs must be contiguous.")  # written in place: no silent copy
+    if bins.ndim != 2 or weights.ndim != 2 or outputs.ndim != 2:
+        raise RuntimeError("bins, weights and outputs must be 2-dimensional.")
+    B, n_bins = weights.shape
+    if bins.shape[0] != B or outputs.shape[0] != B:
+        raise RuntimeError("Batch dimensions of bins, weights and outputs must agree.")
+    if bins.shape[1] != n_bins + 1:
+        raise RuntimeError("There must be one more bin edge than weights.")
+    lib = _lib.load()
+    with torch.cuda.device(bins.device):
+        st = lib.pops_sample_pdf(bins.data_ptr(), weights.data_ptr(), outputs.data_ptr(), B, n_bins,
+                                 outputs.shape[1], float(eps), _stream(bins))
+    _lib.check(st, "sample_pdf")
+    torch.autograd.graph.increment_version(outputs)
+    return None

@@ -36,6 +36,7 @@ SIGNATURES = {
     "pops_sample_farthest_points": (c_int, [_P] * 4 + [c_int64] * 4 + [_P, _P, c_size_t, _P]),
     "pops_packed_to_padded": (c_int, [_P, _P] + [c_int64] * 4 + [_P, _P]),
     "pops_padded_to_packed": (c_int, [_P, _P] + [c_int64] * 4 + [_P, _P]),
+    "pops_sample_pdf": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P]),
     "pops_gather": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P, _P]),
     "pops_gather_backward": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P]),
     "pops_chamfer_forward": (c_int, [_P] * 5 + [c_int64] * 3 + [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),

@@ -323,6 +323,28 @@ def main():
     })
     save("pointclouds_cases", **cases)
 
+    # ---- sample_pdf (functions/sample_pdf.py:14-66 on the reference's CPU kernel) -----------------
+    from pytorch3d_pointops.functions.sample_pdf import sample_pdf
+
+    g = torch.Generator().manual_seed(21)
+    cases = {}
+    # (batch sizes chosen so that the reference's 4-thread split stays in bounds: with B = 5 its
+    #  third worker is handed rows [4, 6) -- sample_pdf_cpu.cpp:121-135 -- and corrupts the heap)
+    for name, (shape, n_bins, n_samples) in {"a": ((4,), 64, 33), "b": ((3, 4), 7, 128), "c": ((1,), 1, 9),
+                                             "d": ((2,), 200, 17)}.items():
+        edges = torch.sort(torch.rand(shape + (n_bins + 1,), generator=g) * 4 - 1, dim=-1).values
+        w = torch.rand(shape + (n_bins,), generator=g)
+        if name == "b":
+            w[..., 2] = 0.0          # empty bins
+            w[0, 0] = 0.0            # an all-empty row
+        cases[f"{name}.bins"], cases[f"{name}.weights"] = edges, w
+        cases[f"{name}.det"] = sample_pdf(edges, w, n_samples, det=True)
+        u = torch.rand(shape + (n_samples,), generator=g)
+        out = u.clone()
+        cref.sample_pdf(edges.reshape(-1, n_bins + 1), w.reshape(-1, n_bins), out.view(-1, n_samples), 1e-5)
+        cases[f"{name}.u"], cases[f"{name}.rand"] = u, out
+    save("sample_pdf_cases", **cases)
+
 
 if __name__ == "__main__":
     main()

@@ -193,3 +193,42 @@ def test_pointclouds_cuda_plumbing(golden):
     assert torch.equal(pc.packed_to_cloud_idx().cpu(), g.t("packed_to_cloud_idx"))
     back = pc.cpu()
     assert torch.equal(back.points_packed(), g.t("points_packed"))
+
+
+def test_sample_pdf_golden_and_oracle(golden, oracle):
+    """sample_pdf: bit-exact vs the reference's golden vectors and the oracle; API errors."""
+    from pytorch3d_pointops_b200 import _C
+    from pytorch3d_pointops_b200.functions.sample_pdf import sample_pdf, sample_pdf_python
+
+    g = golden("sample_pdf_cases")
+    for name, n_samples in (("a", 33), ("b", 128), ("c", 9), ("d", 17)):
+        bins, w = g.t(f"{name}.bins", DEV), g.t(f"{name}.weights", DEV)
+        assert torch.equal(sample_pdf(bins, w, n_samples, det=True).cpu(), g.t(f"{name}.det"))
+        out = g.t(f"{name}.u", DEV).clone()
+        v0 = out._version
+        n_bins = w.shape[-1]
+        _C.sample_pdf(bins.reshape(-1, n_bins + 1), w.reshape(-1, n_bins), out.view(-1, n_samples), 1e-5)
+        assert out._version > v0  # in place + version bump, like the reference
+        assert torch.equal(out.cpu(), g.t(f"{name}.rand"))
+    gen = torch.Generator().manual_seed(12)
+    B, n_bins, n_samples = 4097, 64, 128  # NeRF-like: rays x bins (and a batch the reference cannot split safely)
+    bins = torch.sort(torch.rand(B, n_bins + 1, generator=gen) * 6, dim=-1).values
+    w = torch.rand(B, n_bins, generator=gen) * (torch.rand(B, n_bins, generator=gen) > 0.3)
+    u = torch.rand(B, n_samples, generator=gen)
+    want = oracle.sample_pdf(bins, w, n_samples, u=u)
+    got = u.to(DEV).clone()
+    _C.sample_pdf(bins.to(DEV), w.to(DEV), got, 1e-5)
+    assert torch.equal(got.cpu(), want)
+    # random sampling stays inside the support; the searchsorted variant agrees up to rounding
+    s = sample_pdf(bins.to(DEV), w.to(DEV), 32)
+    assert s.shape == (B, 32) and (s >= bins.min()).all() and (s <= bins.max()).all()
+    det = sample_pdf(bins.to(DEV), w.to(DEV) + 0.05, 16, det=True)
+    assert torch.allclose(det, sample_pdf_python(bins.to(DEV), w.to(DEV) + 0.05, 16, det=True), atol=2e-3)
+    with pytest.raises(ValueError, match="Negative weights"):
+        sample_pdf(bins.to(DEV), -w.to(DEV) - 1.0, 4)
+    with pytest.raises(ValueError, match="Inconsistent shapes"):
+        sample_pdf(bins.to(DEV)[:, :-1], w.to(DEV), 4)
+    with pytest.raises(NotImplementedError):
+        sample_pdf(bins.to(DEV).requires_grad_(True), w.to(DEV), 4)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        _C.sample_pdf(bins, w, u.clone(), 1e-5)

@@ -222,3 +222,26 @@ def test_oracle_threads_and_query_window(oracle):
     win_i, win_d = oracle.knn_points_idx(p, p, None, None, 2, 16, q0=32, q1=96, threads=4)
     assert torch.equal(win_i[:, 32:96], full_i[:, 32:96]) and torch.equal(win_d[:, 32:96], full_d[:, 32:96])
     assert not win_i[:, :32].any() and not win_i[:, 96:].any()
+
+
+def test_sample_pdf_oracle_vs_golden_and_ref(golden):
+    """oracle_sample_pdf == the unmodified reference (golden vectors; oracle/_ref when present)."""
+    from oracle import build_ref
+    from oracle import oracle as O
+
+    g = golden("sample_pdf_cases")
+    for name, n_samples in (("a", 33), ("b", 128), ("c", 9), ("d", 17)):
+        bins, w = g.t(f"{name}.bins"), g.t(f"{name}.weights")
+        assert torch.equal(O.sample_pdf(bins, w, n_samples, det=True), g.t(f"{name}.det"))
+        assert torch.equal(O.sample_pdf(bins, w, n_samples, u=g.t(f"{name}.u")), g.t(f"{name}.rand"))
+    if build_ref.available():
+        ref = build_ref.load()
+        gen = torch.Generator().manual_seed(8)
+        for B, n_bins, n_samples in ((8, 64, 50), (4, 3, 7), (1, 128, 300)):  # B: see make_golden.py
+            bins = torch.sort(torch.randn(B, n_bins + 1, generator=gen), dim=-1).values
+            w = torch.rand(B, n_bins, generator=gen) * (torch.rand(B, n_bins, generator=gen) > 0.2)
+            u = torch.rand(B, n_samples, generator=gen)
+            a, b = u.clone(), u.clone()
+            ref.sample_pdf(bins, w, a, 1e-5)
+            O.sample_pdf_(bins, w, b, 1e-5)
+            assert torch.equal(a, b)
