@@ -12,7 +12,10 @@
 //
 // cosine_similarity follows ATen's formulation (dim=2, eps=1e-6):
 //   cos = sum_k (a_k / max(|a|, eps)) * (b_k / max(|b|, eps)).
-// HBM bound, trivial next to the search; one CTA per cloud (deterministic reductions).
+// HBM bound.  Forward: one CLUSTER of kChamferCluster CTAs per cloud; every CTA reduces its slice of
+// the points, pushes its partials to rank 0 through distributed shared memory, and rank 0 adds them
+// in rank order (deterministic).  Backward: no reduction at all -> flat grid over the points.
+#include <algorithm>
 #include <cfloat>
 
 #include "common.cuh"
@@ -21,6 +24,23 @@ namespace pops {
 
 constexpr int kChamferMaxFeats = 8;
 constexpr int kChamferThreads = 512;
+constexpr int kChamferCluster = 8;  // CTAs per cloud in the forward kernel (portable cluster size)
+constexpr int kBwdThreads = 256;
+
+__device__ __forceinline__ uint32_t ch_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void ch_cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store one 32-bit value into the shared memory of CTA `rank` of this cluster
+__device__ __forceinline__ void ch_st_remote(void* local_smem_ptr, uint32_t rank, uint32_t value) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(value) : "memory");
+}
 
 struct ChamferFeat {
   const float* xf[kChamferMaxFeats];
@@ -72,24 +92,32 @@ chamfer_fwd_kernel(const float* __restrict__ dists, const int64_t* __restrict__ 
                    const float* __restrict__ weights, int P1, int P2, ChamferFeat ft, int reduction,
                    int abs_cosine, int N, float* __restrict__ cham_out, float* __restrict__ feat_out,
                    int64_t* __restrict__ argmax_out) {
+  constexpr int C = kChamferCluster;
   __shared__ float sm[32];
   __shared__ int smi[32];
-  const int n = blockIdx.x, tid = threadIdx.x;
+  // rank 0 only: partials of every CTA of the cluster (slot 0: chamfer term / max value, 1..8: features)
+  __shared__ float part[C][1 + kChamferMaxFeats];
+  __shared__ int parti[C];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const int rank = static_cast<int>(ch_cluster_rank());
   int64_t L1l = len1[n], L2l = len2[n];
   const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
   const bool y_empty = L2l <= 0;
   const float w = weights ? weights[n] : 1.0f;
   const float* dn = dists + static_cast<size_t>(n) * P1;
   const int64_t* in = idx + static_cast<size_t>(n) * P1;
+  // this CTA's contiguous slice of the cloud's points
+  const int per = (P1 + C - 1) / C;
+  const int i0 = rank * per, i1 = min(P1, i0 + per);
 
   // ---- chamfer term -----------------------------------------------------------------------------
   if (reduction == kRedNone) {
-    for (int i = tid; i < P1; i += kChamferThreads)
+    for (int i = i0 + tid; i < i1; i += kChamferThreads)
       cham_out[static_cast<size_t>(n) * P1 + i] = (i < L1) ? dn[i] * w : 0.0f;
   } else if (reduction == kRedMax) {
     float best = -FLT_MAX;
     int bi = 0x7fffffff;
-    for (int i = tid; i < P1; i += kChamferThreads) {
+    for (int i = i0 + tid; i < i1; i += kChamferThreads) {
       const float v = (i < L1) ? dn[i] * w : 0.0f;  // padded points count as 0, as in the reference
       if (v > best) { best = v; bi = i; }
     }
@@ -111,30 +139,30 @@ chamfer_fwd_kernel(const float* __restrict__ dists, const int64_t* __restrict__ 
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
       if (tid == 0) {
-        cham_out[n] = best;
-        argmax_out[n] = bi;
+        ch_st_remote(&part[rank][0], 0, __float_as_uint(best));
+        ch_st_remote(&parti[rank], 0, static_cast<uint32_t>(bi));
       }
     }
     __syncthreads();
   } else {
     float s = 0.f;
-    for (int i = tid; i < L1; i += kChamferThreads) s += dn[i] * w;
+    for (int i = i0 + tid; i < min(i1, L1); i += kChamferThreads) s += dn[i] * w;
     s = block_sum(s, sm);
-    if (tid == 0) cham_out[n] = (reduction == kRedMean) ? s / static_cast<float>(L1 > 0 ? L1 : 1) : s;
+    if (tid == 0) ch_st_remote(&part[rank][0], 0, __float_as_uint(s));
   }
 
   // ---- feature terms ----------------------------------------------------------------------------
   for (int f = 0; f < ft.num; ++f) {
-    const int C = ft.chans[f];
-    const float* xf = ft.xf[f] + static_cast<size_t>(n) * P1 * C;
-    const float* yf = ft.yf[f] + static_cast<size_t>(n) * P2 * C;
+    const int Cf = ft.chans[f];
+    const float* xf = ft.xf[f] + static_cast<size_t>(n) * P1 * Cf;
+    const float* yf = ft.yf[f] + static_cast<size_t>(n) * P2 * Cf;
     float s = 0.f;
-    for (int i = tid; i < P1; i += kChamferThreads) {
+    for (int i = i0 + tid; i < i1; i += kChamferThreads) {
       float fd = 0.0f;
       if (i < L1) {
         float na, nb;
         const int64_t j = in[i];
-        const float c = cosine(xf + static_cast<size_t>(i) * C, yf + static_cast<size_t>(j) * C, C, &na, &nb, y_empty);
+        const float c = cosine(xf + static_cast<size_t>(i) * Cf, yf + static_cast<size_t>(j) * Cf, Cf, &na, &nb, y_empty);
         fd = (1.0f - (abs_cosine ? fabsf(c) : c)) * w;
       }
       if (reduction == kRedNone) feat_out[(static_cast<size_t>(f) * N + n) * P1 + i] = fd;
@@ -142,15 +170,36 @@ chamfer_fwd_kernel(const float* __restrict__ dists, const int64_t* __restrict__ 
     }
     if (reduction != kRedNone) {
       s = block_sum(s, sm);
-      if (tid == 0)
-        feat_out[static_cast<size_t>(f) * N + n] = (reduction == kRedMean) ? s / static_cast<float>(L1 > 0 ? L1 : 1) : s;
+      if (tid == 0) ch_st_remote(&part[rank][1 + f], 0, __float_as_uint(s));
+    }
+  }
+
+  // ---- rank 0 combines the CTAs' partials in rank order ---------------------------------------------
+  ch_cluster_barrier();
+  if (rank == 0 && tid == 0 && reduction != kRedNone) {
+    if (reduction == kRedMax) {
+      float best = part[0][0];
+      int bi = parti[0];
+      for (int r = 1; r < C; ++r)
+        if (part[r][0] > best || (part[r][0] == best && parti[r] < bi)) { best = part[r][0]; bi = parti[r]; }
+      cham_out[n] = best;
+      argmax_out[n] = bi;
+    } else {
+      float s = 0.f;
+      for (int r = 0; r < C; ++r) s += part[r][0];
+      cham_out[n] = (reduction == kRedMean) ? s / static_cast<float>(L1 > 0 ? L1 : 1) : s;
+    }
+    for (int f = 0; f < ft.num; ++f) {
+      float s = 0.f;
+      for (int r = 0; r < C; ++r) s += part[r][1 + f];
+      feat_out[static_cast<size_t>(f) * N + n] = (reduction == kRedMean) ? s / static_cast<float>(L1 > 0 ? L1 : 1) : s;
     }
   }
 }
 
 // grad buffers must be zero-filled by the caller (the host function does it)
 template <int NORM>
-__global__ void __launch_bounds__(kChamferThreads)
+__global__ void __launch_bounds__(kBwdThreads)
 chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                    const int64_t* __restrict__ idx, const int64_t* __restrict__ len1,
                    const int64_t* __restrict__ len2, const float* __restrict__ weights, int P1, int P2,
@@ -158,7 +207,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                    const float* __restrict__ g_cham, const float* __restrict__ g_feat,
                    const int64_t* __restrict__ argmax, float* __restrict__ grad_x,
                    float* __restrict__ grad_y) {
-  const int n = blockIdx.x, tid = threadIdx.x;
+  const int n = blockIdx.y;
   int64_t L1l = len1[n], L2l = len2[n];
   const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
   const bool y_empty = L2l <= 0;
@@ -171,7 +220,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
   float* gyn = grad_y + static_cast<size_t>(n) * P2 * D;
   const int amax = (reduction == kRedMax) ? static_cast<int>(argmax[n]) : -1;
 
-  for (int i = tid; i < L1; i += kChamferThreads) {
+  for (int i = blockIdx.x * kBwdThreads + threadIdx.x; i < L1; i += gridDim.x * kBwdThreads) {
     // ---- chamfer term: d(dist)/dx, d(dist)/dy ----
     float gd;
     if (reduction == kRedNone) gd = g_cham[static_cast<size_t>(n) * P1 + i] * w;
@@ -257,9 +306,22 @@ extern "C" int pops_chamfer_forward(const float* dists, const int64_t* idx, cons
   POPS_CHECK_ARG(point_reduction != kRedMax || argmax_out, "null argmax_out");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   profile_begin("chamfer", st);
-  chamfer_fwd_kernel<<<static_cast<unsigned>(N), kChamferThreads, 0, st>>>(
-      dists, idx, lengths1, lengths2, weights, int(P1), int(P2), ft, point_reduction, abs_cosine, int(N),
-      cham_out, feat_out, argmax_out);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kChamferCluster, static_cast<unsigned>(N));
+    cfg.blockDim = dim3(kChamferThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kChamferCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, chamfer_fwd_kernel, dists, idx, lengths1, lengths2, weights, int(P1), int(P2),
+                                    ft, point_reduction, abs_cosine, int(N), cham_out, feat_out, argmax_out));
+  }
   profile_end("chamfer", st);
   POPS_LAUNCH_OK("chamfer_fwd_kernel");
   return POPS_OK;
@@ -287,12 +349,14 @@ extern "C" int pops_chamfer_backward(const float* x, const float* y, const int64
   }
   if (N == 0 || P1 == 0) return POPS_OK;
   POPS_CHECK_ARG(x && y && idx && lengths1 && lengths2 && g_cham, "null pointer argument");
+  const dim3 bgrid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(P1, kBwdThreads), 64))),
+                   static_cast<unsigned>(N));
   if (norm == 2)
-    chamfer_bwd_kernel<2><<<static_cast<unsigned>(N), kChamferThreads, 0, st>>>(
+    chamfer_bwd_kernel<2><<<bgrid, kBwdThreads, 0, st>>>(
         x, y, idx, lengths1, lengths2, weights, int(P1), int(P2), int(D), ft, point_reduction, abs_cosine,
         int(N), g_cham, g_feat, argmax, grad_x, grad_y);
   else
-    chamfer_bwd_kernel<1><<<static_cast<unsigned>(N), kChamferThreads, 0, st>>>(
+    chamfer_bwd_kernel<1><<<bgrid, kBwdThreads, 0, st>>>(
         x, y, idx, lengths1, lengths2, weights, int(P1), int(P2), int(D), ft, point_reduction, abs_cosine,
         int(N), g_cham, g_feat, argmax, grad_x, grad_y);
   POPS_LAUNCH_OK("chamfer_bwd_kernel");

@@ -46,7 +46,7 @@ def _handle_pointcloud_input(
     if lengths is not None:
         if lengths.ndim != 1 or lengths.shape[0] != points.shape[0]:
             raise ValueError("Expected lengths to be of shape (N,)")
-        if lengths.max() > points.shape[1]:
+        if _lengths_too_long(lengths, points.shape[1]):
             raise ValueError("A length value was too long")
     else:
         lengths = torch.full((points.shape[0],), points.shape[1], dtype=torch.int64,
@@ -58,6 +58,26 @@ def _handle_pointcloud_input(
     elif torch.is_tensor(features) and features.ndim != 3:
         raise ValueError("Expected features to be of shape (N, P, C)")
     return points, lengths, features
+
+
+# lengths tensors already checked against a padded size: the same tensor object at the same version
+# need not pay the device->host read again (the check itself is the reference's, :58-60)
+_LENGTHS_OK = {}
+
+
+def _lengths_too_long(lengths: torch.Tensor, P: int) -> bool:
+    key = id(lengths)
+    hit = _LENGTHS_OK.get(key)
+    if hit is not None and hit[0]() is lengths and hit[1] == lengths._version and hit[2] <= P:
+        return False
+    too_long = bool(lengths.max() > P)
+    if not too_long:
+        import weakref
+
+        if len(_LENGTHS_OK) > 256:
+            _LENGTHS_OK.clear()
+        _LENGTHS_OK[key] = (weakref.ref(lengths, lambda _r, k=key: _LENGTHS_OK.pop(k, None)), lengths._version, P)
+    return too_long
 
 
 class _ChamferDirection(torch.autograd.Function):
