@@ -240,3 +240,88 @@ def test_host_pipeline_matches_device_call():
     L1 = torch.full((N,), 500, device=DEV)
     ri, rd = _C.knn_points_idx(q.to(DEV), p.to(DEV), L1, L.to(DEV), 2, K, -1)
     assert torch.equal(i, ri.cpu()) and torch.equal(d, rd.cpu())
+
+
+@pytest.fixture
+def force_ordered():
+    """Route every D=3 L2 K<=32 call through the Morton-ordered, box-pruned search, whatever P2."""
+    from pytorch3d_pointops_b200 import _lib
+
+    lib = _lib.load()
+    lib.pops_set_option(b"knn_order", 1)
+    yield
+    lib.pops_set_option(b"knn_order", -1)
+
+
+def test_pruned_search_adversarial(oracle, golden, force_ordered):
+    """The pruned path on the inputs that stress it: exact ties on integer grids (bounds equal to
+    the K-th distance), duplicated points (degenerate boxes), offsets / scales (filter margins),
+    collinear clouds (flat boxes), K > lengths2, empty clouds, tiny clouds, p1 != p2."""
+    _C, _, _ = _ops()
+    g = golden("knn_cases")
+    p = g.t("grid.p", DEV)
+    L = torch.tensor([p.shape[1]], device=DEV)
+    for K in (1, 3, 7, 16, 17, 32):
+        idx, dists = _C.knn_points_idx(p, p, L, L, 2, K, -1)
+        assert torch.equal(idx.cpu(), g.t(f"grid.K{K}.idx")), K
+        assert torch.equal(dists.cpu(), g.t(f"grid.K{K}.dists")), K
+    gen = torch.Generator().manual_seed(78)
+    base = torch.rand(2, 2500, 3, generator=gen)
+    cases = {
+        "dups": base[:, torch.randint(0, 40, (2500,), generator=gen)],
+        "same": torch.full((2, 2500, 3), 0.5),
+        "offset1e3": base + 1000.0,
+        "offset1e5": base * 0.01 + 1e5,
+        "tiny": base * 1e-20,
+        "huge": base * 1e15,
+        "mixed": torch.cat([base[:, :1200] * 1e-3, base[:, 1200:] * 50 + 7], 1),
+        "line": torch.stack([base[..., 0], base[..., 0] * 0, base[..., 0] * 0], -1),
+        "clusters": (base * 0.01 + torch.randint(0, 3, (2, 2500, 1), generator=gen).float()),
+    }
+    for name, pts in cases.items():
+        pts = pts.contiguous()
+        Lc = torch.tensor([2500, 1301])
+        for K in (1, 16, 32):
+            oi, od = oracle.knn_points_idx(pts, pts, Lc, Lc, 2, K, threads=8)
+            gi, gd = _C.knn_points_idx(pts.to(DEV), pts.to(DEV), Lc.to(DEV), Lc.to(DEV), 2, K, -1)
+            assert torch.equal(gi.cpu(), oi), (name, K)
+            assert torch.equal(gd.cpu(), od), (name, K)
+    # p1 != p2, ragged both sides, K > lengths2, empty and one-point clouds
+    p1 = torch.randn(4, 700, 3, generator=gen)
+    p2 = torch.randn(4, 1500, 3, generator=gen) * 0.5 + 0.3
+    l1 = torch.tensor([700, 0, 13, 699])
+    l2 = torch.tensor([1500, 900, 5, 0])
+    for K in (1, 8, 16, 20):
+        oi, od = oracle.knn_points_idx(p1, p2, l1, l2, 2, K)
+        gi, gd = _C.knn_points_idx(p1.to(DEV), p2.to(DEV), l1.to(DEV), l2.to(DEV), 2, K, -1)
+        assert torch.equal(gi.cpu(), oi), K
+        assert torch.equal(gd.cpu(), od), K
+    one = torch.rand(1, 1, 3, generator=gen)
+    gi, gd = _C.knn_points_idx(one.to(DEV), one.to(DEV), torch.tensor([1], device=DEV), torch.tensor([1], device=DEV), 2, 4, -1)
+    oi, od = oracle.knn_points_idx(one, one, torch.tensor([1]), torch.tensor([1]), 2, 4)
+    assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od)
+
+
+def test_pruned_search_both_thread_shapes(oracle):
+    """Q = 2 and Q = 4 queries per thread, wide candidate ids (clouds beyond 262144 points use u32)."""
+    from pytorch3d_pointops_b200 import _lib
+
+    _C, _, _ = _ops()
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(5)
+    p = torch.rand(2, 5000, 3, generator=gen)
+    L = torch.tensor([5000, 3333])
+    oi, od = oracle.knn_points_idx(p, p, L, L, 2, 16, threads=8)
+    try:
+        for q in (2, 4):
+            lib.pops_set_option(b"knn_q", q)
+            gi, gd = _C.knn_points_idx(p.to(DEV), p.to(DEV), L.to(DEV), L.to(DEV), 2, 16, -1)
+            assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od), q
+    finally:
+        lib.pops_set_option(b"knn_q", 4)
+    big = torch.rand(1, 300000, 3, generator=gen)
+    q1 = big[:, :256].contiguous()
+    Lb, Lq = torch.tensor([300000]), torch.tensor([256])
+    oi, od = oracle.knn_points_idx(q1, big, Lq, Lb, 2, 8, threads=8)
+    gi, gd = _C.knn_points_idx(q1.to(DEV), big.to(DEV), Lq.to(DEV), Lb.to(DEV), 2, 8, -1)
+    assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od)
