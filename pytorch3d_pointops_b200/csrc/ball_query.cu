@@ -9,10 +9,15 @@
 // the tile in index order and stops once it holds K hits; the CTA leaves the tile loop as soon
 // as all of its queries are complete (__syncthreads_or), which is where the time goes for
 // dense clouds (sequential-scan semantics make the work data dependent).
-//   D == 3: tile is SoA (x[],y[],z[],w=|p|^2) and points are first screened 4 at a time with the
-//           expanded-form filter  s = w - 2 q.p  against  (r2 - |q|^2) + E  (same error bound as
-//           the KNN filter); only groups that pass are evaluated exactly.  The exact
-//           value alone decides membership.
+//   D == 3: ball_query_scan_kernel -- the structure of the KNN scan (knn.cu): every thread owns 4
+//           queries; the tile is SoA (x[],y[],z[],w=|p|^2) built on the fly; per group of 4 points
+//           and per query 6 FFMA2 evaluate the expanded form  s = w - 2 q.p  against
+//           (r2 - |q|^2) + E  (same error bound as the KNN filter) and a group that may
+//           hold a hit is appended, predicated, to the query's candidate buffer.  Buffers are
+//           drained in warp-converged flushes, in index order: exact unfused distance, strict
+//           d < r2, hits written straight to the outputs until the query holds K.  The exact value
+//           alone decides membership.  (ball_query_d3_kernel, thread per query with the recheck
+//           inside the loop, is kept for small inputs.)
 //   other D: exact distance on an AoS tile.
 #include <cfloat>
 
@@ -161,6 +166,174 @@ ball_query_d3_kernel(const BqParams prm) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// D == 3, buffered: 4 queries per thread, candidate groups flushed out of the dense loop
+// ---------------------------------------------------------------------------------------------
+constexpr int kBqsThreads = 128;
+constexpr int kBqsQ = 4;
+constexpr int kBqsTile = 1024;   // points per tile
+constexpr int kBqsCap = 16;      // candidate groups a query buffers between flushes
+constexpr int kBqsChunk = 4;     // groups between overflow checks
+
+// Drain one query's candidate buffer (group ids within the tile, in scan order = index order).
+// Not inlined; warp-converged call, divergent inside (rare).  Returns the new hit count.
+__device__ __noinline__ int bq_flush_one(const float* tile, const unsigned short* cand_col, int c_end, float qx,
+                                         float qy, float qz, float r2, int j0, int L2, int K, int count,
+                                         int64_t* oi, float* od) {
+  constexpr int QPB = kBqsQ * kBqsThreads;
+  for (int c = 0; c < c_end && count < K; ++c) {
+    const int g = cand_col[c * QPB];
+    const float4 X = reinterpret_cast<const float4*>(tile)[g];
+    const float4 Y = reinterpret_cast<const float4*>(tile + kBqsTile)[g];
+    const float4 Z = reinterpret_cast<const float4*>(tile + 2 * kBqsTile)[g];
+    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + g * 4 + i;
+      const float dx = __fsub_rn(qx, xs[i]), dy = __fsub_rn(qy, ys[i]), dz = __fsub_rn(qz, zs[i]);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d2 < r2 && j < L2 && count < K) {
+        oi[count] = j;
+        od[count] = d2;
+        ++count;
+      }
+    }
+  }
+  return count;
+}
+
+__global__ void __launch_bounds__(kBqsThreads, 3)
+ball_query_scan_kernel(const BqParams prm) {
+  constexpr int Q = kBqsQ, THREADS = kBqsThreads, QPB = Q * THREADS, RS = kBqsTile;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* tile = reinterpret_cast<float*>(smem);                                     // x,y,z,w rows of RS (+ pad)
+  unsigned short* cand = reinterpret_cast<unsigned short*>(smem + (4 * RS + 16) * 4);  // [kBqsCap][QPB]
+  __shared__ float s_maxabs;
+  const int n = blockIdx.y, tid = threadIdx.x, q_base = blockIdx.x * QPB;
+  const int K = prm.K;
+  int64_t L1l = prm.len1[n], L2l = prm.len2[n];
+  const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > prm.P1 ? prm.P1 : L1l));
+  const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
+  const float INF = __int_as_float(0x7f800000);
+  const float r2 = prm.radius2;
+
+  float q[Q][3], a[Q][3], qq[Q], qmax[Q], T[Q];
+  int count[Q];
+  uint32_t cw[Q];
+  bool valid[Q];
+  constexpr uint32_t CSTRIDE = QPB * 2;
+  const uint32_t cand_base = smem_u32(cand) + static_cast<uint32_t>(tid) * 2u;
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    const int qi = q_base + tid + t * THREADS;
+    valid[t] = qi < L1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      q[t][d] = valid[t] ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * 3 + d] : 0.0f;
+      a[t][d] = -2.0f * q[t][d];
+    }
+    qq[t] = fmaf(q[t][2], q[t][2], fmaf(q[t][1], q[t][1], q[t][0] * q[t][0]));
+    qmax[t] = fmaxf(fabsf(q[t][0]), fmaxf(fabsf(q[t][1]), fabsf(q[t][2])));
+    count[t] = 0;
+    T[t] = -INF;
+    cw[t] = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
+  }
+  const float* p2n = prm.p2 + static_cast<size_t>(n) * prm.P2 * 3;
+  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(kBqsCap - kBqsChunk) * CSTRIDE;
+
+  auto flush = [&](int t, int j0) {
+    const uint32_t base = cand_base + static_cast<uint32_t>(t) * (THREADS * 2u);
+    const int c_end = static_cast<int>((cw[t] - base) / CSTRIDE);
+    cw[t] = base;
+    if (!__any_sync(0xffffffffu, c_end > 0)) return;
+    const int qi = q_base + tid + t * THREADS;
+    const size_t row = static_cast<size_t>(n) * prm.P1 + (qi < prm.P1 ? qi : 0);
+    count[t] = bq_flush_one(tile, cand + tid + t * THREADS, c_end, q[t][0], q[t][1], q[t][2], r2, j0, L2, K,
+                            count[t], prm.idx + row * K, prm.dists + row * K);
+    if (count[t] >= K) T[t] = -INF;  // complete: never buffers again
+  };
+
+  for (int j0 = 0; j0 < L2; j0 += RS) {
+    const int pts = min(RS, L2 - j0);
+    const int ngroups = (pts + 4 * kBqsChunk - 1) / (4 * kBqsChunk) * kBqsChunk;  // whole chunks; padded with sentinels
+    bool active = false;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) active = active || (valid[t] && count[t] < K);
+    if (!__syncthreads_or(active ? 1 : 0)) break;  // every query of the CTA holds K hits
+    if (tid == 0) s_maxabs = 0.0f;
+    __syncthreads();
+    float m = 0.0f;
+    for (int jl = tid; jl < ngroups * 4; jl += THREADS) {  // (the scan's last prefetch reads one group past: in bounds, unused)
+      float x = 0.f, y = 0.f, z = 0.f, w = INF;
+      if (jl < pts) {
+        const float* p = p2n + static_cast<size_t>(j0 + jl) * 3;
+        x = p[0]; y = p[1]; z = p[2];
+        w = fmaf(z, z, fmaf(y, y, x * x));
+        m = fmaxf(m, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
+      }
+      tile[jl] = x; tile[RS + jl] = y; tile[2 * RS + jl] = z; tile[3 * RS + jl] = w;
+    }
+    m = warp_max(m);
+    if ((tid & 31) == 0) atomicMax(reinterpret_cast<int*>(&s_maxabs), __float_as_int(m));
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const float M = fmaxf(s_maxabs, qmax[t]);
+      const float E = fmaf(M * M, 1.52587890625e-05f, 1e-37f);
+      T[t] = (valid[t] && count[t] < K) ? __fadd_rn(__fsub_rn(r2, qq[t]), E) : -INF;
+    }
+    const float4* tp = reinterpret_cast<const float4*>(tile);
+    float4 Xc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Xc[r] = tp[r * (RS / 4)];
+    for (int g = 0; g < ngroups; g += kBqsChunk) {
+#pragma unroll
+      for (int c = 0; c < kBqsChunk; ++c) {
+        float4 Xn[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Xn[r] = tp[r * (RS / 4) + g + c + 1];
+        const unsigned short g16 = static_cast<unsigned short>(g + c);
+#pragma unroll
+        for (int t = 0; t < Q; ++t) {
+          float2 s01 = make_float2(Xc[3].x, Xc[3].y), s23 = make_float2(Xc[3].z, Xc[3].w);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const float2 ad = make_float2(a[t][d], a[t][d]);
+            s01 = __ffma2_rn(ad, make_float2(Xc[d].x, Xc[d].y), s01);
+            s23 = __ffma2_rn(ad, make_float2(Xc[d].z, Xc[d].w), s23);
+          }
+          const float mn = fminf(fminf(s01.x, s01.y), fminf(s23.x, s23.y));
+          if (mn <= T[t]) {  // predicated: one STS.U16 + one IADD
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(cw[t]), "h"(g16) : "memory");
+            cw[t] += CSTRIDE;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Xc[r] = Xn[r];
+      }
+      uint32_t mx = cw[0];
+#pragma unroll
+      for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (THREADS * 2u));
+      if (g + kBqsChunk >= ngroups || __any_sync(0xffffffffu, mx > cw_limit)) {
+#pragma unroll
+        for (int t = 0; t < Q; ++t) flush(t, j0);
+      }
+    }
+    __syncthreads();  // everyone is done with the tile
+  }
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    const int qi = q_base + tid + t * THREADS;
+    if (qi >= prm.P1) continue;
+    int64_t* oi = prm.idx + (static_cast<size_t>(n) * prm.P1 + qi) * K;
+    float* od = prm.dists + (static_cast<size_t>(n) * prm.P1 + qi) * K;
+    for (int k = count[t]; k < K; ++k) {
+      oi[k] = -1;
+      od[k] = 0.0f;
+    }
+  }
+}
+
 }  // namespace pops
 
 using namespace pops;
@@ -185,6 +358,17 @@ extern "C" int pops_ball_query(const float* p1, const float* p2, const int64_t* 
   prm.P1 = int(P1); prm.P2 = int(P2); prm.D = int(D); prm.K = int(K);
   prm.radius2 = radius * radius;  // f32 product, ball_query_cpu.cpp:26
   dim3 grid(static_cast<unsigned>(ceil_div(P1, kBqThreads)), static_cast<unsigned>(N));
+  if (D == 3 && P1 >= 1024 && get_option("bq_scan", 1)) {
+    prm.TP = kBqsTile;
+    const size_t smem = size_t(4 * kBqsTile + 16) * 4 + size_t(kBqsCap) * kBqsQ * kBqsThreads * 2;
+    POPS_CUDA_OK(cudaFuncSetAttribute(ball_query_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    dim3 sgrid(static_cast<unsigned>(ceil_div(P1, kBqsQ * kBqsThreads)), static_cast<unsigned>(N));
+    profile_begin("ball_query", st);
+    ball_query_scan_kernel<<<sgrid, kBqsThreads, smem, st>>>(prm);
+    profile_end("ball_query", st);
+    POPS_LAUNCH_OK("ball_query_scan_kernel");
+    return POPS_OK;
+  }
   if (D == 3) {
     prm.TP = 2048;
     const size_t smem = size_t(4) * prm.TP * 4;
