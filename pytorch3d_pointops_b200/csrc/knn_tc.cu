@@ -53,7 +53,7 @@ constexpr int TC_N = 128;        // points per tile = TMEM columns per accumulat
 constexpr int TC_KBLK = 32;      // floats per k-block: one 128-byte swizzle span
 constexpr int TC_ABUF = 4;       // accumulator buffers (4 x 128 = all 512 TMEM columns)
 constexpr int TC_LIST = 32;      // the re-rank keeps the 32 smallest s of a query (K <= 16)
-constexpr int TC_GCAP = 256;     // candidates a (query, column half) can hold in global memory
+constexpr int TC_GCAP = 128;     // candidates a (query, column half) can hold in global memory (≈55 used on C5)
 constexpr int TC_TOUR = 32;      // tournament minima per thread; threshold = their 16th smallest
 constexpr int TC_CAND = 24;      // candidate entries a thread stages in shared memory between flushes
 constexpr int TC_SUB = 8;        // columns between two staging-overflow checks
