@@ -41,10 +41,14 @@ struct KeyLayout {
   int end_bit;
 };
 
-inline KeyLayout key_layout(int64_t N, bool two_tensors) {
+// Morton resolution follows the cloud size: ~16 cells per point order the blocks of 64 points as
+// well as 2^30 cells would, and every 8 key bits less is one radix-sort pass less (each pass is a
+// latency-bound ~15 us launch on these small inputs).
+inline KeyLayout key_layout(int64_t N, int64_t P2, bool two_tensors) {
   KeyLayout k;
   const int cl = clog2(std::max<int64_t>(N, 1));
-  k.axis_bits = std::min(10, std::max(1, (30 - cl) / 3));
+  const int want = (clog2(std::max<int64_t>(P2, 1)) + 4 + 2) / 3;
+  k.axis_bits = std::min(std::min(10, std::max(1, (30 - cl) / 3)), std::max(4, want));
   k.code_bits = 3 * k.axis_bits;
   k.cloud_shift = k.code_bits + 1;
   k.tensor_shift = k.cloud_shift + cl;
@@ -301,7 +305,7 @@ size_t knn_order_workspace_bytes(int64_t N, int64_t P1, int64_t P2) {
 int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2,
                       int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st) {
   const int nbox = static_cast<int>(knn_order_num_boxes(P2));
-  const KeyLayout kl = key_layout(N, !self_knn);
+  const KeyLayout kl = key_layout(N, P2, !self_knn);
   bbox_maxabs_kernel<<<N, 1024, 0, st>>>(p1, p2, len1, len2, P1, P2, self_knn, b.bbox, b.maxabs_bits);
   POPS_LAUNCH_OK("bbox_maxabs_kernel");
   const int64_t items = static_cast<int64_t>(N) * P2 + (self_knn ? 0 : static_cast<int64_t>(N) * P1);
