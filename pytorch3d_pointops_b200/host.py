@@ -22,15 +22,26 @@ class HostKnn:
     out_idx (N,P1,K) int64 and out_dists (N,P1,K) float32 are pinned host tensors owned by this
     object and overwritten by every call."""
 
-    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices: int = 3, graph: bool = True):
+    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=3, graph: bool = True):
         self.device = torch.device(device)
         self.N, self.P1, self.P2, self.D, self.K = N, P1, P2, D, K
-        self.slices = max(1, min(slices, N))
+        # `slices`: a count (equal slices) or an explicit list of slice sizes in clouds.  Measured on
+        # the B=32 x P=16384 x K=16 shape: 3 equal slices 2.61 ms, uneven schedules with a short
+        # first slice 2.70-3.07 ms, a single slice 3.19 ms.
+        if isinstance(slices, (list, tuple)):
+            sizes = [int(v) for v in slices if int(v) > 0]
+            assert sum(sizes) == N, "slice sizes must add up to the batch"
+            bounds = [0]
+            for v in sizes:
+                bounds.append(bounds[-1] + v)
+            self.slices = len(sizes)
+        else:
+            self.slices = max(1, min(int(slices), N))
+            bounds = [round(i * N / self.slices) for i in range(self.slices + 1)]
         self.out_idx = torch.empty((N, P1, K), dtype=torch.int64).pin_memory()
         self.out_dists = torch.empty((N, P1, K), dtype=torch.float32).pin_memory()
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
-        bounds = [round(i * N / self.slices) for i in range(self.slices + 1)]
         self.ranges = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
         # The whole pipeline (copies on three streams + ~10 launches per slice) is captured into ONE
         # CUDA graph per set of host buffers and replayed: the slices are short enough that
