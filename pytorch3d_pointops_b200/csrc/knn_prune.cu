@@ -39,7 +39,8 @@ namespace {
 
 constexpr int kRingSlots = 4;   // blocks resident per warp
 constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
-constexpr int kPruneBufCap = 24; // candidate groups a query can buffer between flushes
+// candidate groups a query can buffer between flushes (a query meets ~K/4 + Morton scatter groups in total)
+constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : 24; }
 constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
 constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
 constexpr uint32_t kBlockBytes = kBlockFloats * 4;
@@ -63,7 +64,7 @@ struct KnnPruneParams {
 __device__ unsigned long long g_knn_stats[8];
 
 // CID: candidate id type -- unsigned short while the cloud has at most 65536 groups (262144 points)
-template <int Q, int THREADS, typename CID>
+template <int Q, int THREADS, typename CID, int KT>
 struct PruneSmem {
   static constexpr int WARPS = THREADS / 32;
   static constexpr int QPB = Q * THREADS;
@@ -71,7 +72,7 @@ struct PruneSmem {
   static constexpr size_t ring_off = 256;
   static constexpr size_t ring_bytes = size_t(WARPS) * kRingSlots * kBlockBytes;
   static constexpr size_t cand_off = ring_off + ring_bytes;
-  static constexpr size_t cand_bytes = size_t(kPruneBufCap) * QPB * sizeof(CID);  // global group ids
+  static constexpr size_t cand_bytes = size_t(prune_buf_cap(KT)) * QPB * sizeof(CID);  // global group ids
   static constexpr size_t surv_off = (cand_off + cand_bytes + 15) / 16 * 16;
   static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
   static constexpr size_t cold_off = surv_off + surv_bytes;
@@ -225,7 +226,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   constexpr int QPB = Q * THREADS, S = kRingSlots;
   constexpr int NSEED = KT <= 4 ? 1 : (KT <= 16 ? 2 : 4);  // >= 4 seed points per tournament subset
   static_assert(NSEED <= S, "the seed blocks sit in the ring together");
-  using SM = PruneSmem<Q, THREADS, CID>;
+  using SM = PruneSmem<Q, THREADS, CID, KT>;
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr unsigned FULL = 0xffffffffu;
 
@@ -408,7 +409,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   };
 
   // ---- flush glue ------------------------------------------------------------------------------------
-  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(kPruneBufCap - kChunk) * CBYTES;
+  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(prune_buf_cap(KT) - kChunk) * CBYTES;
   // only_full: drain just the query slots in which some lane's buffer is nearly full
   auto flush_all = [&](bool only_full) {
     if (prm.stats && lane == 0) atomicAdd(prm.stats + 2, 1ull);
@@ -537,7 +538,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
 
 template <int Q, int KT, int THREADS, typename CID>
 int launch_prune(const KnnPruneParams& prm, int N, cudaStream_t st) {
-  using SM = PruneSmem<Q, THREADS, CID>;
+  using SM = PruneSmem<Q, THREADS, CID, KT>;
   auto kern = knn_prune_kernel<Q, KT, THREADS, CID>;
   POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM::total)));
   dim3 grid(static_cast<unsigned>(ceil_div(prm.P1, SM::QPB)), N);
