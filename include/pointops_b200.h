@@ -173,6 +173,17 @@ int pops_gather_backward(const float* grad_out, const int64_t* idx, const int64_
                          float* grad_x, pops_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused neighbourhood covariances (additive).  Replaces the torch sequence of get_point_covariances
+ * (functions/utils.py:111-153) after the KNN search: gather, mean over the K slots, centring, outer
+ * products, mean.  x (N,M,D) f32 with 1 <= D <= 4, idx (N,P,K) i64 from pops_knn_points_idx,
+ * lengths (N) i64 or NULL (slots k >= lengths[n] gather zeros, as knn_gather does)
+ * -> nn (N,P,K,D), cov (N,P,D,D).
+ * ------------------------------------------------------------------------------------------- */
+int pops_point_covariances(const float* x, const int64_t* idx, const int64_t* lengths, int64_t N,
+                           int64_t P, int64_t M, int64_t D, int64_t K, float* nn, float* cov,
+                           pops_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused chamfer post-processing (additive).  Replaces the ~20 torch kernels per direction that
  * functions/chamfer.py:114-189 runs after the K=1 search (mask, weights, knn_gather,
  * cosine_similarity, abs, 1-x, point reduction) and their autograd mirror images.

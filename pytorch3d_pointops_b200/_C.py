@@ -360,3 +360,24 @@ def sample_pdf(bins, weights, outputs, eps):
     _lib.check(st, "sample_pdf")
     torch.autograd.graph.increment_version(outputs)
     return None
+
+
+def point_covariances(x, idx, lengths):
+    """Additive: neighbourhood gather + covariance in one kernel (functions/utils.py:111-153).
+    x (N,M,D<=4) f32, idx (N,P,K) i64, lengths (N) i64 or None -> (cov (N,P,D,D), nn (N,P,K,D))."""
+    lib = _lib.load()
+    x = _cuda_f32(x, "points")
+    idx = _cuda_i64(idx, "idx", x)
+    if lengths is not None:
+        lengths = _cuda_i64(lengths, "lengths", x)
+    N, M, D = x.shape
+    _, P, K = idx.shape
+    nn = torch.empty((N, P, K, D), dtype=torch.float32, device=x.device)
+    cov = torch.empty((N, P, D, D), dtype=torch.float32, device=x.device)
+    if nn.numel() == 0:
+        return cov, nn
+    with torch.cuda.device(x.device):
+        st = lib.pops_point_covariances(x.data_ptr(), idx.data_ptr(), _ptr(lengths), N, P, M, D, K,
+                                        nn.data_ptr(), cov.data_ptr(), _stream(x))
+    _lib.check(st, "point_covariances")
+    return cov, nn

@@ -37,6 +37,7 @@ SIGNATURES = {
     "pops_packed_to_padded": (c_int, [_P, _P] + [c_int64] * 4 + [_P, _P]),
     "pops_padded_to_packed": (c_int, [_P, _P] + [c_int64] * 4 + [_P, _P]),
     "pops_sample_pdf": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P]),
+    "pops_point_covariances": (c_int, [_P, _P, _P] + [c_int64] * 5 + [_P, _P, _P]),
     "pops_gather": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P, _P]),
     "pops_gather_backward": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P]),
     "pops_chamfer_forward": (c_int, [_P] * 5 + [c_int64] * 3 + [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),

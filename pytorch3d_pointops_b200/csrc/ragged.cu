@@ -112,6 +112,60 @@ __global__ void gather_backward_kernel(const float* __restrict__ grad_out,
   }
 }
 
+// Fused neighbourhood covariance (functions/utils.py:111-153 of the reference): per query row the K
+// gathered neighbours nn[k] = x[n, idx[k]] (zero where k >= lengths[n], as knn_gather does), their
+// mean over ALL K slots, and cov = mean_k (nn[k] - mean)(nn[k] - mean)^T.  One thread per query row
+// writes nn (N,P,K,DT) and cov (N,P,DT,DT); the reference materialises (N,P,K,D) centred values and
+// (N,P,K,D,D) outer products in between.
+template <int DT>
+__global__ void point_cov_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
+                                 const int64_t* __restrict__ lengths, int P, int M, int K,
+                                 float* __restrict__ nn, float* __restrict__ cov) {
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const size_t row = static_cast<size_t>(n) * P + p;
+  const int64_t len = lengths ? lengths[n] : K;
+  const float* xn = x + static_cast<size_t>(n) * M * DT;
+  const int64_t* ir = idx + row * K;
+  float* nr = nn + row * K * DT;
+  float mean[DT];
+#pragma unroll
+  for (int d = 0; d < DT; ++d) mean[d] = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    const int64_t j = ir[k];
+    const bool take = k < len && j >= 0 && j < M;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      const float v = take ? xn[j * DT + d] : 0.0f;
+      nr[k * DT + d] = v;
+      mean[d] += v;
+    }
+  }
+  const float invK = 1.0f / static_cast<float>(K);
+#pragma unroll
+  for (int d = 0; d < DT; ++d) mean[d] *= invK;
+  float c[DT][DT];
+#pragma unroll
+  for (int a = 0; a < DT; ++a)
+#pragma unroll
+    for (int b = 0; b < DT; ++b) c[a][b] = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    float v[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] = nr[k * DT + d] - mean[d];  // re-read of what this thread just wrote
+#pragma unroll
+    for (int a = 0; a < DT; ++a)
+#pragma unroll
+      for (int b = 0; b < DT; ++b) c[a][b] += v[a] * v[b];
+  }
+  float* cr = cov + row * DT * DT;
+#pragma unroll
+  for (int a = 0; a < DT; ++a)
+#pragma unroll
+    for (int b = 0; b < DT; ++b) cr[a * DT + b] = c[a][b] * invK;
+}
+
 inline int flat_grid(int64_t total, int threads) {
   return int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, threads), int64_t(num_sms()) * 32)));
 }
@@ -198,5 +252,25 @@ extern "C" int pops_gather_backward(const float* grad_out, const int64_t* idx,
   else
     gather_backward_kernel<POPS_GATHER_MASKED><<<grid, 256, 0, st>>>(grad_out, idx, lengths, L * K, int(K), int(M), int(U), rows, grad_x);
   POPS_LAUNCH_OK("gather_backward_kernel");
+  return POPS_OK;
+}
+
+extern "C" int pops_point_covariances(const float* x, const int64_t* idx, const int64_t* lengths, int64_t N,
+                                      int64_t P, int64_t M, int64_t D, int64_t K, float* nn, float* cov,
+                                      pops_stream_t stream) {
+  POPS_CHECK_ARG(N >= 0 && P >= 0 && M >= 0 && K >= 1, "bad sizes");
+  if (D < 1 || D > 4) return fail(POPS_ERR_UNSUPPORTED, "point_covariances: fused path covers 1 <= D <= 4");
+  if (N == 0 || P == 0) return POPS_OK;
+  POPS_CHECK_ARG(x && idx && nn && cov, "null pointer argument");
+  POPS_CHECK_ARG(N < 65536 && P < (int64_t(1) << 31) && M < (int64_t(1) << 31), "size too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>(ceil_div(P, 128)), static_cast<unsigned>(N));
+  switch (D) {
+    case 1: point_cov_kernel<1><<<grid, 128, 0, st>>>(x, idx, lengths, int(P), int(M), int(K), nn, cov); break;
+    case 2: point_cov_kernel<2><<<grid, 128, 0, st>>>(x, idx, lengths, int(P), int(M), int(K), nn, cov); break;
+    case 3: point_cov_kernel<3><<<grid, 128, 0, st>>>(x, idx, lengths, int(P), int(M), int(K), nn, cov); break;
+    default: point_cov_kernel<4><<<grid, 128, 0, st>>>(x, idx, lengths, int(P), int(M), int(K), nn, cov); break;
+  }
+  POPS_LAUNCH_OK("point_cov_kernel");
   return POPS_OK;
 }

@@ -49,6 +49,13 @@ def get_point_covariances(
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per-point covariance of the K nearest neighbours (reference: functions/utils.py:111-153).
     Returns (covariances (N,P,D,D), k_nearest_neighbors (N,P,K,D))."""
+    D = points_padded.shape[-1]
+    if 1 <= D <= 4 and not (torch.is_grad_enabled() and points_padded.requires_grad):
+        # no gradient wanted: search, then ONE kernel gathers the neighbourhoods and reduces them to
+        # covariances (no (N,P,K,D,D) outer-product temporary)
+        res = knn_points(points_padded, points_padded, lengths1=num_points_per_cloud,
+                         lengths2=num_points_per_cloud, K=neighborhood_size, return_nn=False)
+        return _C.point_covariances(points_padded.float(), res.idx, num_points_per_cloud)
     nn = knn_points(
         points_padded,
         points_padded,

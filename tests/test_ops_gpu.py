@@ -232,3 +232,25 @@ def test_sample_pdf_golden_and_oracle(golden, oracle):
         sample_pdf(bins.to(DEV).requires_grad_(True), w.to(DEV), 4)
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         _C.sample_pdf(bins, w, u.clone(), 1e-5)
+
+
+def test_point_covariances_fused_matches_torch_formula():
+    """get_point_covariances: the fused kernel (no grad) against the reference's torch formula
+    (functions/utils.py:111-153) evaluated on our knn_points(return_nn=True)."""
+    from pytorch3d_pointops_b200.functions import get_point_covariances, knn_points
+
+    gen = torch.Generator().manual_seed(6)
+    for D, K in ((3, 16), (2, 5), (4, 9)):
+        pts = torch.randn(3, 700, D, generator=gen).to(DEV)
+        L = torch.tensor([700, 433, 6], device=DEV)  # the last cloud has fewer points than K=9/16
+        cov, nn = get_point_covariances(pts, L, K)
+        ref_nn = knn_points(pts, pts, lengths1=L, lengths2=L, K=K, return_nn=True).knn
+        centred = ref_nn - ref_nn.mean(2, keepdim=True)
+        ref_cov = (centred.unsqueeze(4) * centred.unsqueeze(3)).mean(2)
+        assert torch.equal(nn, ref_nn)
+        assert torch.allclose(cov, ref_cov, rtol=1e-5, atol=1e-6)
+        # with gradients the torch path is taken and stays differentiable
+        pg = pts.clone().requires_grad_(True)
+        cov_g, _ = get_point_covariances(pg, L, K)
+        cov_g.sum().backward()
+        assert torch.allclose(cov_g.detach(), cov, rtol=1e-5, atol=1e-6) and pg.grad is not None
