@@ -224,7 +224,7 @@ template <int Q, int KT, int THREADS, typename CID>
 __global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : 8)))
 knn_prune_kernel(const KnnPruneParams prm) {
   constexpr int QPB = Q * THREADS, S = kRingSlots;
-  constexpr int NSEED = KT <= 4 ? 1 : (KT <= 16 ? 2 : 4);  // >= 4 seed points per tournament subset
+  constexpr int NSEED = KT <= 4 ? 3 : (KT <= 16 ? 2 : 4);  // >= 4 seed points per tournament subset; small K: home +- 1 keeps the worst bound of the warp down
   static_assert(NSEED <= S, "the seed blocks sit in the ring together");
   using SM = PruneSmem<Q, THREADS, CID, KT>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -390,6 +390,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   const float* blocks_n = prm.blocks + static_cast<size_t>(n) * prm.nbox * kBlockFloats;
   float slot_lb = 0.0f;  // lane s: bound of the block in slot s
   int slot_blk = 0;      // lane s: index of the block in slot s
+  float4 slot_lo = make_float4(0.f, 0.f, 0.f, 0.f), slot_hi = slot_lo;  // lane s: its bounding box
   int head = 0, tail = 0;  // blocks issued / scanned
   auto issue = [&](int b) {
     const int s = head & (S - 1);
@@ -403,6 +404,10 @@ knn_prune_kernel(const KnnPruneParams prm) {
     if (lane == s) {
       slot_lb = picked_lb;
       slot_blk = b;
+      if (KT <= 4) {
+        slot_lo = boxes_n[static_cast<size_t>(b) * 2];  // consumed when the block is scanned: latency hidden
+        slot_hi = boxes_n[static_cast<size_t>(b) * 2 + 1];
+      }
     }
     ++head;
     if (prm.stats && lane == 0) atomicAdd(prm.stats + 0, 1ull);
@@ -473,7 +478,25 @@ knn_prune_kernel(const KnnPruneParams prm) {
     if (tail == head) break;
     const int s = tail & (S - 1);
     mbar_wait(&bars[s], (tail / S) & 1);
-    if (__shfl_sync(FULL, slot_lb, s) <= dkmax) {  // dkmax may have dropped since the fetch
+    bool wanted = __shfl_sync(FULL, slot_lb, s) <= dkmax;  // dkmax may have dropped since the fetch
+    // (small K only: the 6 extra registers per lane cost the K = 16 / 32 variants, which sit at their
+    //  register cap, more in spills than the 25 % fewer blocks give back: 1.28 vs 1.21 ms on the T shape)
+    if (KT <= 4 && wanted && prm.prune) {
+      // per-query refinement: the warp-wide test used the box of ALL its queries against the LARGEST
+      // bound; scan only if some query's own bound reaches the block (same exact lower bound, with
+      // the query as a degenerate box)
+      float4 lo, hi;
+      lo.x = __shfl_sync(FULL, slot_lo.x, s); lo.y = __shfl_sync(FULL, slot_lo.y, s); lo.z = __shfl_sync(FULL, slot_lo.z, s);
+      hi.x = __shfl_sync(FULL, slot_hi.x, s); hi.y = __shfl_sync(FULL, slot_hi.y, s); hi.z = __shfl_sync(FULL, slot_hi.z, s);
+      bool need = false;
+#pragma unroll
+      for (int t = 0; t < Q; ++t) {
+        const float qp[3] = {-0.5f * a[t][0], -0.5f * a[t][1], -0.5f * a[t][2]};
+        need = need || (box_lower_bound(lo, hi, qp, qp) <= cold_dk[slot0 + t * 32]);  // dk = -1 beyond lengths1
+      }
+      wanted = __any_sync(FULL, need);
+    }
+    if (wanted) {
       if (prm.stats && lane == 0) atomicAdd(prm.stats + 1, 1ull);
       const float4* tp = ring4 + s * kBlockF4;
       const unsigned gid0 = static_cast<unsigned>(__shfl_sync(FULL, slot_blk, s)) * kBlockGroups;
