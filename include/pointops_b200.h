@@ -90,6 +90,24 @@ int pops_knn_points_idx(const float* p1, const float* p2, const int64_t* lengths
                         int64_t K, int norm, int version, int64_t* idx, float* dists,
                         void* workspace, size_t workspace_bytes, pops_stream_t stream);
 
+/* The same search in two phases, for host pipelines that want the result slice by slice (the outer
+ * `for n` of knn_cpu.cpp:35 is independent per cloud; host.py: HostKnn overlaps the device-to-host
+ * copy of one slice with the search of the next).  Additive: the reference has no counterpart.
+ *   pops_knn_points_prepare     everything that precedes the search, once for ALL N clouds (the
+ *                               spatial pre-pass of the D = 3 path; nothing for the other paths)
+ *   pops_knn_points_idx_range   the rows of clouds [n0, n1) of idx / dists, which are the FULL
+ *                               (N,P1,K) arrays; all other arguments as passed to prepare
+ * Same stream (or ordered after prepare), same workspace of pops_knn_workspace_bytes(N, ...). */
+int pops_knn_points_prepare(const float* p1, const float* p2, const int64_t* lengths1,
+                            const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2, int64_t D,
+                            int64_t K, int norm, void* workspace, size_t workspace_bytes,
+                            pops_stream_t stream);
+int pops_knn_points_idx_range(const float* p1, const float* p2, const int64_t* lengths1,
+                              const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2, int64_t D,
+                              int64_t K, int norm, int version, int64_t n0, int64_t n1, int64_t* idx,
+                              float* dists, void* workspace, size_t workspace_bytes,
+                              pops_stream_t stream);
+
 /* _C.knn_check_version (ext.cpp:19; knn.cu:292-303): which (D,K) the reference's kernel
  * variant `version` accepts.  Kept so callers probing it keep working; returns 0/1. */
 int pops_knn_check_version(int version, int64_t D, int64_t K);

@@ -89,6 +89,47 @@ def knn_points_idx(p1, p2, lengths1, lengths2, norm, K, version):
     return idx, dists
 
 
+class KnnSliced:
+    """pops_knn_points_prepare + pops_knn_points_idx_range (additive, pointops_b200.h): one pre-pass
+    for the whole batch, then the rows of a range of clouds per call.  Owns idx / dists / workspace."""
+
+    def __init__(self, p1, p2, lengths1, lengths2, norm, K):
+        self.lib = _lib.load()
+        self.p1 = _cuda_f32(p1, "p1")
+        self.p2 = _cuda_f32(p2, "p2")
+        _same_device(self.p1, self.p2, "p1 and p2")
+        if norm not in (1, 2):
+            raise RuntimeError("Norm must be 1 or 2.")
+        self.l1 = _cuda_i64(lengths1, "lengths1", self.p1)
+        self.l2 = _cuda_i64(lengths2, "lengths2", self.p1)
+        self.N, self.P1, self.D = self.p1.shape
+        self.P2 = self.p2.shape[1]
+        self.K, self.norm = int(K), int(norm)
+        dev = self.p1.device
+        self.idx = torch.empty((self.N, self.P1, self.K), dtype=torch.int64, device=dev)
+        self.dists = torch.empty((self.N, self.P1, self.K), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            self.ws = _ws(self.lib.pops_knn_workspace_bytes(self.N, self.P1, self.P2, self.D, self.K, self.norm), dev)
+
+    def _args(self):
+        return (self.p1.data_ptr(), self.p2.data_ptr(), self.l1.data_ptr(), self.l2.data_ptr(), self.N, self.P1,
+                self.P2, self.D, self.K, self.norm)
+
+    def prepare(self):
+        with torch.cuda.device(self.p1.device):
+            st = self.lib.pops_knn_points_prepare(*self._args(), self.ws.data_ptr(), self.ws.numel(), _stream(self.p1))
+        _lib.check(st, "knn_points_prepare")
+
+    def search(self, n0, n1):
+        if self.idx.numel() == 0:
+            return
+        with torch.cuda.device(self.p1.device):
+            st = self.lib.pops_knn_points_idx_range(*self._args(), -1, int(n0), int(n1), self.idx.data_ptr(),
+                                                    self.dists.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                                    _stream(self.p1))
+        _lib.check(st, "knn_points_idx_range")
+
+
 def knn_check_version(version, D, K):
     """knn.h:161 / knn.cu:292-303."""
     return bool(_lib.load().pops_knn_check_version(int(version), int(D), int(K)))

@@ -28,6 +28,9 @@ SIGNATURES = {
     "pops_fp32_peak_probe": (ctypes.c_double, [c_int, _P]),
     "pops_knn_workspace_bytes": (c_size_t, [c_int64] * 5 + [c_int]),
     "pops_knn_points_idx": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "pops_knn_points_prepare": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int, _P, c_size_t, _P]),
+    "pops_knn_points_idx_range": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int, c_int] + [c_int64] * 2
+                                  + [_P, _P, _P, c_size_t, _P]),
     "pops_knn_check_version": (c_int, [c_int, c_int64, c_int64]),
     "pops_knn_points_backward": (c_int, [_P] * 6 + [c_int64] * 5 + [c_int, _P, _P, _P]),
     "pops_ball_query_workspace_bytes": (c_size_t, [c_int64] * 5),

@@ -681,6 +681,66 @@ extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64
   return POPS_OK;
 }
 
+// ---- two-phase form for host pipelines (host.py: HostKnn) ---------------------------------------
+// The batch is independent per cloud, but the ordered search is preceded by a pre-pass whose ~10
+// small launches cost the same for 8 clouds as for 32.  A pipeline that wants results slice by slice
+// (so that their device-to-host copies overlap the search of the next slice) runs the pre-pass once
+// for the whole batch and then searches ranges of clouds.
+namespace {
+inline bool ordered_path(int64_t P2, int64_t D, int64_t K, int norm) {
+  return D == 3 && norm == 2 && tiled_k_ok(int(K)) && use_ordered(P2, int(K));
+}
+}  // namespace
+
+extern "C" int pops_knn_points_prepare(const float* p1, const float* p2, const int64_t* lengths1,
+                                       const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2,
+                                       int64_t D, int64_t K, int norm, void* workspace,
+                                       size_t workspace_bytes, pops_stream_t stream) {
+  POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
+  POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0 && K >= 0, "negative size");
+  if (N == 0 || P1 == 0 || K == 0 || P2 == 0 || D == 0) return POPS_OK;
+  POPS_CHECK_ARG(p1 && p2 && lengths1 && lengths2, "null pointer argument");
+  POPS_CHECK_ARG(P2 < (int64_t(1) << 31) && P1 < (int64_t(1) << 31) && N < 65536, "size too large");
+  if (workspace_bytes < pops_knn_workspace_bytes(N, P1, P2, D, K, norm) || !workspace)
+    return fail(POPS_ERR_WORKSPACE, "knn: workspace missing or too small");
+  if (!ordered_path(P2, D, K, norm)) return POPS_OK;  // nothing to share between ranges
+  KnnOrderBuffers ob;
+  knn_order_carve(workspace, N, P1, P2, &ob);
+  const bool self_knn = (p1 == p2) && (lengths1 == lengths2) && (P1 == P2);
+  return knn_order_prepass(p1, p2, lengths1, lengths2, int(N), int(P1), int(P2), self_knn, ob,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pops_knn_points_idx_range(const float* p1, const float* p2, const int64_t* lengths1,
+                                         const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2,
+                                         int64_t D, int64_t K, int norm, int version, int64_t n0,
+                                         int64_t n1, int64_t* idx, float* dists, void* workspace,
+                                         size_t workspace_bytes, pops_stream_t stream) {
+  POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
+  POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0 && K >= 0, "negative size");
+  POPS_CHECK_ARG(0 <= n0 && n0 <= n1 && n1 <= N, "cloud range outside the batch");
+  if (n0 == n1 || P1 == 0 || K == 0) return POPS_OK;
+  POPS_CHECK_ARG(p1 && p2 && lengths1 && lengths2 && idx && dists, "null pointer argument");
+  if (workspace_bytes < pops_knn_workspace_bytes(N, P1, P2, D, K, norm) || !workspace)
+    return fail(POPS_ERR_WORKSPACE, "knn: workspace missing or too small");
+  int64_t* idx_r = idx + size_t(n0) * P1 * K;
+  float* dists_r = dists + size_t(n0) * P1 * K;
+  if (P2 == 0 || D == 0 || !ordered_path(P2, D, K, norm))  // no shared pre-pass: the range is a batch of its own
+    return pops_knn_points_idx(p1 + size_t(n0) * P1 * D, p2 + size_t(n0) * P2 * D, lengths1 + n0, lengths2 + n0,
+                               n1 - n0, P1, P2, D, K, norm, version, idx_r, dists_r, workspace, workspace_bytes,
+                               stream);
+  KnnOrderBuffers ob;
+  knn_order_carve(workspace, N, P1, P2, &ob);
+  const size_t nbox = size_t(knn_order_num_boxes(P2));
+  ob.maxabs_bits += n0;
+  ob.blocks += size_t(n0) * nbox * kBlockFloats;
+  ob.boxes += size_t(n0) * nbox * 2;
+  ob.qsorted += size_t(n0) * P1;
+  ob.qhome += size_t(n0) * P1;
+  return knn_prune_search(ob, lengths1 + n0, lengths2 + n0, int(n1 - n0), int(P1), int(P2), int(K), idx_r, dists_r,
+                          static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const int64_t* lengths1,
                                         const int64_t* lengths2, const int64_t* idx,
                                         const float* grad_dists, int64_t N, int64_t P1, int64_t P2,

@@ -3,9 +3,10 @@
 `knn_points` (functions/knn.py, the reference's API) takes device tensors.  When the clouds live
 in host memory and the (idx, dists) result is wanted back on the host -- 100 MB for the
 B=32 x P=16384 x K=16 shape, most of the end-to-end time -- the batch is independent per cloud
-(outer `for n` of knn_cpu.cpp:35), so the three legs pipeline: while slice i is searched, slice
-i+1 is on its way in and the results of slice i-1 are on their way out.  Copies run on two side
-streams, the kernels on the caller's current stream; buffers are pinned once and reused.
+(outer `for n` of knn_cpu.cpp:35), so the legs pipeline: the clouds go in with one copy (6 MB), the
+spatial pre-pass runs once for the whole batch, and while slice i is searched the results of slice
+i-1 are on their way out.  Copies run on two side streams, the kernels on the caller's current
+stream; buffers are pinned once and reused.
 """
 from __future__ import annotations
 
@@ -22,12 +23,14 @@ class HostKnn:
     out_idx (N,P1,K) int64 and out_dists (N,P1,K) float32 are pinned host tensors owned by this
     object and overwritten by every call."""
 
-    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=3, graph: bool = True):
+    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=4, graph: bool = True):
         self.device = torch.device(device)
         self.N, self.P1, self.P2, self.D, self.K = N, P1, P2, D, K
         # `slices`: a count (equal slices) or an explicit list of slice sizes in clouds.  Measured on
-        # the B=32 x P=16384 x K=16 shape: 3 equal slices 2.61 ms, uneven schedules with a short
-        # first slice 2.70-3.07 ms, a single slice 3.19 ms.
+        # the B=32 x P=16384 x K=16 shape (D2H of the 100 MB result alone: 1.77 ms): 1 slice 3.19 ms,
+        # 2: 2.71, 3: 2.55, 4: 2.50, 6: 2.93, 8: 3.18 -- a slice below one wave of CTAs (~10 clouds)
+        # still costs one CTA's latency (~0.45 ms), so more slices stretch the search; searching the
+        # slices on 2-3 alternating streams evens that out but ends at the same 2.46-2.56 ms.
         if isinstance(slices, (list, tuple)):
             sizes = [int(v) for v in slices if int(v) > 0]
             assert sum(sizes) == N, "slice sizes must add up to the batch"
@@ -43,7 +46,7 @@ class HostKnn:
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
         self.ranges = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
-        # The whole pipeline (copies on three streams + ~10 launches per slice) is captured into ONE
+        # The whole pipeline (copies on two side streams, the pre-pass, one search per slice) is captured into ONE
         # CUDA graph per set of host buffers and replayed: the slices are short enough that
         # launching them from Python would leave the GPU idle between them.
         self.use_graph = graph
@@ -87,33 +90,33 @@ class HostKnn:
         dev = self.device
         main = torch.cuda.current_stream(dev)
         self_knn = p2 is None
-        keep = []
-        staged = []
         with torch.cuda.stream(self.h2d):
             self.h2d.wait_stream(main)
-            for a, b in self.ranges:
-                d1 = p1[a:b].to(dev, non_blocking=True)
-                d2 = d1 if self_knn else p2[a:b].to(dev, non_blocking=True)
-                l1 = lengths1[a:b].to(dev, non_blocking=True)
-                l2 = l1 if self_knn and lengths2 is lengths1 else lengths2[a:b].to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.h2d)
-                staged.append((d1, d2, l1, l2, ev))
-        for (a, b), (d1, d2, l1, l2, ev) in zip(self.ranges, staged):
-            main.wait_event(ev)
-            if not recording:
-                for t in (d1, d2, l1, l2):
-                    t.record_stream(main)
-            idx, dists = _C.knn_points_idx(d1, d2, l1, l2, norm, self.K, -1)
+            d1 = p1.to(dev, non_blocking=True)
+            d2 = d1 if self_knn else p2.to(dev, non_blocking=True)
+            l1 = lengths1.to(dev, non_blocking=True)
+            l2 = l1 if self_knn and lengths2 is lengths1 else lengths2.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.h2d)
+        main.wait_event(ev)
+        if not recording:
+            for t in (d1, d2, l1, l2):
+                t.record_stream(main)
+        # one pre-pass for the whole batch, then the search slice by slice (pointops_b200.h:
+        # pops_knn_points_prepare / pops_knn_points_idx_range)
+        ks = _C.KnnSliced(d1, d2, l1, l2, norm, self.K)
+        ks.prepare()
+        for a, b in self.ranges:
+            ks.search(a, b)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(done)
-                if not recording:
-                    idx.record_stream(self.d2h)
-                    dists.record_stream(self.d2h)
-                self.out_idx[a:b].copy_(idx, non_blocking=True)
-                self.out_dists[a:b].copy_(dists, non_blocking=True)
-            keep.append((d1, d2, l1, l2, idx, dists))
+                self.out_idx[a:b].copy_(ks.idx[a:b], non_blocking=True)
+                self.out_dists[a:b].copy_(ks.dists[a:b], non_blocking=True)
+        if not recording:
+            for t in (ks.idx, ks.dists, ks.ws):
+                t.record_stream(self.d2h)
+        keep = [d1, d2, l1, l2, ks]
         main.wait_stream(self.d2h)
         return keep

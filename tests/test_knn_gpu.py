@@ -219,7 +219,8 @@ def test_no_cuda_errors_and_streams():
 
 
 def test_host_pipeline_matches_device_call():
-    """host.HostKnn (sliced, three streams) returns exactly what one knn_points_idx call returns."""
+    """host.HostKnn (one pre-pass, sliced search, copies on side streams) returns exactly what one
+    knn_points_idx call returns."""
     from pytorch3d_pointops_b200.host import HostKnn
 
     _C, _, _ = _ops()
@@ -240,6 +241,42 @@ def test_host_pipeline_matches_device_call():
     L1 = torch.full((N,), 500, device=DEV)
     ri, rd = _C.knn_points_idx(q.to(DEV), p.to(DEV), L1, L.to(DEV), 2, K, -1)
     assert torch.equal(i, ri.cpu()) and torch.equal(d, rd.cpu())
+
+
+def test_two_phase_range_api_matches_single_call():
+    """pops_knn_points_prepare + pops_knn_points_idx_range, any partition of the batch, equals one
+    pops_knn_points_idx call -- on the path with a shared pre-pass (D=3, L2, large P2) and on the
+    paths where a range is simply a batch of its own (D=5; L1; tiny P2)."""
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(21)
+    for (N, P1, P2, D, K, norm) in [(9, 700, 2500, 3, 8, 2), (5, 300, 400, 5, 6, 2), (4, 300, 1500, 3, 5, 1),
+                                    (6, 100, 50, 3, 3, 2), (3, 1100, 1100, 3, 40, 2)]:
+        p1 = torch.rand(N, P1, D, generator=gen).to(DEV)
+        p2 = torch.rand(N, P2, D, generator=gen).to(DEV)
+        l1 = torch.randint(0, P1 + 1, (N,), generator=gen).to(DEV)
+        l2 = torch.randint(0, P2 + 1, (N,), generator=gen).to(DEV)
+        ri, rd = _C.knn_points_idx(p1, p2, l1, l2, norm, K, -1)
+        ks = _C.KnnSliced(p1, p2, l1, l2, norm, K)
+        ks.idx.fill_(-7)
+        ks.dists.fill_(-7.0)
+        ks.prepare()
+        cuts = [0, 1, 1, N // 2, N]  # includes an empty range
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            ks.search(a, b)
+        torch.cuda.synchronize()
+        assert torch.equal(ks.idx, ri) and torch.equal(ks.dists, rd), (N, P1, P2, D, K, norm)
+    # self-KNN through the same tensor (the pre-pass sorts the cloud once)
+    p = torch.rand(4, 3000, 3, generator=gen).to(DEV)
+    L = torch.tensor([3000, 1, 0, 2999], device=DEV)
+    ri, rd = _C.knn_points_idx(p, p, L, L, 2, 16, -1)
+    ks = _C.KnnSliced(p, p, L, L, 2, 16)
+    ks.prepare()
+    ks.search(2, 4)
+    ks.search(0, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(ks.idx, ri) and torch.equal(ks.dists, rd)
+    with pytest.raises(RuntimeError):
+        ks.search(3, 9)
 
 
 @pytest.fixture
