@@ -108,6 +108,18 @@ int pops_knn_points_idx_range(const float* p1, const float* p2, const int64_t* l
                               float* dists, void* workspace, size_t workspace_bytes,
                               pops_stream_t stream);
 
+/* Both directions of a two-sided search in one call -- what chamfer_distance needs
+ * (functions/chamfer.py:136 calls knn_points(x, y) and, for the other direction, knn_points(y, x)):
+ * idx12/dists12 (N,P1,K) = neighbours of p1 in p2, idx21/dists21 (N,P2,K) = neighbours of p2 in p1,
+ * each exactly what pops_knn_points_idx returns for that direction.  On the D = 3 path both clouds
+ * are ordered by ONE pre-pass (one sort instead of two).  Additive. */
+size_t pops_knn_pair_workspace_bytes(int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K, int norm);
+int pops_knn_points_idx_pair(const float* p1, const float* p2, const int64_t* lengths1,
+                             const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2, int64_t D,
+                             int64_t K, int norm, int64_t* idx12, float* dists12, int64_t* idx21,
+                             float* dists21, void* workspace, size_t workspace_bytes,
+                             pops_stream_t stream);
+
 /* _C.knn_check_version (ext.cpp:19; knn.cu:292-303): which (D,K) the reference's kernel
  * variant `version` accepts.  Kept so callers probing it keep working; returns 0/1. */
 int pops_knn_check_version(int version, int64_t D, int64_t K);
@@ -210,7 +222,9 @@ int pops_point_covariances(const float* x, const int64_t* idx, const int64_t* le
  *   pairs (host arrays of device pointers);  point_reduction 0 none | 1 sum | 2 mean | 3 max.
  *   forward: cham_out (N) [or (N,P1) for none], feat_out (F,N) [or (F,N,P1)], argmax_out (N) for max.
  *   backward: g_cham / g_feat shaped like the forward outputs; grad_x (N,P1,D), grad_y (N,P2,D),
- *   grad_xf[f], grad_yf[f] are zero-filled and written by the call (float atomics on the y side).
+ *   grad_xf[f], grad_yf[f] are zero-filled and written by the call (float atomics on the y side);
+ *   accumulate != 0: the buffers are NOT cleared and the call adds to them -- the y -> x direction of
+ *   a two-sided loss lands on the x -> y direction's gradients without a separate sum.
  * ------------------------------------------------------------------------------------------- */
 int pops_chamfer_forward(const float* dists, const int64_t* idx, const int64_t* lengths1,
                          const int64_t* lengths2, const float* weights, int64_t N, int64_t P1,
@@ -223,7 +237,7 @@ int pops_chamfer_backward(const float* x, const float* y, const int64_t* idx, co
                           const float* const* yf, const int64_t* chans, int point_reduction,
                           int abs_cosine, const float* g_cham, const float* g_feat,
                           const int64_t* argmax, float* grad_x, float* grad_y, float* const* grad_xf,
-                          float* const* grad_yf, pops_stream_t stream);
+                          float* const* grad_yf, int accumulate, pops_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,30 @@ def _same_device(a: torch.Tensor, b: torch.Tensor, what: str) -> None:
 
 
 def _stream(t: torch.Tensor) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    # the raw handle of the current stream (what torch.cuda.current_stream(dev).cuda_stream returns,
+    # without building two Python objects per call: these wrappers sit on launch-bound paths)
+    return torch._C._cuda_getCurrentRawStream(t.device.index)
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` that costs nothing when `dev` is already current."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch._C._cuda_getDevice()
+        if cur != self.idx:
+            self.prev = cur
+            torch._C._cuda_setDevice(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch._C._cuda_setDevice(self.prev)
+        return False
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -78,7 +101,7 @@ def knn_points_idx(p1, p2, lengths1, lengths2, norm, K, version):
     dists = torch.empty((N, P1, K), dtype=torch.float32, device=p1.device)
     if idx.numel() == 0:
         return idx, dists
-    with torch.cuda.device(p1.device):
+    with _on_device(p1.device):
         nbytes = lib.pops_knn_workspace_bytes(N, P1, P2, D, K, int(norm))
         ws = _ws(nbytes, p1.device)
         st = lib.pops_knn_points_idx(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
@@ -87,6 +110,38 @@ def knn_points_idx(p1, p2, lengths1, lengths2, norm, K, version):
                                      _stream(p1))
     _lib.check(st, "knn_points_idx")
     return idx, dists
+
+
+def knn_points_idx_pair(p1, p2, lengths1, lengths2, norm, K):
+    """pops_knn_points_idx_pair (additive): knn_points_idx(p1, p2, ...) and knn_points_idx(p2, p1, ...)
+    in one call, sharing one spatial pre-pass.  Returns (idx12, dists12, idx21, dists21)."""
+    lib = _lib.load()
+    p1 = _cuda_f32(p1, "p1")
+    p2 = _cuda_f32(p2, "p2")
+    _same_device(p1, p2, "p1 and p2")
+    if p1.dim() != 3 or p2.dim() != 3 or p1.shape[0] != p2.shape[0] or p1.shape[2] != p2.shape[2]:
+        raise RuntimeError("p1 and p2 must be (N, P, D) with matching N and D")
+    if norm not in (1, 2):
+        raise RuntimeError("Norm must be 1 or 2.")
+    lengths1 = _cuda_i64(lengths1, "lengths1", p1)
+    lengths2 = _cuda_i64(lengths2, "lengths2", p1)
+    N, P1, D = p1.shape
+    P2 = p2.shape[1]
+    K = int(K)
+    dev = p1.device
+    idx12 = torch.empty((N, P1, K), dtype=torch.int64, device=dev)
+    d12 = torch.empty((N, P1, K), dtype=torch.float32, device=dev)
+    idx21 = torch.empty((N, P2, K), dtype=torch.int64, device=dev)
+    d21 = torch.empty((N, P2, K), dtype=torch.float32, device=dev)
+    if N == 0 or K == 0:
+        return idx12, d12, idx21, d21
+    with _on_device(dev):
+        ws = _ws(lib.pops_knn_pair_workspace_bytes(N, P1, P2, D, K, int(norm)), dev)
+        st = lib.pops_knn_points_idx_pair(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(), lengths2.data_ptr(),
+                                          N, P1, P2, D, K, int(norm), idx12.data_ptr(), d12.data_ptr(),
+                                          idx21.data_ptr(), d21.data_ptr(), ws.data_ptr(), ws.numel(), _stream(p1))
+    _lib.check(st, "knn_points_idx_pair")
+    return idx12, d12, idx21, d21
 
 
 class KnnSliced:
@@ -108,7 +163,7 @@ class KnnSliced:
         dev = self.p1.device
         self.idx = torch.empty((self.N, self.P1, self.K), dtype=torch.int64, device=dev)
         self.dists = torch.empty((self.N, self.P1, self.K), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             self.ws = _ws(self.lib.pops_knn_workspace_bytes(self.N, self.P1, self.P2, self.D, self.K, self.norm), dev)
 
     def _args(self):
@@ -116,14 +171,14 @@ class KnnSliced:
                 self.P2, self.D, self.K, self.norm)
 
     def prepare(self):
-        with torch.cuda.device(self.p1.device):
+        with _on_device(self.p1.device):
             st = self.lib.pops_knn_points_prepare(*self._args(), self.ws.data_ptr(), self.ws.numel(), _stream(self.p1))
         _lib.check(st, "knn_points_prepare")
 
     def search(self, n0, n1):
         if self.idx.numel() == 0:
             return
-        with torch.cuda.device(self.p1.device):
+        with _on_device(self.p1.device):
             st = self.lib.pops_knn_points_idx_range(*self._args(), -1, int(n0), int(n1), self.idx.data_ptr(),
                                                     self.dists.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
                                                     _stream(self.p1))
@@ -152,7 +207,7 @@ def knn_points_backward(p1, p2, lengths1, lengths2, idxs, norm, grad_dists):
     K = idxs.shape[2]
     grad_p1 = torch.empty_like(p1)
     grad_p2 = torch.empty_like(p2)
-    with torch.cuda.device(p1.device):
+    with _on_device(p1.device):
         st = lib.pops_knn_points_backward(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
                                           lengths2.data_ptr(), idxs.data_ptr(),
                                           grad_dists.data_ptr(), N, P1, P2, D, K, int(norm),
@@ -178,7 +233,7 @@ def ball_query(p1, p2, lengths1, lengths2, K, radius):
         return idx, dists
     if P2 == 0 or D == 0:
         return idx.fill_(-1), dists.zero_()
-    with torch.cuda.device(p1.device):
+    with _on_device(p1.device):
         ws = _ws(lib.pops_ball_query_workspace_bytes(N, P1, P2, D, K), p1.device)
         st = lib.pops_ball_query(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
                                  lengths2.data_ptr(), N, P1, P2, D, K, float(radius),
@@ -206,7 +261,7 @@ def sample_farthest_points(points, lengths, K, start_idxs, max_K=None):
         idx.fill_(-1)
         idx[:, 0] = start_idxs
         return idx
-    with torch.cuda.device(points.device):
+    with _on_device(points.device):
         ws = _ws(lib.pops_fps_workspace_bytes(N, P, D, max_K), points.device)
         st = lib.pops_sample_farthest_points(points.data_ptr(), lengths.data_ptr(), K.data_ptr(),
                                              start_idxs.data_ptr(), N, P, D, max_K,
@@ -228,7 +283,7 @@ def packed_to_padded(inputs_packed, first_idxs, max_size):
     out = torch.empty((B, int(max_size), D), dtype=torch.float32, device=x.device)
     if out.numel() == 0:
         return out
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         st = lib.pops_packed_to_padded(x.data_ptr(), first.data_ptr(), F, B, int(max_size), D,
                                        out.data_ptr(), _stream(x))
     _lib.check(st, "packed_to_padded")
@@ -246,7 +301,7 @@ def padded_to_packed(inputs_padded, first_idxs, num_inputs):
     out = torch.empty((int(num_inputs), D), dtype=torch.float32, device=x.device)
     if out.numel() == 0:
         return out
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         st = lib.pops_padded_to_packed(x.data_ptr(), first.data_ptr(), int(num_inputs), B, M, D,
                                        out.data_ptr(), _stream(x))
     _lib.check(st, "padded_to_packed")
@@ -272,7 +327,7 @@ def gather(x, idx, lengths, mode, oob_flag=None):
         return out
     if M == 0:
         return out.zero_()
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         st = lib.pops_gather(x.data_ptr(), idx.data_ptr(), _ptr(lengths), N, M, U, L, K, int(mode),
                              out.data_ptr(), _ptr(oob_flag), _stream(x))
     _lib.check(st, "gather")
@@ -290,7 +345,7 @@ def gather_backward(grad_out, idx, lengths, M, mode):
     grad_x = torch.empty((N, int(M), U), dtype=torch.float32, device=g.device)
     if grad_x.numel() == 0:
         return grad_x
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         st = lib.pops_gather_backward(g.data_ptr(), idx.data_ptr(), _ptr(lengths), N, int(M), U, L,
                                       K, int(mode), grad_x.data_ptr(), _stream(g))
     _lib.check(st, "gather_backward")
@@ -318,9 +373,12 @@ def _chan_array(tensors):
     return arr
 
 
-def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point_reduction, abs_cosine):
+def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point_reduction, abs_cosine,
+                    out=None):
     """Fused per-direction chamfer post-processing (see include/pointops_b200.h).
     dists/idx (N,P1) from the K=1 search; xfs/yfs lists of (N,P,C) feature tensors.
+    out: optional (1+F, N) float32 buffer for the "sum" / "mean" reductions (row 0 = cham, rows
+    1.. = features) so that two directions can land in one tensor.
     Returns (cham, feats (F,...) or None, argmax or None)."""
     lib = _lib.load()
     dists = _cuda_f32(dists, "dists")
@@ -331,14 +389,18 @@ def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point
     yfs = [_cuda_f32(t, "y_feature") for t in yfs]
     red = RED[point_reduction]
     shape = (N, P1) if red == 0 else (N,)
-    cham = torch.empty(shape, dtype=torch.float32, device=dists.device)
-    feats = torch.empty((F,) + shape, dtype=torch.float32, device=dists.device) if F else None
+    if out is not None:
+        assert red in (1, 2) and out.shape == (1 + F, N) and out.is_contiguous() and out.dtype == torch.float32
+        cham, feats = out[0], (out[1:] if F else None)
+    else:
+        cham = torch.empty(shape, dtype=torch.float32, device=dists.device)
+        feats = torch.empty((F,) + shape, dtype=torch.float32, device=dists.device) if F else None
     argmax = torch.empty((N,), dtype=torch.int64, device=dists.device) if red == 3 else None
     if N == 0:
         return cham, feats, argmax
     if weights is not None:
         weights = _cuda_f32(weights, "weights")
-    with torch.cuda.device(dists.device):
+    with _on_device(dists.device):
         st = lib.pops_chamfer_forward(dists.data_ptr(), idx.data_ptr(), lengths1.data_ptr(),
                                       lengths2.data_ptr(), _ptr(weights), N, P1, int(P2), F,
                                       _ptr_array(xfs), _ptr_array(yfs), _chan_array(xfs), red,
@@ -349,28 +411,35 @@ def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point
 
 
 def chamfer_backward(x, y, idx, lengths1, lengths2, weights, norm, xfs, yfs, point_reduction, abs_cosine,
-                     g_cham, g_feat, argmax):
-    """Returns (grad_x, grad_y, [grad_xf...], [grad_yf...])."""
+                     g_cham, g_feat, argmax, into=None):
+    """Returns (grad_x, grad_y, [grad_xf...], [grad_yf...]).
+    into: optional (grad_x, grad_y, [grad_xf...], [grad_yf...]) of already initialised buffers the
+    call ADDS to (accumulate mode of pops_chamfer_backward)."""
     lib = _lib.load()
     x = _cuda_f32(x, "x")
     y = _cuda_f32(y, "y")
     N, P1, D = x.shape
     P2 = y.shape[1]
     F = len(xfs)
-    grad_x = torch.empty_like(x)
-    grad_y = torch.empty_like(y)
-    gxf = [torch.empty_like(t) for t in xfs]
-    gyf = [torch.empty_like(t) for t in yfs]
+    if into is not None:
+        grad_x, grad_y, gxf, gyf = into
+        for t, r in [(grad_x, x), (grad_y, y)] + list(zip(gxf, xfs)) + list(zip(gyf, yfs)):
+            assert t.shape == r.shape and t.is_contiguous() and t.dtype == torch.float32 and t.device == r.device
+    else:
+        grad_x = torch.empty_like(x)
+        grad_y = torch.empty_like(y)
+        gxf = [torch.empty_like(t) for t in xfs]
+        gyf = [torch.empty_like(t) for t in yfs]
     g_cham = _cuda_f32(g_cham, "g_cham")
     if g_feat is not None:
         g_feat = _cuda_f32(g_feat, "g_feat")
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         st = lib.pops_chamfer_backward(x.data_ptr(), y.data_ptr(), idx.data_ptr(), lengths1.data_ptr(),
                                        lengths2.data_ptr(), _ptr(weights), N, P1, P2, D, int(norm), F,
                                        _ptr_array(xfs), _ptr_array(yfs), _chan_array(xfs),
                                        RED[point_reduction], int(bool(abs_cosine)), g_cham.data_ptr(),
                                        _ptr(g_feat), _ptr(argmax), grad_x.data_ptr(), grad_y.data_ptr(),
-                                       _ptr_array(gxf), _ptr_array(gyf), _stream(x))
+                                       _ptr_array(gxf), _ptr_array(gyf), int(into is not None), _stream(x))
     _lib.check(st, "chamfer_backward")
     return grad_x, grad_y, gxf, gyf
 
@@ -395,7 +464,7 @@ def sample_pdf(bins, weights, outputs, eps):
     if bins.shape[1] != n_bins + 1:
         raise RuntimeError("There must be one more bin edge than weights.")
     lib = _lib.load()
-    with torch.cuda.device(bins.device):
+    with _on_device(bins.device):
         st = lib.pops_sample_pdf(bins.data_ptr(), weights.data_ptr(), outputs.data_ptr(), B, n_bins,
                                  outputs.shape[1], float(eps), _stream(bins))
     _lib.check(st, "sample_pdf")
@@ -417,7 +486,7 @@ def point_covariances(x, idx, lengths):
     cov = torch.empty((N, P, D, D), dtype=torch.float32, device=x.device)
     if nn.numel() == 0:
         return cov, nn
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         st = lib.pops_point_covariances(x.data_ptr(), idx.data_ptr(), _ptr(lengths), N, P, M, D, K,
                                         nn.data_ptr(), cov.data_ptr(), _stream(x))
     _lib.check(st, "point_covariances")

@@ -31,6 +31,8 @@ SIGNATURES = {
     "pops_knn_points_prepare": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int, _P, c_size_t, _P]),
     "pops_knn_points_idx_range": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int, c_int] + [c_int64] * 2
                                   + [_P, _P, _P, c_size_t, _P]),
+    "pops_knn_pair_workspace_bytes": (c_size_t, [c_int64] * 5 + [c_int]),
+    "pops_knn_points_idx_pair": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int] + [_P] * 5 + [c_size_t, _P]),
     "pops_knn_check_version": (c_int, [c_int, c_int64, c_int64]),
     "pops_knn_points_backward": (c_int, [_P] * 6 + [c_int64] * 5 + [c_int, _P, _P, _P]),
     "pops_ball_query_workspace_bytes": (c_size_t, [c_int64] * 5),
@@ -45,7 +47,7 @@ SIGNATURES = {
     "pops_gather_backward": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P]),
     "pops_chamfer_forward": (c_int, [_P] * 5 + [c_int64] * 3 + [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
     "pops_chamfer_backward": (c_int, [_P] * 6 + [c_int64] * 4 + [c_int, c_int, _P, _P, _P, c_int, c_int]
-                              + [_P] * 8),
+                              + [_P] * 7 + [c_int, _P]),
 }
 
 

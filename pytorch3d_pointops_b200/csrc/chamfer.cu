@@ -197,7 +197,10 @@ chamfer_fwd_kernel(const float* __restrict__ dists, const int64_t* __restrict__ 
   }
 }
 
-// grad buffers must be zero-filled by the caller (the host function does it)
+// grad buffers must be zero-filled by the caller (the host function does it unless `acc`: then they
+// hold the other direction's gradient and this launch adds to it -- the per-point stores become
+// read-modify-writes, which no other thread of this launch touches: its atomics go to the other
+// cloud's buffers)
 template <int NORM>
 __global__ void __launch_bounds__(kBwdThreads)
 chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -206,7 +209,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                    int D, ChamferFeat ft, int reduction, int abs_cosine, int N,
                    const float* __restrict__ g_cham, const float* __restrict__ g_feat,
                    const int64_t* __restrict__ argmax, float* __restrict__ grad_x,
-                   float* __restrict__ grad_y) {
+                   float* __restrict__ grad_y, int acc) {
   const int n = blockIdx.y;
   int64_t L1l = len1[n], L2l = len2[n];
   const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
@@ -231,7 +234,8 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
       for (int d = 0; d < D; ++d) {
         const float a = xn[static_cast<size_t>(i) * D + d], b = yn[static_cast<size_t>(j) * D + d];
         const float diff = (NORM == 1) ? gd * ((a > b) ? 1.0f : -1.0f) : 2.0f * gd * (a - b);
-        gxn[static_cast<size_t>(i) * D + d] = diff;
+        float* gp = gxn + static_cast<size_t>(i) * D + d;
+        *gp = acc ? *gp + diff : diff;
         atomicAdd(gyn + static_cast<size_t>(j) * D + d, -diff);
       }
     }
@@ -263,7 +267,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
         const float ah = a[k] / na, bh = bv / nb;
         const float da = (bh - (a_free ? c * ah : 0.0f)) / na;
         const float db = (ah - (b_free ? c * bh : 0.0f)) / nb;
-        ga[k] = dc * da;
+        ga[k] = acc ? ga[k] + dc * da : dc * da;
         if (!y_empty) atomicAdd(gb + k, dc * db);
       }
     }
@@ -334,18 +338,21 @@ extern "C" int pops_chamfer_backward(const float* x, const float* y, const int64
                                      const float* const* yf, const int64_t* chans, int point_reduction,
                                      int abs_cosine, const float* g_cham, const float* g_feat,
                                      const int64_t* argmax, float* grad_x, float* grad_y,
-                                     float* const* grad_xf, float* const* grad_yf, pops_stream_t stream) {
+                                     float* const* grad_xf, float* const* grad_yf, int accumulate,
+                                     pops_stream_t stream) {
   POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
   POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0, "negative size");
   POPS_CHECK_ARG(point_reduction >= 0 && point_reduction <= 3, "bad point_reduction");
   ChamferFeat ft;
   POPS_CHECK_ARG(fill_feats(&ft, num_feats, xf, yf, grad_xf, grad_yf, chans) == 0, "too many features (max 8)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (N * P1 * D > 0) POPS_CUDA_OK(cudaMemsetAsync(grad_x, 0, size_t(N) * P1 * D * 4, st));
-  if (N * P2 * D > 0) POPS_CUDA_OK(cudaMemsetAsync(grad_y, 0, size_t(N) * P2 * D * 4, st));
-  for (int f = 0; f < num_feats; ++f) {
-    if (N * P1 * chans[f] > 0) POPS_CUDA_OK(cudaMemsetAsync(ft.gxf[f], 0, size_t(N) * P1 * chans[f] * 4, st));
-    if (N * P2 * chans[f] > 0) POPS_CUDA_OK(cudaMemsetAsync(ft.gyf[f], 0, size_t(N) * P2 * chans[f] * 4, st));
+  if (!accumulate) {
+    if (N * P1 * D > 0) POPS_CUDA_OK(cudaMemsetAsync(grad_x, 0, size_t(N) * P1 * D * 4, st));
+    if (N * P2 * D > 0) POPS_CUDA_OK(cudaMemsetAsync(grad_y, 0, size_t(N) * P2 * D * 4, st));
+    for (int f = 0; f < num_feats; ++f) {
+      if (N * P1 * chans[f] > 0) POPS_CUDA_OK(cudaMemsetAsync(ft.gxf[f], 0, size_t(N) * P1 * chans[f] * 4, st));
+      if (N * P2 * chans[f] > 0) POPS_CUDA_OK(cudaMemsetAsync(ft.gyf[f], 0, size_t(N) * P2 * chans[f] * 4, st));
+    }
   }
   if (N == 0 || P1 == 0) return POPS_OK;
   POPS_CHECK_ARG(x && y && idx && lengths1 && lengths2 && g_cham, "null pointer argument");
@@ -354,11 +361,11 @@ extern "C" int pops_chamfer_backward(const float* x, const float* y, const int64
   if (norm == 2)
     chamfer_bwd_kernel<2><<<bgrid, kBwdThreads, 0, st>>>(
         x, y, idx, lengths1, lengths2, weights, int(P1), int(P2), int(D), ft, point_reduction, abs_cosine,
-        int(N), g_cham, g_feat, argmax, grad_x, grad_y);
+        int(N), g_cham, g_feat, argmax, grad_x, grad_y, accumulate ? 1 : 0);
   else
     chamfer_bwd_kernel<1><<<bgrid, kBwdThreads, 0, st>>>(
         x, y, idx, lengths1, lengths2, weights, int(P1), int(P2), int(D), ft, point_reduction, abs_cosine,
-        int(N), g_cham, g_feat, argmax, grad_x, grad_y);
+        int(N), g_cham, g_feat, argmax, grad_x, grad_y, accumulate ? 1 : 0);
   POPS_LAUNCH_OK("chamfer_bwd_kernel");
   return POPS_OK;
 }

@@ -741,6 +741,53 @@ extern "C" int pops_knn_points_idx_range(const float* p1, const float* p2, const
                           static_cast<cudaStream_t>(stream));
 }
 
+// ---- both directions of a two-sided search (chamfer) ------------------------------------------------
+namespace {
+inline bool pair_ordered(int64_t P1, int64_t P2, int64_t D, int64_t K, int norm) {
+  return ordered_path(P1, D, K, norm) && ordered_path(P2, D, K, norm) && get_option("knn_pair", 1) != 0;
+}
+}  // namespace
+
+extern "C" size_t pops_knn_pair_workspace_bytes(int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K,
+                                                int norm) {
+  const size_t a = pops_knn_workspace_bytes(N, P1, P2, D, K, norm), b = pops_knn_workspace_bytes(N, P2, P1, D, K, norm);
+  return align_up(a, 256) + b;  // one region per direction (the shared sort lives in the first)
+}
+
+extern "C" int pops_knn_points_idx_pair(const float* p1, const float* p2, const int64_t* lengths1,
+                                        const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2,
+                                        int64_t D, int64_t K, int norm, int64_t* idx12, float* dists12,
+                                        int64_t* idx21, float* dists21, void* workspace,
+                                        size_t workspace_bytes, pops_stream_t stream) {
+  POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
+  POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0 && K >= 0, "negative size");
+  if (workspace_bytes < pops_knn_pair_workspace_bytes(N, P1, P2, D, K, norm) || !workspace)
+    return fail(POPS_ERR_WORKSPACE, "knn: workspace missing or too small");
+  const size_t wa = align_up(pops_knn_workspace_bytes(N, P1, P2, D, K, norm), 256);
+  char* wsa = reinterpret_cast<char*>(workspace);
+  char* wsb = wsa + wa;
+  if (N == 0 || K == 0 || P1 == 0 || P2 == 0 || D == 0 || !pair_ordered(P1, P2, D, K, norm)) {
+    const int rc = pops_knn_points_idx(p1, p2, lengths1, lengths2, N, P1, P2, D, K, norm, -1, idx12, dists12, wsa, wa,
+                                       stream);
+    if (rc != POPS_OK) return rc;
+    return pops_knn_points_idx(p2, p1, lengths2, lengths1, N, P2, P1, D, K, norm, -1, idx21, dists21, wsb,
+                               workspace_bytes - wa, stream);
+  }
+  POPS_CHECK_ARG(p1 && p2 && lengths1 && lengths2 && idx12 && dists12 && idx21 && dists21, "null pointer argument");
+  POPS_CHECK_ARG(P2 < (int64_t(1) << 31) && P1 < (int64_t(1) << 31) && N < 65536, "size too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KnnOrderBuffers a, b;
+  knn_order_carve(wsa, N, P1, P2, &a);
+  knn_order_carve(wsb, N, P2, P1, &b);
+  b.maxabs_bits = a.maxabs_bits;
+  b.bbox = a.bbox;
+  int rc = knn_order_prepass_pair(p1, p2, lengths1, lengths2, int(N), int(P1), int(P2), a, b, st);
+  if (rc != POPS_OK) return rc;
+  rc = knn_prune_search(a, lengths1, lengths2, int(N), int(P1), int(P2), int(K), idx12, dists12, st);
+  if (rc != POPS_OK) return rc;
+  return knn_prune_search(b, lengths2, lengths1, int(N), int(P2), int(P1), int(K), idx21, dists21, st);
+}
+
 extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const int64_t* lengths1,
                                         const int64_t* lengths2, const int64_t* idx,
                                         const float* grad_dists, int64_t N, int64_t P1, int64_t P2,

@@ -87,7 +87,8 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sm) {
 __global__ void __launch_bounds__(1024)
 bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                    const int64_t* __restrict__ len1, const int64_t* __restrict__ len2, int P1, int P2,
-                   bool self_knn, float* __restrict__ bbox, unsigned* __restrict__ maxabs_bits) {
+                   bool self_knn, bool union_box, float* __restrict__ bbox,
+                   unsigned* __restrict__ maxabs_bits) {
   __shared__ float sm[32];
   const int n = blockIdx.x;
   int64_t L2l = len2[n];
@@ -102,15 +103,27 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       mx[d] = fmaxf(mx[d], v);
     }
   }
-  float m = 0.0f;
+  bool none = L2 == 0;
+  if (union_box) {  // pair pre-pass: one Morton grid over both clouds
+    int64_t L1l = len1[n];
+    const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
+    none = none && L1 == 0;
+    const float* a = p1 + static_cast<size_t>(n) * P1 * 3;
+    for (int j = threadIdx.x; j < L1; j += blockDim.x) {
 #pragma unroll
-  for (int d = 0; d < 3; ++d) m = fmaxf(m, fmaxf(fabsf(mn[d]), fabsf(mx[d])));
-  if (L2 == 0) m = 0.0f;
-  if (!self_knn) {
+      for (int d = 0; d < 3; ++d) {
+        const float v = a[static_cast<size_t>(j) * 3 + d];
+        mn[d] = fminf(mn[d], v);
+        mx[d] = fmaxf(mx[d], v);
+      }
+    }
+  }
+  float m1 = 0.0f;  // max |coordinate| of p1 when it is not part of the box
+  if (!self_knn && !union_box) {
     int64_t L1l = len1[n];
     const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
     const float* a = p1 + static_cast<size_t>(n) * P1 * 3;
-    for (int e = threadIdx.x; e < L1 * 3; e += blockDim.x) m = fmaxf(m, fabsf(a[e]));
+    for (int e = threadIdx.x; e < L1 * 3; e += blockDim.x) m1 = fmaxf(m1, fabsf(a[e]));
   }
   float out[6];
 #pragma unroll
@@ -118,8 +131,13 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     out[d] = block_reduce(mn[d], false, sm);
     out[3 + d] = block_reduce(mx[d], true, sm);
   }
-  m = block_reduce(m, true, sm);
+  m1 = block_reduce(m1, true, sm);
   if (threadIdx.x == 0) {
+    float m = 0.0f;  // from the REDUCED box: threads that saw no point still hold the +-FLT_MAX seeds
+#pragma unroll
+    for (int d = 0; d < 3; ++d) m = fmaxf(m, fmaxf(fabsf(out[d]), fabsf(out[3 + d])));
+    if (none) m = 0.0f;
+    m = fmaxf(m, m1);
 #pragma unroll
     for (int d = 0; d < 6; ++d) bbox[n * 6 + d] = out[d];
     maxabs_bits[n] = __float_as_uint(m);
@@ -263,6 +281,51 @@ __global__ void box_kernel(const float* __restrict__ blocks, int nbox, float4* _
   }
 }
 
+// Pair pre-pass: one sorted cloud serves as the BLOCKS of one direction and as the QUERIES of the
+// other.  Entry j of cloud n of the tensor `pts` (sorted position j): block row entry, query entry,
+// and the query's home = lower bound of its code among the other tensor's sorted keys.
+__global__ void gather_pair_kernel(const float* __restrict__ pts, const int64_t* __restrict__ len_self,
+                                   const int64_t* __restrict__ len_other, int P, int P_other, int nbox,
+                                   const unsigned* __restrict__ keys_self, const unsigned* __restrict__ vals_self,
+                                   const unsigned* __restrict__ keys_other, unsigned self_bit, unsigned other_bit,
+                                   float* __restrict__ blocks, float4* __restrict__ qsorted,
+                                   unsigned* __restrict__ qhome) {
+  const int n = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nbox * kBoxPoints) return;
+  int64_t Ll = len_self[n], Lol = len_other[n];
+  const int L = static_cast<int>(Ll < 0 ? 0 : (Ll > P ? P : Ll));
+  const int Lo = static_cast<int>(Lol < 0 ? 0 : (Lol > P_other ? P_other : Lol));
+  float x = 0.f, y = 0.f, z = 0.f, w = __int_as_float(0x7f800000);
+  unsigned orig = kNoPoint;
+  if (j < P) {
+    const unsigned o = vals_self[static_cast<size_t>(n) * P + j];
+    unsigned home = 0;
+    if (j < L) {
+      const float* src = pts + (static_cast<size_t>(n) * P + o) * 3;
+      x = src[0]; y = src[1]; z = src[2];
+      w = fmaf(z, z, fmaf(y, y, x * x));
+      orig = o;
+      const unsigned target = (keys_self[static_cast<size_t>(n) * P + j] & ~self_bit) | other_bit;
+      const unsigned* ko = keys_other + static_cast<size_t>(n) * P_other;
+      int lo = 0, hi = Lo;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ko[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      home = static_cast<unsigned>(lo);
+    }
+    qsorted[static_cast<size_t>(n) * P + j] = make_float4(x, y, z, __uint_as_float(o));
+    qhome[static_cast<size_t>(n) * P + j] = home;
+  }
+  float* dst = blocks + (static_cast<size_t>(n) * nbox + j / kBoxPoints) * kBlockFloats + (j % kBoxPoints);
+  dst[0] = x;
+  dst[kBoxPoints] = y;
+  dst[2 * kBoxPoints] = z;
+  dst[3 * kBoxPoints] = w;
+  dst[4 * kBoxPoints] = __uint_as_float(orig);
+}
+
 size_t cub_temp_bytes_for(int64_t items) {
   size_t bytes = 0;
   unsigned* nul = nullptr;
@@ -306,7 +369,7 @@ int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, con
                       int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st) {
   const int nbox = static_cast<int>(knn_order_num_boxes(P2));
   const KeyLayout kl = key_layout(N, P2, !self_knn);
-  bbox_maxabs_kernel<<<N, 1024, 0, st>>>(p1, p2, len1, len2, P1, P2, self_knn, b.bbox, b.maxabs_bits);
+  bbox_maxabs_kernel<<<N, 1024, 0, st>>>(p1, p2, len1, len2, P1, P2, self_knn, false, b.bbox, b.maxabs_bits);
   POPS_LAUNCH_OK("bbox_maxabs_kernel");
   const int64_t items = static_cast<int64_t>(N) * P2 + (self_knn ? 0 : static_cast<int64_t>(N) * P1);
   {
@@ -335,6 +398,52 @@ int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, con
     gather_p1_kernel<<<grid, 256, 0, st>>>(p1, len1, len2, N, P1, P2, b.keys_out, b.vals_out, kl,
                                            b.qsorted, b.qhome);
     POPS_LAUNCH_OK("gather_p1_kernel");
+  }
+  return POPS_OK;
+}
+
+// Both directions of a two-sided search (chamfer: x -> y and y -> x) from ONE sort: `a` serves the
+// queries p1 over the blocks of p2, `b` the queries p2 over the blocks of p1.  Only a's scratch
+// buffers are used; b.maxabs_bits / b.bbox are not written (the caller points them at a's).
+int knn_order_prepass_pair(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
+                           int P1, int P2, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
+  const int nbox2 = static_cast<int>(knn_order_num_boxes(P2)), nbox1 = static_cast<int>(knn_order_num_boxes(P1));
+  const KeyLayout kl = key_layout(N, std::max(P1, P2), true);
+  bbox_maxabs_kernel<<<N, 1024, 0, st>>>(p1, p2, len1, len2, P1, P2, false, true, a.bbox, a.maxabs_bits);
+  POPS_LAUNCH_OK("bbox_maxabs_kernel");
+  const int64_t items = static_cast<int64_t>(N) * (P1 + P2);
+  {
+    const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(items, 256), int64_t(num_sms()) * 16));
+    morton_keys_kernel<<<blocks, 256, 0, st>>>(p1, p2, len1, len2, N, P1, P2, false, a.bbox, kl, a.keys_in, a.vals_in);
+    POPS_LAUNCH_OK("morton_keys_kernel");
+  }
+  size_t temp = a.cub_temp_bytes;
+  POPS_CUDA_OK(cub::DeviceRadixSort::SortPairs(a.cub_temp, temp, a.keys_in, a.keys_out, a.vals_in, a.vals_out,
+                                               static_cast<int>(items), 0, kl.end_bit, st));
+  g_launch_count.fetch_add(4, std::memory_order_relaxed);
+  const unsigned tbit = 1u << kl.tensor_shift;
+  const size_t base1 = static_cast<size_t>(N) * P2;  // sorted p1 entries follow the p2 entries
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(int64_t(nbox2) * kBoxPoints, 256)), N);
+    gather_pair_kernel<<<grid, 256, 0, st>>>(p2, len2, len1, P2, P1, nbox2, a.keys_out, a.vals_out,
+                                             a.keys_out + base1, 0u, tbit, a.blocks, b.qsorted, b.qhome);
+    POPS_LAUNCH_OK("gather_pair_kernel");
+  }
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(int64_t(nbox1) * kBoxPoints, 256)), N);
+    gather_pair_kernel<<<grid, 256, 0, st>>>(p1, len1, len2, P1, P2, nbox1, a.keys_out + base1, a.vals_out + base1,
+                                             a.keys_out, tbit, 0u, b.blocks, a.qsorted, a.qhome);
+    POPS_LAUNCH_OK("gather_pair_kernel");
+  }
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(nbox2, 8)), N);
+    box_kernel<<<grid, 256, 0, st>>>(a.blocks, nbox2, a.boxes);
+    POPS_LAUNCH_OK("box_kernel");
+  }
+  {
+    dim3 grid(static_cast<unsigned>(ceil_div(nbox1, 8)), N);
+    box_kernel<<<grid, 256, 0, st>>>(b.blocks, nbox1, b.boxes);
+    POPS_LAUNCH_OK("box_kernel");
   }
   return POPS_OK;
 }

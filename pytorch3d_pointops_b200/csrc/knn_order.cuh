@@ -38,4 +38,9 @@ size_t knn_order_carve(void* ws, int64_t N, int64_t P1, int64_t P2, KnnOrderBuff
 int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2,
                       int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st);
 
+// One sort for both directions of a two-sided search: `a` = queries p1 over blocks of p2, `b` = queries
+// p2 over blocks of p1 (b's scratch, maxabs_bits and bbox are not used: point them at a's).
+int knn_order_prepass_pair(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
+                           int P1, int P2, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st);
+
 }  // namespace pops

@@ -120,6 +120,68 @@ class _ChamferDirection(torch.autograd.Function):
         return (gx, gy, None, None, None, None, None, None, None) + tuple(gxf) + tuple(gyf)
 
 
+class _ChamferBoth(torch.autograd.Function):
+    """Both directions of the loss for point_reduction "sum" / "mean" in one autograd node.
+
+    Same kernels as two `_ChamferDirection` nodes; what it removes is the glue around them, which
+    is what a step of this size spends its time on (the step is launch-bound: ~65 launches of a
+    few microseconds): the two directions write into ONE (2, 1+F, N) tensor, one `sum` adds the
+    directions (and the batch), and the backward runs the y -> x kernel in accumulate mode on top
+    of the x -> y gradients -- no per-tensor zero fills, no `grad_a + grad_b`.
+    Outputs: (1+F) tensors -- the loss and one per feature -- shaped (N,) or () after the batch
+    reduction (`batch_mode` 0 none | 1 sum | 2 mean over N clouds)."""
+
+    @staticmethod
+    def forward(ctx, x, y, x_lengths, y_lengths, norm, point_reduction, abs_cosine, nfeat, batch_mode, *feats):
+        xfs, yfs = list(feats[:nfeat]), list(feats[nfeat:])
+        N, P1, P2 = x.shape[0], x.shape[1], y.shape[1]
+        out = torch.empty((2, 1 + nfeat, N), dtype=torch.float32, device=x.device)
+        idx1, d1, idx2, d2 = _C.knn_points_idx_pair(x, y, x_lengths, y_lengths, norm, 1)  # one pre-pass for both
+        _C.chamfer_forward(d1.view(N, P1), idx1.view(N, P1), x_lengths, y_lengths, None, P2, xfs, yfs,
+                           point_reduction, abs_cosine, out=out[0])
+        _C.chamfer_forward(d2.view(N, P2), idx2.view(N, P2), y_lengths, x_lengths, None, P1, yfs, xfs,
+                           point_reduction, abs_cosine, out=out[1])
+        if batch_mode == 0:
+            total = out.sum(0)  # (1+F, N)
+        else:
+            total = out.sum((0, 2))  # (1+F,)
+            if batch_mode == 2:
+                total = total / max(N, 1)
+        ctx.save_for_backward(x, y, x_lengths, y_lengths, idx1, idx2, *xfs, *yfs)
+        ctx.cfg = (norm, point_reduction, abs_cosine, nfeat, batch_mode)
+        return tuple(total[i] for i in range(1 + nfeat))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *grads):
+        norm, point_reduction, abs_cosine, nfeat, batch_mode = ctx.cfg
+        x, y, x_lengths, y_lengths, idx1, idx2 = ctx.saved_tensors[:6]
+        xfs = list(ctx.saved_tensors[6:6 + nfeat])
+        yfs = list(ctx.saved_tensors[6 + nfeat:])
+        N, P1, P2 = x.shape[0], x.shape[1], y.shape[1]
+        like = next(g for g in grads if g is not None)
+        g = torch.stack([gi if gi is not None else torch.zeros_like(like) for gi in grads], 0).float()
+        if batch_mode != 0:  # scalars: every cloud receives the same gradient
+            if batch_mode == 2:
+                g = g / max(N, 1)
+            g = g.view(1 + nfeat, 1).expand(1 + nfeat, N)
+        g = g.contiguous()
+        g_cham, g_feat = g[0], (g[1:] if nfeat else None)
+        # one zero fill for every gradient, carved into the per-tensor views
+        srcs = [x, y] + xfs + yfs
+        flat = torch.zeros(sum(t.numel() for t in srcs), dtype=torch.float32, device=x.device)
+        views, off = [], 0
+        for t in srcs:
+            views.append(flat[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+        gx, gy, gxf, gyf = views[0], views[1], views[2:2 + nfeat], views[2 + nfeat:]
+        _C.chamfer_backward(x, y, idx1.view(N, P1), x_lengths, y_lengths, None, norm, xfs, yfs, point_reduction,
+                            abs_cosine, g_cham, g_feat, None, into=(gx, gy, gxf, gyf))
+        _C.chamfer_backward(y, x, idx2.view(N, P2), y_lengths, x_lengths, None, norm, yfs, xfs, point_reduction,
+                            abs_cosine, g_cham, g_feat, None, into=(gy, gx, gyf, gxf))
+        return (gx, gy) + (None,) * 7 + tuple(gxf) + tuple(gyf)
+
+
 def _chamfer_distance_single_direction(
     x, y, x_lengths, y_lengths, x_features, y_features, weights,
     point_reduction: Union[str, None], norm: int, abs_cosine: bool,
@@ -186,6 +248,39 @@ def _apply_batch_reduction(cham_x, cham_features_x, weights, batch_reduction: Un
     return (cham_x, cham_features_x)
 
 
+def _chamfer_both(x, y, x_lengths, y_lengths, x_features, y_features, weights, batch_reduction,
+                  point_reduction, norm, single_directional, abs_cosine, feature_names):
+    """The common two-sided, unweighted, point-reduced call as ONE autograd node (`_ChamferBoth`);
+    None when the call is of another kind (the per-direction path then serves it).  Same
+    validation and the same error messages as the per-direction path."""
+    if single_directional or weights is not None or point_reduction not in ("mean", "sum"):
+        return None
+    with_features = (
+        x_features is not None and y_features is not None
+        and feature_names is not None and len(feature_names) > 0
+    )
+    if feature_names and x_features is not None and y_features is not None:
+        for name in feature_names:
+            if name not in x_features:
+                raise ValueError(f"Feature '{name}' is missing in x_features.")
+            if name not in y_features:
+                raise ValueError(f"Feature '{name}' is missing in y_features.")
+    N, P1, D = x.shape
+    if y.shape[0] != N or y.shape[2] != D:
+        raise ValueError("y does not have the correct shape.")
+    names = list(feature_names) if with_features else []
+    if len(names) > 8:
+        raise ValueError("at most 8 feature names are supported per call")
+    if N == 0:
+        return None
+    xfs = [x_features[n].contiguous() for n in names]
+    yfs = [y_features[n].contiguous() for n in names]
+    batch_mode = {None: 0, "sum": 1, "mean": 2}[batch_reduction]
+    out = _ChamferBoth.apply(x.contiguous(), y.contiguous(), x_lengths, y_lengths, norm, point_reduction,
+                             bool(abs_cosine), len(names), batch_mode, *xfs, *yfs)
+    return out[0], ({n: out[1 + i] for i, n in enumerate(names)} if with_features else None)
+
+
 def chamfer_distance(
     x,
     y,
@@ -216,6 +311,11 @@ def chamfer_distance(
 
     x, x_lengths, x_features = _handle_pointcloud_input(x, x_lengths, x_features)
     y, y_lengths, y_features = _handle_pointcloud_input(y, y_lengths, y_features)
+
+    fused = _chamfer_both(x, y, x_lengths, y_lengths, x_features, y_features, weights, batch_reduction,
+                          point_reduction, norm, single_directional, abs_cosine, feature_names)
+    if fused is not None:
+        return fused
 
     cham_x, feat_x = _chamfer_distance_single_direction(
         x, y, x_lengths, y_lengths, x_features, y_features, weights, point_reduction, norm,

@@ -1,0 +1,23 @@
+import sys, os
+sys.path.insert(0, "/root/repo")
+import torch
+from pytorch3d_pointops_b200 import _C, _lib
+lib = _lib.load()
+dev = torch.device("cuda:0")
+B, P, K = 32, 16384, 16
+g = torch.Generator().manual_seed(0)
+p = torch.rand(B, P, 3, generator=g).to(dev); L = torch.full((B,), P, dtype=torch.int64, device=dev)
+def timeit(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+ks = _C.KnnSliced(p, p, L, L, 2, K)
+print("prepare", timeit(ks.prepare))
+for q in (4, 2):
+    lib.pops_set_option(b"knn_q", q)
+    for n in (1, 2, 4, 8, 16, 32):
+        print(f"Q={q} search {n} clouds: {timeit(lambda: ks.search(0, n)):.3f} ms")

@@ -279,6 +279,32 @@ def test_two_phase_range_api_matches_single_call():
         ks.search(3, 9)
 
 
+def test_pair_search_matches_two_calls():
+    """pops_knn_points_idx_pair = knn_points_idx(p1, p2) and knn_points_idx(p2, p1), bit for bit, on
+    the shared-pre-pass path (both clouds >= 1024 points, D=3, L2) with ragged, tiny and empty
+    clouds, duplicated points and offset clouds, and on the shapes where it is two plain calls."""
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(33)
+    cases = [(6, 3000, 2200, 3, 1, 2), (4, 1024, 5000, 3, 8, 2), (3, 1500, 1500, 3, 32, 2), (3, 700, 2000, 3, 1, 2),
+             (2, 1200, 1300, 3, 1, 1), (2, 300, 400, 5, 4, 2)]
+    for (N, P1, P2, D, K, norm) in cases:
+        p1 = torch.rand(N, P1, D, generator=gen).to(DEV)
+        p2 = (torch.rand(N, P2, D, generator=gen) * 0.7 + 0.4).to(DEV)  # partly overlapping boxes
+        p2[:, : P2 // 8] = p2[:, P2 // 8 : 2 * (P2 // 8)]  # duplicated points
+        l1 = torch.randint(1, P1 + 1, (N,), generator=gen).to(DEV)
+        l2 = torch.randint(1, P2 + 1, (N,), generator=gen).to(DEV)
+        l1[0], l2[0] = P1, P2
+        if N > 2:
+            l1[1], l2[1] = 3, P2   # tiny cloud against a full one
+            l1[2], l2[2] = P1, 0   # empty cloud
+        i12, d12, i21, d21 = _C.knn_points_idx_pair(p1, p2, l1, l2, norm, K)
+        ri, rd = _C.knn_points_idx(p1, p2, l1, l2, norm, K, -1)
+        si, sd = _C.knn_points_idx(p2, p1, l2, l1, norm, K, -1)
+        torch.cuda.synchronize()
+        assert torch.equal(i12, ri) and torch.equal(d12, rd), (N, P1, P2, D, K, norm)
+        assert torch.equal(i21, si) and torch.equal(d21, sd), (N, P1, P2, D, K, norm)
+
+
 @pytest.fixture
 def force_ordered():
     """Route every D=3 L2 K<=32 call through the Morton-ordered, box-pruned search, whatever P2."""
