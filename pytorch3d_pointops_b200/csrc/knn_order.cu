@@ -10,7 +10,8 @@
 //
 // This file builds that order:
 //   1. bbox_maxabs_kernel   per cloud: bounding box of the valid p2 points, max |coord| of p1, p2
-//   2. morton_keys_kernel   key = [tensor | cloud | invalid | Morton code], value = index in cloud
+//   2. morton_keys_kernel   key = [tensor | cloud | Morton code], value = index in cloud (padding
+//                           entries: largest code; the stable sort keeps them behind the valid points)
 //   3. cub::DeviceRadixSort one sort for every cloud of both tensors
 //   4. gather kernels       p2 -> blocks of 64 sorted points (rows x,y,z,w,orig_idx; + sentinels);
 //                           p1 -> float4 (x,y,z,orig_idx) in sorted order + each query's home
@@ -36,7 +37,7 @@ inline int clog2(int64_t n) {
 struct KeyLayout {
   int axis_bits;     // Morton bits per axis
   int code_bits;     // 3 * axis_bits
-  int cloud_shift;   // code_bits + 1 (one bit marks padding entries, which sort last in the cloud)
+  int cloud_shift;   // = code_bits (padding entries carry the largest code: see morton_keys_kernel)
   int tensor_shift;  // cloud_shift + clog2(N)
   int end_bit;
 };
@@ -50,7 +51,7 @@ inline KeyLayout key_layout(int64_t N, int64_t P2, bool two_tensors) {
   const int want = (clog2(std::max<int64_t>(P2, 1)) + 4 + 2) / 3;
   k.axis_bits = std::min(std::min(10, std::max(1, (30 - cl) / 3)), std::max(4, want));
   k.code_bits = 3 * k.axis_bits;
-  k.cloud_shift = k.code_bits + 1;
+  k.cloud_shift = k.code_bits;
   k.tensor_shift = k.cloud_shift + cl;
   k.end_bit = k.tensor_shift + (two_tensors ? 1 : 0);
   return k;
@@ -83,19 +84,40 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sm) {
   return v;
 }
 
-// one CTA per cloud
-__global__ void __launch_bounds__(1024)
+constexpr int kBboxCluster = 8;   // CTAs per cloud (one thread-block cluster)
+constexpr int kBboxThreads = 256;
+
+__device__ __forceinline__ uint32_t bb_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void bb_cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bb_st_remote(void* local_smem_ptr, uint32_t rank, float value) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(value) : "memory");
+}
+
+// One cluster of kBboxCluster CTAs per cloud: every CTA reduces a strided share of the points, the
+// partial boxes meet in the shared memory of CTA 0 (DSMEM stores + one cluster barrier).
+__global__ void __launch_bounds__(kBboxThreads)
 bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                    const int64_t* __restrict__ len1, const int64_t* __restrict__ len2, int P1, int P2,
                    bool self_knn, bool union_box, float* __restrict__ bbox,
                    unsigned* __restrict__ maxabs_bits) {
   __shared__ float sm[32];
-  const int n = blockIdx.x;
+  __shared__ float part[kBboxCluster][8];  // per CTA: min xyz, max xyz, max |p1|
+  const int n = blockIdx.y;
+  const int rank = static_cast<int>(bb_cluster_rank());
+  const int t0 = rank * kBboxThreads + threadIdx.x, stride = kBboxCluster * kBboxThreads;
   int64_t L2l = len2[n];
   const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > P2 ? P2 : L2l));
   const float* b = p2 + static_cast<size_t>(n) * P2 * 3;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int j = threadIdx.x; j < L2; j += blockDim.x) {
+  for (int j = t0; j < L2; j += stride) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const float v = b[static_cast<size_t>(j) * 3 + d];
@@ -109,7 +131,7 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
     none = none && L1 == 0;
     const float* a = p1 + static_cast<size_t>(n) * P1 * 3;
-    for (int j = threadIdx.x; j < L1; j += blockDim.x) {
+    for (int j = t0; j < L1; j += stride) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         const float v = a[static_cast<size_t>(j) * 3 + d];
@@ -123,25 +145,62 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     int64_t L1l = len1[n];
     const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
     const float* a = p1 + static_cast<size_t>(n) * P1 * 3;
-    for (int e = threadIdx.x; e < L1 * 3; e += blockDim.x) m1 = fmaxf(m1, fabsf(a[e]));
+    for (int e = t0; e < L1 * 3; e += stride) m1 = fmaxf(m1, fabsf(a[e]));
   }
-  float out[6];
+  float out[7];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     out[d] = block_reduce(mn[d], false, sm);
     out[3 + d] = block_reduce(mx[d], true, sm);
   }
-  m1 = block_reduce(m1, true, sm);
-  if (threadIdx.x == 0) {
+  out[6] = block_reduce(m1, true, sm);
+  if (threadIdx.x < 7) {
+    float v = out[0];
+#pragma unroll
+    for (int d = 1; d < 7; ++d) v = (threadIdx.x == d) ? out[d] : v;
+    bb_st_remote(&part[rank][threadIdx.x], 0, v);
+  }
+  bb_cluster_barrier();
+  if (rank == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int d = 0; d < 7; ++d) out[d] = part[0][d];
+    for (int r = 1; r < kBboxCluster; ++r) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        out[d] = fminf(out[d], part[r][d]);
+        out[3 + d] = fmaxf(out[3 + d], part[r][3 + d]);
+      }
+      out[6] = fmaxf(out[6], part[r][6]);
+    }
     float m = 0.0f;  // from the REDUCED box: threads that saw no point still hold the +-FLT_MAX seeds
 #pragma unroll
     for (int d = 0; d < 3; ++d) m = fmaxf(m, fmaxf(fabsf(out[d]), fabsf(out[3 + d])));
     if (none) m = 0.0f;
-    m = fmaxf(m, m1);
+    m = fmaxf(m, out[6]);
 #pragma unroll
     for (int d = 0; d < 6; ++d) bbox[n * 6 + d] = out[d];
     maxabs_bits[n] = __float_as_uint(m);
   }
+}
+
+int launch_bbox(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1, int P2,
+                bool self_knn, bool union_box, float* bbox, unsigned* maxabs_bits, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kBboxCluster, static_cast<unsigned>(N));
+  cfg.blockDim = dim3(kBboxThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kBboxCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, bbox_maxabs_kernel, p1, p2, len1, len2, P1, P2, self_knn, union_box, bbox,
+                                  maxabs_bits));
+  POPS_LAUNCH_OK("bbox_maxabs_kernel");
+  return POPS_OK;
 }
 
 __device__ __forceinline__ unsigned morton_code(const float* p, const float* bb, int axis_bits) {
@@ -172,7 +231,9 @@ __global__ void morton_keys_kernel(const float* __restrict__ p1, const float* __
     const int n = static_cast<int>(r / P), j = static_cast<int>(r % P);
     const int64_t L = second ? len1[n] : len2[n];
     const float* src = (second ? p1 : p2) + (static_cast<size_t>(n) * P + j) * 3;
-    unsigned low = 1u << kl.code_bits;  // padding entries sort after every valid point of the cloud
+    // padding entries carry the largest code and still end up after every valid point of the cloud:
+    // the radix sort is stable and they follow the valid points in the input (j >= L)
+    unsigned low = (1u << kl.code_bits) - 1u;
     if (j < L) low = morton_code(src, bbox + n * 6, kl.axis_bits);
     keys[e] = (second ? (1u << kl.tensor_shift) : 0u) | (static_cast<unsigned>(n) << kl.cloud_shift) | low;
     vals[e] = static_cast<unsigned>(j);
@@ -369,8 +430,10 @@ int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, con
                       int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st) {
   const int nbox = static_cast<int>(knn_order_num_boxes(P2));
   const KeyLayout kl = key_layout(N, P2, !self_knn);
-  bbox_maxabs_kernel<<<N, 1024, 0, st>>>(p1, p2, len1, len2, P1, P2, self_knn, false, b.bbox, b.maxabs_bits);
-  POPS_LAUNCH_OK("bbox_maxabs_kernel");
+  {
+    const int rc = launch_bbox(p1, p2, len1, len2, N, P1, P2, self_knn, false, b.bbox, b.maxabs_bits, st);
+    if (rc != POPS_OK) return rc;
+  }
   const int64_t items = static_cast<int64_t>(N) * P2 + (self_knn ? 0 : static_cast<int64_t>(N) * P1);
   {
     const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(items, 256), int64_t(num_sms()) * 16));
@@ -409,8 +472,10 @@ int knn_order_prepass_pair(const float* p1, const float* p2, const int64_t* len1
                            int P1, int P2, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
   const int nbox2 = static_cast<int>(knn_order_num_boxes(P2)), nbox1 = static_cast<int>(knn_order_num_boxes(P1));
   const KeyLayout kl = key_layout(N, std::max(P1, P2), true);
-  bbox_maxabs_kernel<<<N, 1024, 0, st>>>(p1, p2, len1, len2, P1, P2, false, true, a.bbox, a.maxabs_bits);
-  POPS_LAUNCH_OK("bbox_maxabs_kernel");
+  {
+    const int rc = launch_bbox(p1, p2, len1, len2, N, P1, P2, false, true, a.bbox, a.maxabs_bits, st);
+    if (rc != POPS_OK) return rc;
+  }
   const int64_t items = static_cast<int64_t>(N) * (P1 + P2);
   {
     const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(items, 256), int64_t(num_sms()) * 16));
