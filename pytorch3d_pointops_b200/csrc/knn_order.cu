@@ -203,25 +203,52 @@ int launch_bbox(const float* p1, const float* p2, const int64_t* len1, const int
   return POPS_OK;
 }
 
-__device__ __forceinline__ unsigned morton_code(const float* p, const float* bb, int axis_bits) {
-  unsigned code = 0;
+// Position of the point's grid cell on a space-filling curve (axis_bits bits per axis).  Hilbert
+// (Skilling's transpose form: "Programming the Hilbert curve", AIP Conf. Proc. 707, 2004) rather
+// than Morton: consecutive cells of a Hilbert curve are always neighbours, so a run of 64 sorted
+// points (a block) or of 128 sorted queries (a warp) has a tighter bounding box and the pruned
+// searches visit fewer blocks; the results never depend on the order.
+__device__ __forceinline__ unsigned curve_code(const float* p, const float* bb, int axis_bits, bool hilbert) {
   const float cells = static_cast<float>(1u << axis_bits);
+  unsigned X[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const float lo = bb[d], hi = bb[3 + d];
     const float ext = hi - lo;
     float t = ext > 0.0f ? (p[d] - lo) / ext * cells : 0.0f;
     t = fminf(fmaxf(t, 0.0f), cells - 1.0f);  // clamps p1 points outside p2's box; NaN -> 0
-    code |= spread3(static_cast<unsigned>(t)) << d;
+    X[d] = static_cast<unsigned>(t);
   }
-  return code;
+  if (!hilbert) return spread3(X[0]) | (spread3(X[1]) << 1) | (spread3(X[2]) << 2);
+  const unsigned M = 1u << (axis_bits - 1);
+  for (unsigned Q = M; Q > 1u; Q >>= 1) {  // inverse undo
+    const unsigned P = Q - 1u;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q) {
+        X[0] ^= P;
+      } else {
+        const unsigned t = (X[0] ^ X[i]) & P;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];  // Gray encode
+  X[2] ^= X[1];
+  unsigned t = 0u;
+  for (unsigned Q = M; Q > 1u; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1u;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
 }
 
 // element e in [0, N*P2) -> tensor 0 (p2); [N*P2, N*(P1+P2)) -> tensor 1 (p1)
 __global__ void morton_keys_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                    const int64_t* __restrict__ len1, const int64_t* __restrict__ len2,
                                    int N, int P1, int P2, bool self_knn, const float* __restrict__ bbox,
-                                   KeyLayout kl, unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
+                                   KeyLayout kl, bool hilbert, unsigned* __restrict__ keys,
+                                   unsigned* __restrict__ vals) {
   const int64_t total = static_cast<int64_t>(N) * P2 + (self_knn ? 0 : static_cast<int64_t>(N) * P1);
   for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
        e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -234,7 +261,7 @@ __global__ void morton_keys_kernel(const float* __restrict__ p1, const float* __
     // padding entries carry the largest code and still end up after every valid point of the cloud:
     // the radix sort is stable and they follow the valid points in the input (j >= L)
     unsigned low = (1u << kl.code_bits) - 1u;
-    if (j < L) low = morton_code(src, bbox + n * 6, kl.axis_bits);
+    if (j < L) low = curve_code(src, bbox + n * 6, kl.axis_bits, hilbert);
     keys[e] = (second ? (1u << kl.tensor_shift) : 0u) | (static_cast<unsigned>(n) << kl.cloud_shift) | low;
     vals[e] = static_cast<unsigned>(j);
   }
@@ -438,7 +465,7 @@ int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, con
   {
     const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(items, 256), int64_t(num_sms()) * 16));
     morton_keys_kernel<<<blocks, 256, 0, st>>>(p1, p2, len1, len2, N, P1, P2, self_knn, b.bbox, kl,
-                                               b.keys_in, b.vals_in);
+                                               get_option("knn_curve", 1) != 0, b.keys_in, b.vals_in);
     POPS_LAUNCH_OK("morton_keys_kernel");
   }
   size_t temp = b.cub_temp_bytes;
@@ -479,7 +506,8 @@ int knn_order_prepass_pair(const float* p1, const float* p2, const int64_t* len1
   const int64_t items = static_cast<int64_t>(N) * (P1 + P2);
   {
     const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(items, 256), int64_t(num_sms()) * 16));
-    morton_keys_kernel<<<blocks, 256, 0, st>>>(p1, p2, len1, len2, N, P1, P2, false, a.bbox, kl, a.keys_in, a.vals_in);
+    morton_keys_kernel<<<blocks, 256, 0, st>>>(p1, p2, len1, len2, N, P1, P2, false, a.bbox, kl,
+                                               get_option("knn_curve", 1) != 0, a.keys_in, a.vals_in);
     POPS_LAUNCH_OK("morton_keys_kernel");
   }
   size_t temp = a.cub_temp_bytes;
