@@ -48,7 +48,7 @@ const char* pops_last_error(void);
 int64_t pops_launch_count(void);
 
 /* Tuning / measurement knobs, also readable from the environment as POPS_<NAME> (upper case):
- *   knn_order   -1 auto | 0 never | 1 always use the Morton-ordered, box-pruned D=3 search
+ *   knn_order   -1 auto | 0 never | 1 always use the curve-ordered, box-pruned D=3 search
  *   knn_prune   1 | 0: visit every block (brute force in the same order; bench.py uses it to report
  *               the evaluation rate of the scan loop next to the pruned time)
  *   knn_q       queries per thread of the pruned search (4 | 2)

@@ -522,7 +522,7 @@ int launch_scan(const KnnScanParams& prm, int N, cudaStream_t st) {
   return POPS_OK;
 }
 
-// D = 3, L2, K <= 32: Morton-ordered clouds + box-pruned search (knn_order.cu, knn_prune.cu).
+// D = 3, L2, K <= 32: Hilbert-ordered clouds + box-pruned search (knn_order.cu, knn_prune.cu).
 // Worth its pre-pass once the cloud spans more than a few blocks.
 inline bool use_ordered(int64_t P2, int K) {
   const int force = get_option("knn_order", -1);  // test aid

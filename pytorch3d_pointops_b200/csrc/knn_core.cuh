@@ -1,4 +1,4 @@
-// Pieces shared by the KNN scan kernels (knn.cu: tiled brute force; knn_prune.cu: Morton-ordered,
+// Pieces shared by the KNN scan kernels (knn.cu: tiled brute force; knn_prune.cu: Hilbert-ordered,
 // box-pruned D = 3 search): constants, register sorting networks on 64-bit keys, and the
 // warp-converged candidate flush.
 #pragma once
@@ -286,7 +286,7 @@ __device__ __noinline__ float knn_flush_one(const float* tile, const unsigned sh
 
 
 
-// knn_prune.cu: D = 3, L2, K <= 32 search over the pre-pass output (Morton order, blocks, boxes).
+// knn_prune.cu: D = 3, L2, K <= 32 search over the pre-pass output (curve order, blocks, boxes).
 int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64_t* len2, int N, int P1,
                      int P2, int K, int64_t* idx, float* dists, cudaStream_t st);
 

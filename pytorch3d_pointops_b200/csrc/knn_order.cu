@@ -4,13 +4,14 @@
 // but the ORDER in which a warp meets the points decides how often a point beats the running
 // K-th distance (a "record"), and records are what the expensive flush path pays for.  With
 // points in random order a query sees ~K(1+ln(P/K)) records (~115 buffered groups at P=16384,
-// K=16).  If both clouds are sorted along a Morton curve and every warp starts scanning at its
+// K=16).  If both clouds are sorted along a space-filling curve (Hilbert; Morton kept as option
+// knn_curve=0) and every warp starts scanning at its
 // own queries' position and moves outward, the first points it meets are already its near
 // neighbours and the threshold is tight almost immediately (model: ~20 groups per query).
 //
 // This file builds that order:
 //   1. bbox_maxabs_kernel   per cloud: bounding box of the valid p2 points, max |coord| of p1, p2
-//   2. morton_keys_kernel   key = [tensor | cloud | Morton code], value = index in cloud (padding
+//   2. morton_keys_kernel   key = [tensor | cloud | curve code], value = index in cloud (padding
 //                           entries: largest code; the stable sort keeps them behind the valid points)
 //   3. cub::DeviceRadixSort one sort for every cloud of both tensors
 //   4. gather kernels       p2 -> blocks of 64 sorted points (rows x,y,z,w,orig_idx; + sentinels);
@@ -35,14 +36,14 @@ inline int clog2(int64_t n) {
 }
 
 struct KeyLayout {
-  int axis_bits;     // Morton bits per axis
+  int axis_bits;     // grid bits per axis
   int code_bits;     // 3 * axis_bits
   int cloud_shift;   // = code_bits (padding entries carry the largest code: see morton_keys_kernel)
   int tensor_shift;  // cloud_shift + clog2(N)
   int end_bit;
 };
 
-// Morton resolution follows the cloud size: ~16 cells per point order the blocks of 64 points as
+// Grid resolution follows the cloud size: ~16 cells per point order the blocks of 64 points as
 // well as 2^30 cells would, and every 8 key bits less is one radix-sort pass less (each pass is a
 // latency-bound ~15 us launch on these small inputs).
 inline KeyLayout key_layout(int64_t N, int64_t P2, bool two_tensors) {
@@ -126,7 +127,7 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     }
   }
   bool none = L2 == 0;
-  if (union_box) {  // pair pre-pass: one Morton grid over both clouds
+  if (union_box) {  // pair pre-pass: one grid over both clouds
     int64_t L1l = len1[n];
     const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
     none = none && L1 == 0;

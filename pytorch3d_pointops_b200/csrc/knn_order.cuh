@@ -8,8 +8,8 @@ namespace pops {
 struct KnnOrderBuffers {
   unsigned* maxabs_bits;  // [N]        max |coordinate| over p1 and p2 of the cloud (float bits)
   float* bbox;            // [N][6]     min xyz, max xyz of the valid p2 points
-  float* blocks;          // [N][nbox][5][kBoxPoints]  x, y, z, w=|p|^2, original index (u32 bits), Morton order
-  float4* qsorted;        // [N][P1]    x, y, z, original index (u32 bits), Morton order
+  float* blocks;          // [N][nbox][5][kBoxPoints]  x, y, z, w=|p|^2, original index (u32 bits), curve order
+  float4* qsorted;        // [N][P1]    x, y, z, original index (u32 bits), curve order
   unsigned* qhome;        // [N][P1]    position in the sorted p2 where the query's code would go
   float4* boxes;          // [N][nbox][2]  (min xyz, -), (max xyz, -) of every kBoxPoints sorted p2 points
   // scratch

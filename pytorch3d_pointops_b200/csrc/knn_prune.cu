@@ -1,10 +1,10 @@
-// D = 3, L2, K <= 32 nearest neighbours over Morton-ordered clouds with exact bounding-box pruning.
+// D = 3, L2, K <= 32 nearest neighbours over Hilbert-ordered clouds with exact bounding-box pruning.
 //
 // Same contract as every other KNN path (knn_cpu.cpp:13-69 of the reference: the K
 // lexicographically smallest (dist, idx), dist = the unfused float32 sum), different amount of
 // work: a (query, point) pair is evaluated only if the point's block can still hold a neighbour.
 //
-//   pre-pass (knn_order.cu)   both clouds sorted along a Morton curve; p2 cut into blocks of 64
+//   pre-pass (knn_order.cu)   both clouds sorted along a Hilbert curve; p2 cut into blocks of 64
 //                             points (1280 contiguous bytes: rows x, y, z, w=|p|^2, original index)
 //                             with one bounding box each.
 //   this kernel               one WARP = Q*32 consecutive sorted queries, fully independent of the
@@ -39,7 +39,7 @@ namespace {
 
 constexpr int kRingSlots = 4;   // blocks resident per warp
 constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
-// candidate groups a query can buffer between flushes (a query meets ~K/4 + Morton scatter groups in total)
+// candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total)
 constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : 24; }
 constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
 constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
@@ -276,7 +276,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   const float E = fmaf(M * M, 1.52587890625e-05f /* 2^-16 */, 1e-37f);
   constexpr uint32_t CB = sizeof(CID);
   constexpr uint32_t CBYTES = QPB * CB;  // bytes between consecutive entries of one candidate buffer
-  const int slot0 = warp * (Q * 32) + lane;  // a warp's Q*32 queries are contiguous in Morton order
+  const int slot0 = warp * (Q * 32) + lane;  // a warp's Q*32 queries are contiguous in curve order
   const int wq0 = q_base + warp * (Q * 32);
   float a[Q][3];   // -2 q_d (FFMA2 takes it as a broadcast scalar operand)
   float T[Q];      // filter threshold

@@ -307,7 +307,7 @@ def test_pair_search_matches_two_calls():
 
 @pytest.fixture
 def force_ordered():
-    """Route every D=3 L2 K<=32 call through the Morton-ordered, box-pruned search, whatever P2."""
+    """Route every D=3 L2 K<=32 call through the curve-ordered, box-pruned search, whatever P2."""
     from pytorch3d_pointops_b200 import _lib
 
     lib = _lib.load()
