@@ -79,3 +79,44 @@ def test_chamfer_config2_vs_oracle(oracle):
         assert torch.allclose(a.detach().cpu(), b.detach(), rtol=1e-5, atol=1e-8)
     for a, b in zip(g_grads, o_grads):
         assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-5 * float(b.abs().max()))
+
+
+def test_chamfer_one_node_matches_per_direction_path():
+    """The two-sided call as ONE autograd node (pair pre-pass, shared output tensor, accumulate-mode
+    backward) against the per-direction nodes (forced by weights = 1): losses and all gradients,
+    every batch / point reduction it serves, both norms, with and without features, ragged clouds
+    including a 3-point one, and an upstream gradient that differs per output."""
+    from pytorch3d_pointops_b200.functions.chamfer import chamfer_distance
+
+    gen = torch.Generator().manual_seed(5)
+    N, P1, P2 = 5, 1500, 2100
+    x, y = torch.rand(N, P1, 3, generator=gen), torch.rand(N, P2, 3, generator=gen) * 0.8 + 0.3
+    xl = torch.randint(1024, P1 + 1, (N,), generator=gen)
+    yl = torch.randint(1024, P2 + 1, (N,), generator=gen)
+    xl[1], yl[2] = 3, 1
+    xn, yn = torch.randn(N, P1, 3, generator=gen), torch.randn(N, P2, 3, generator=gen)
+    xc, yc = torch.rand(N, P1, 4, generator=gen), torch.rand(N, P2, 4, generator=gen)
+    ones = torch.ones(N, device=DEV)
+
+    def run(weights, br, pr, norm, feats):
+        ts = [t.to(DEV).clone().requires_grad_(True) for t in (x, y, xn, yn, xc, yc)]
+        kw = dict(x_lengths=xl.to(DEV), y_lengths=yl.to(DEV), weights=weights, batch_reduction=br,
+                  point_reduction=pr, norm=norm)
+        if feats:
+            kw.update(x_features={"normals": ts[2], "colors": ts[4]}, y_features={"normals": ts[3], "colors": ts[5]},
+                      feature_names=["normals", "colors"])
+        loss, lf = chamfer_distance(ts[0], ts[1], **kw)
+        outs = [loss] + ([lf["normals"], lf["colors"]] if feats else [])
+        up = [torch.linspace(0.5, 1.5, o.numel(), device=DEV).view(o.shape) * (i + 1) for i, o in enumerate(outs)]
+        torch.autograd.backward(outs, up)
+        return outs, [t.grad for t in (ts if feats else ts[:2])]
+
+    for br in (None, "sum", "mean"):
+        for pr in ("sum", "mean"):
+            for norm, feats in ((2, True), (1, False), (2, False)):
+                a_out, a_g = run(None, br, pr, norm, feats)
+                b_out, b_g = run(ones, br, pr, norm, feats)
+                for a, b in zip(a_out, b_out):
+                    assert a.shape == b.shape and torch.allclose(a, b, rtol=2e-6, atol=1e-7), (br, pr, norm, feats)
+                for a, b in zip(a_g, b_g):
+                    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max())), (br, pr, norm, feats)
