@@ -50,7 +50,8 @@ inline KeyLayout key_layout(int64_t N, int64_t P2, bool two_tensors) {
   KeyLayout k;
   const int cl = clog2(std::max<int64_t>(N, 1));
   const int want = (clog2(std::max<int64_t>(P2, 1)) + 4 + 2) / 3;
-  k.axis_bits = std::min(std::min(10, std::max(1, (30 - cl) / 3)), std::max(4, want));
+  const int forced = get_option("knn_axis_bits", 0);  // tuning aid
+  k.axis_bits = std::min(std::min(10, std::max(1, (30 - cl) / 3)), forced > 0 ? forced : std::max(4, want));
   k.code_bits = 3 * k.axis_bits;
   k.cloud_shift = k.code_bits;
   k.tensor_shift = k.cloud_shift + cl;
