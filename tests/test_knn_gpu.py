@@ -381,7 +381,7 @@ def test_pruned_search_both_thread_shapes(oracle):
             gi, gd = _C.knn_points_idx(p.to(DEV), p.to(DEV), L.to(DEV), L.to(DEV), 2, 16, -1)
             assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od), q
     finally:
-        lib.pops_set_option(b"knn_q", 4)
+        lib.pops_set_option(b"knn_q", 0)
     big = torch.rand(1, 300000, 3, generator=gen)
     q1 = big[:, :256].contiguous()
     Lb, Lq = torch.tensor([300000]), torch.tensor([256])
