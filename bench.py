@@ -592,7 +592,7 @@ def run_ours(args, rank, world, local_rank):
     alg_flops = 3.0 * D * pairs_per_step  # D sub + D mul + D add per pair
     achieved = alg_flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
     roofline = {
-        "kernel": "knn_prune_kernel<Q=4,KT=16> (Hilbert-ordered blocks, exact box pruning)", "bound": "fp32",
+        "kernel": "knn_prune_kernel<Q=1,KT=16> (Hilbert-ordered blocks, exact box pruning)", "bound": "fp32",
         "achieved": achieved,
         "peak": fp32_theory, "unit": "TFLOP/s", "frac": (achieved / fp32_theory) if achieved else None,
         "traffic": ncu_traffic_bytes("r01_knn_prune_ncu_full.txt"),

@@ -51,7 +51,7 @@ int64_t pops_launch_count(void);
  *   knn_order   -1 auto | 0 never | 1 always use the curve-ordered, box-pruned D=3 search
  *   knn_prune   1 | 0: visit every block (brute force in the same order; bench.py uses it to report
  *               the evaluation rate of the scan loop next to the pruned time)
- *   knn_q       queries per thread of the pruned search (0 auto by K | 4 | 2)
+ *   knn_q       queries per thread of the pruned search (0 auto by K | 4 | 2 | 1)
  *   knn_stats   1: collect block / flush counters (pops_knn_debug_stats)
  *   knn_curve   1 Hilbert (default) | 0 Morton order in the spatial pre-pass; knn_axis_bits n: grid bits
  *               per axis of the curve codes (0 = sized to the cloud); knn_pair 1 | 0: one pre-pass for

@@ -221,9 +221,10 @@ __device__ __noinline__ float prune_flush_one(const float* __restrict__ blocks_n
 }
 
 template <int Q, int KT, int THREADS, typename CID>
-__global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : 8)))
+__global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : ((Q == 1 && KT == 1) ? 10 : 8))))
 knn_prune_kernel(const KnnPruneParams prm) {
   constexpr int QPB = Q * THREADS, S = kRingSlots;
+  constexpr bool REFINE = KT <= 4;  // per-query box test before a block is scanned
   constexpr int NSEED = KT <= 4 ? 3 : (KT <= 16 ? 2 : 4);  // >= 4 seed points per tournament subset; small K: home +- 1 keeps the worst bound of the warp down
   static_assert(NSEED <= S, "the seed blocks sit in the ring together");
   using SM = PruneSmem<Q, THREADS, CID, KT>;
@@ -404,7 +405,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
     if (lane == s) {
       slot_lb = picked_lb;
       slot_blk = b;
-      if (KT <= 4) {
+      if (REFINE) {
         slot_lo = boxes_n[static_cast<size_t>(b) * 2];  // consumed when the block is scanned: latency hidden
         slot_hi = boxes_n[static_cast<size_t>(b) * 2 + 1];
       }
@@ -481,7 +482,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
     bool wanted = __shfl_sync(FULL, slot_lb, s) <= dkmax;  // dkmax may have dropped since the fetch
     // (small K only: the 6 extra registers per lane cost the K = 16 / 32 variants, which sit at their
     //  register cap, more in spills than the 25 % fewer blocks give back: 1.28 vs 1.21 ms on the T shape)
-    if (KT <= 4 && wanted && prm.prune) {
+    if (REFINE && wanted && prm.prune) {
       // per-query refinement: the warp-wide test used the box of ALL its queries against the LARGEST
       // bound; scan only if some query's own bound reaches the block (same exact lower bound, with
       // the query as a degenerate box)
@@ -586,11 +587,12 @@ int launch_prune_k(const KnnPruneParams& prm, int N, cudaStream_t st) {
 int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64_t* len2, int N, int P1,
                      int P2, int K, int64_t* idx, float* dists, cudaStream_t st) {
   const int prune = get_option("knn_prune", 1);  // 0: visit every block (measurement aid)
-  // queries per thread: 2 for K <= 4 and K > 16 (measured on the T and chamfer shapes with the Hilbert
-  // order: 0.43 vs 0.47 ms at K=4, 0.37 vs 0.40 ms for the chamfer pair, 2.38 vs 2.48 ms at K=32), 4
-  // for 4 < K <= 16; knn_q = 2 | 4 forces one (tuning aid)
+  // queries per thread.  With the Hilbert order one query per thread (a warp = 32 consecutive sorted
+  // queries, 128 registers, 8-10 CTAs per SM) wins on the T and chamfer shapes: K=16 0.955 vs 1.06 ms
+  // (Q=4), K=4 0.41 vs 0.46, chamfer pair 0.32 vs 0.40; K=32 (218 registers at Q=1) 2.38 ms at Q=2.
+  // knn_q = 1 | 2 | 4 forces one (tuning aid)
   int q = get_option("knn_q", 0);
-  if (q != 2 && q != 4) q = (K <= 4 || K > 16) ? 2 : 4;
+  if (q != 1 && q != 2 && q != 4) q = K > 16 ? 2 : 1;
   KnnPruneParams prm;
   prm.qsorted = ob.qsorted; prm.qhome = ob.qhome; prm.blocks = ob.blocks; prm.boxes = ob.boxes;
   prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits; prm.idx = idx; prm.dists = dists;
@@ -600,6 +602,7 @@ int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64
   prm.stats = nullptr;
   if (stats) POPS_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&prm.stats), g_knn_stats));
   const bool narrow = int64_t(prm.nbox) * kBlockGroups <= 65536;
+  if (q == 1) return narrow ? launch_prune_k<1, unsigned short>(prm, N, st) : launch_prune_k<1, unsigned>(prm, N, st);
   if (q == 2) return narrow ? launch_prune_k<2, unsigned short>(prm, N, st) : launch_prune_k<2, unsigned>(prm, N, st);
   return narrow ? launch_prune_k<4, unsigned short>(prm, N, st) : launch_prune_k<4, unsigned>(prm, N, st);
 }

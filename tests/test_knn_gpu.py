@@ -376,7 +376,7 @@ def test_pruned_search_both_thread_shapes(oracle):
     L = torch.tensor([5000, 3333])
     oi, od = oracle.knn_points_idx(p, p, L, L, 2, 16, threads=8)
     try:
-        for q in (2, 4):
+        for q in (1, 2, 4):
             lib.pops_set_option(b"knn_q", q)
             gi, gd = _C.knn_points_idx(p.to(DEV), p.to(DEV), L.to(DEV), L.to(DEV), 2, 16, -1)
             assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od), q
