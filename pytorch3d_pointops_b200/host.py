@@ -23,14 +23,14 @@ class HostKnn:
     out_idx (N,P1,K) int64 and out_dists (N,P1,K) float32 are pinned host tensors owned by this
     object and overwritten by every call."""
 
-    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=4, graph: bool = True):
+    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=6, graph: bool = True):
         self.device = torch.device(device)
         self.N, self.P1, self.P2, self.D, self.K = N, P1, P2, D, K
         # `slices`: a count (equal slices) or an explicit list of slice sizes in clouds.  Measured on
-        # the B=32 x P=16384 x K=16 shape (D2H of the 100 MB result alone: 1.77 ms): 1 slice 3.19 ms,
-        # 2: 2.71, 3: 2.55, 4: 2.50, 6: 2.93, 8: 3.18 -- a slice below one wave of CTAs (~10 clouds)
-        # still costs one CTA's latency (~0.45 ms), so more slices stretch the search; searching the
-        # slices on 2-3 alternating streams evens that out but ends at the same 2.46-2.56 ms.
+        # the B=32 x P=16384 x K=16 shape (D2H of the 100 MB result alone: 1.77-1.85 ms): 2 slices
+        # 2.52 ms, 3: 2.40, 4: 2.32, 5: 2.30, 6: 2.28, 8: 2.30 -- a slice below one wave of CTAs still
+        # costs one CTA's latency, so many slices stretch the search; searching the slices on 2-3
+        # alternating streams or uneven slice sizes end at the same floor.
         if isinstance(slices, (list, tuple)):
             sizes = [int(v) for v in slices if int(v) > 0]
             assert sum(sizes) == N, "slice sizes must add up to the batch"
