@@ -599,7 +599,8 @@ def run_ours(args, rank, world, local_rank):
         "peak": fp32_theory, "unit": "TFLOP/s", "frac": (achieved / fp32_theory) if achieved else None,
         "traffic": ncu_traffic_bytes("r01_knn_prune_ncu_full.txt"),
         "traffic_note": "DRAM bytes per launch from profiles/r01_knn_prune_ncu_full.txt (same shape); the "
-                        "algorithmic minimum is 6.3 MB of points in + 100.7 MB of (idx, dists) out",
+                        "algorithmic minimum is 6.3 MB of points in + 100.7 MB of (idx, dists) out -- part of the output is still "
+                        "in the 126 MB L2 when the kernel ends, so the capture can read below that",
         "note": "achieved = ALGORITHMIC flop (3*D per (query, point) pair of the brute-force definition, SURVEY 8d) "
                 "/ kernel time; the kernel proves most blocks irrelevant and skips them, so frac can exceed "
                 "what any brute-force scan reaches -- see executed_pair_fraction and bruteforce",
