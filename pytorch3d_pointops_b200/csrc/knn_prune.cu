@@ -578,6 +578,7 @@ int launch_prune_k(const KnnPruneParams& prm, int N, cudaStream_t st) {
   constexpr int THREADS = 64;
   if (prm.K == 1) return launch_prune<Q, 1, THREADS, CID>(prm, N, st);
   if (prm.K <= 4) return launch_prune<Q, 4, THREADS, CID>(prm, N, st);
+  if (prm.K <= 8) return launch_prune<Q, 8, THREADS, CID>(prm, N, st);
   if (prm.K <= 16) return launch_prune<Q, 16, THREADS, CID>(prm, N, st);
   return launch_prune<Q, 32, THREADS, CID>(prm, N, st);
 }

@@ -12,7 +12,7 @@ def timeit(fn, n=20):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
-for q in (4, 2):
+for q in (0,):
     lib.pops_set_option(b"knn_q", q)
-    for K in (1, 4, 8, 16, 32):
+    for K in (1, 4, 6, 8, 12, 16, 32):
         print(f"Q={q} K={K}: {timeit(lambda: _C.knn_points_idx(p, p, L, L, 2, K, -1)):.4f} ms")
