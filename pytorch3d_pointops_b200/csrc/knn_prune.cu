@@ -593,7 +593,9 @@ int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64
   // (Q=4), K=4 0.41 vs 0.46, chamfer pair 0.32 vs 0.40; K=32 (218 registers at Q=1) 2.38 ms at Q=2.
   // knn_q = 1 | 2 | 4 forces one (tuning aid)
   int q = get_option("knn_q", 0);
-  if (q != 1 && q != 2 && q != 4) q = K > 16 ? 2 : 1;
+  // (very large clouds: every warp tests all nbox / 32 chunks of boxes, which 4x more warps repeat 4x as
+  //  often -- 300 K points, K=16: 0.82 ms at Q=4 vs 0.93 at Q=1; at 100 K points Q=1 is still ahead)
+  if (q != 1 && q != 2 && q != 4) q = P2 >= 262144 ? 4 : (K > 16 ? 2 : 1);
   KnnPruneParams prm;
   prm.qsorted = ob.qsorted; prm.qhome = ob.qhome; prm.blocks = ob.blocks; prm.boxes = ob.boxes;
   prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits; prm.idx = idx; prm.dists = dists;
