@@ -228,6 +228,9 @@ int pops_point_covariances(const float* x, const int64_t* idx, const int64_t* le
  *   grad_xf[f], grad_yf[f] are zero-filled and written by the call (float atomics on the y side);
  *   accumulate != 0: the buffers are NOT cleared and the call adds to them -- the y -> x direction of
  *   a two-sided loss lands on the x -> y direction's gradients without a separate sum.
+ *   g_broadcast != 0 (point_reduction sum / mean only): g_cham is ONE scalar and g_feat holds one
+ *   scalar per feature, shared by all N clouds (the gradient of a batch-reduced loss); g_scale
+ *   multiplies them (1/N for a batch mean, else 1).
  * ------------------------------------------------------------------------------------------- */
 int pops_chamfer_forward(const float* dists, const int64_t* idx, const int64_t* lengths1,
                          const int64_t* lengths2, const float* weights, int64_t N, int64_t P1,
@@ -240,7 +243,8 @@ int pops_chamfer_backward(const float* x, const float* y, const int64_t* idx, co
                           const float* const* yf, const int64_t* chans, int point_reduction,
                           int abs_cosine, const float* g_cham, const float* g_feat,
                           const int64_t* argmax, float* grad_x, float* grad_y, float* const* grad_xf,
-                          float* const* grad_yf, int accumulate, pops_stream_t stream);
+                          float* const* grad_yf, int accumulate, int g_broadcast, float g_scale,
+                          pops_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -411,10 +411,11 @@ def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point
 
 
 def chamfer_backward(x, y, idx, lengths1, lengths2, weights, norm, xfs, yfs, point_reduction, abs_cosine,
-                     g_cham, g_feat, argmax, into=None):
+                     g_cham, g_feat, argmax, into=None, g_broadcast=False, g_scale=1.0):
     """Returns (grad_x, grad_y, [grad_xf...], [grad_yf...]).
     into: optional (grad_x, grad_y, [grad_xf...], [grad_yf...]) of already initialised buffers the
-    call ADDS to (accumulate mode of pops_chamfer_backward)."""
+    call ADDS to (accumulate mode of pops_chamfer_backward).
+    g_broadcast: g_cham is one scalar and g_feat one scalar per feature for all clouds, times g_scale."""
     lib = _lib.load()
     x = _cuda_f32(x, "x")
     y = _cuda_f32(y, "y")
@@ -439,7 +440,8 @@ def chamfer_backward(x, y, idx, lengths1, lengths2, weights, norm, xfs, yfs, poi
                                        _ptr_array(xfs), _ptr_array(yfs), _chan_array(xfs),
                                        RED[point_reduction], int(bool(abs_cosine)), g_cham.data_ptr(),
                                        _ptr(g_feat), _ptr(argmax), grad_x.data_ptr(), grad_y.data_ptr(),
-                                       _ptr_array(gxf), _ptr_array(gyf), int(into is not None), _stream(x))
+                                       _ptr_array(gxf), _ptr_array(gyf), int(into is not None), int(bool(g_broadcast)),
+                                       float(g_scale), _stream(x))
     _lib.check(st, "chamfer_backward")
     return grad_x, grad_y, gxf, gyf
 

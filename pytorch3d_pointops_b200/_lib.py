@@ -47,7 +47,7 @@ SIGNATURES = {
     "pops_gather_backward": (c_int, [_P, _P, _P] + [c_int64] * 5 + [c_int, _P, _P]),
     "pops_chamfer_forward": (c_int, [_P] * 5 + [c_int64] * 3 + [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
     "pops_chamfer_backward": (c_int, [_P] * 6 + [c_int64] * 4 + [c_int, c_int, _P, _P, _P, c_int, c_int]
-                              + [_P] * 7 + [c_int, _P]),
+                              + [_P] * 7 + [c_int, c_int, c_float, _P]),
 }
 
 

@@ -209,7 +209,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                    int D, ChamferFeat ft, int reduction, int abs_cosine, int N,
                    const float* __restrict__ g_cham, const float* __restrict__ g_feat,
                    const int64_t* __restrict__ argmax, float* __restrict__ grad_x,
-                   float* __restrict__ grad_y, int acc) {
+                   float* __restrict__ grad_y, int acc, int g_bcast, float g_scale) {
   const int n = blockIdx.y;
   int64_t L1l = len1[n], L2l = len2[n];
   const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
@@ -228,7 +228,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
     float gd;
     if (reduction == kRedNone) gd = g_cham[static_cast<size_t>(n) * P1 + i] * w;
     else if (reduction == kRedMax) gd = (i == amax) ? g_cham[n] * w : 0.0f;
-    else gd = g_cham[n] * w * (reduction == kRedMean ? inv_len : 1.0f);
+    else gd = g_cham[g_bcast ? 0 : n] * g_scale * w * (reduction == kRedMean ? inv_len : 1.0f);  // g_bcast: one upstream scalar for every cloud
     const int64_t j = in[i];
     if (gd != 0.0f && !y_empty) {
       for (int d = 0; d < D; ++d) {
@@ -244,7 +244,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
       const int C = ft.chans[f];
       float gf;
       if (reduction == kRedNone) gf = g_feat[(static_cast<size_t>(f) * N + n) * P1 + i] * w;
-      else gf = g_feat[static_cast<size_t>(f) * N + n] * w * (reduction == kRedMean ? inv_len : 1.0f);
+      else gf = g_feat[g_bcast ? static_cast<size_t>(f) : static_cast<size_t>(f) * N + n] * g_scale * w * (reduction == kRedMean ? inv_len : 1.0f);
       if (gf == 0.0f) continue;
       const float* a = ft.xf[f] + (static_cast<size_t>(n) * P1 + i) * C;
       const float* b = ft.yf[f] + (static_cast<size_t>(n) * P2 + j) * C;
@@ -339,10 +339,12 @@ extern "C" int pops_chamfer_backward(const float* x, const float* y, const int64
                                      int abs_cosine, const float* g_cham, const float* g_feat,
                                      const int64_t* argmax, float* grad_x, float* grad_y,
                                      float* const* grad_xf, float* const* grad_yf, int accumulate,
-                                     pops_stream_t stream) {
+                                     int g_broadcast, float g_scale, pops_stream_t stream) {
   POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
   POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0, "negative size");
   POPS_CHECK_ARG(point_reduction >= 0 && point_reduction <= 3, "bad point_reduction");
+  POPS_CHECK_ARG(!g_broadcast || point_reduction == kRedSum || point_reduction == kRedMean,
+                 "g_broadcast needs point_reduction sum or mean");
   ChamferFeat ft;
   POPS_CHECK_ARG(fill_feats(&ft, num_feats, xf, yf, grad_xf, grad_yf, chans) == 0, "too many features (max 8)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -361,11 +363,11 @@ extern "C" int pops_chamfer_backward(const float* x, const float* y, const int64
   if (norm == 2)
     chamfer_bwd_kernel<2><<<bgrid, kBwdThreads, 0, st>>>(
         x, y, idx, lengths1, lengths2, weights, int(P1), int(P2), int(D), ft, point_reduction, abs_cosine,
-        int(N), g_cham, g_feat, argmax, grad_x, grad_y, accumulate ? 1 : 0);
+        int(N), g_cham, g_feat, argmax, grad_x, grad_y, accumulate ? 1 : 0, g_broadcast ? 1 : 0, g_scale);
   else
     chamfer_bwd_kernel<1><<<bgrid, kBwdThreads, 0, st>>>(
         x, y, idx, lengths1, lengths2, weights, int(P1), int(P2), int(D), ft, point_reduction, abs_cosine,
-        int(N), g_cham, g_feat, argmax, grad_x, grad_y, accumulate ? 1 : 0);
+        int(N), g_cham, g_feat, argmax, grad_x, grad_y, accumulate ? 1 : 0, g_broadcast ? 1 : 0, g_scale);
   POPS_LAUNCH_OK("chamfer_bwd_kernel");
   return POPS_OK;
 }

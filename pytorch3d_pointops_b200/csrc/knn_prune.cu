@@ -40,7 +40,7 @@ namespace {
 constexpr int kRingSlots = 4;   // blocks resident per warp
 constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
 // candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total)
-constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : 24; }
+constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : 24); }
 constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
 constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
 constexpr uint32_t kBlockBytes = kBlockFloats * 4;

@@ -160,13 +160,12 @@ class _ChamferBoth(torch.autograd.Function):
         yfs = list(ctx.saved_tensors[6 + nfeat:])
         N, P1, P2 = x.shape[0], x.shape[1], y.shape[1]
         like = next(g for g in grads if g is not None)
-        g = torch.stack([gi if gi is not None else torch.zeros_like(like) for gi in grads], 0).float()
-        if batch_mode != 0:  # scalars: every cloud receives the same gradient
-            if batch_mode == 2:
-                g = g / max(N, 1)
-            g = g.view(1 + nfeat, 1).expand(1 + nfeat, N)
-        g = g.contiguous()
-        g_cham, g_feat = g[0], (g[1:] if nfeat else None)
+        g = torch.stack([gi if gi is not None else torch.zeros_like(like) for gi in grads], 0).float().contiguous()
+        # batch-reduced loss: the (1+F) upstream scalars serve every cloud (the kernel broadcasts and
+        # scales them), no (1+F, N) expansion on the way
+        bcast = batch_mode != 0
+        g_scale = 1.0 / max(N, 1) if batch_mode == 2 else 1.0
+        g_cham, g_feat = g[0:1] if bcast else g[0], (g[1:] if nfeat else None)
         # one zero fill for every gradient, carved into the per-tensor views
         srcs = [x, y] + xfs + yfs
         flat = torch.zeros(sum(t.numel() for t in srcs), dtype=torch.float32, device=x.device)
@@ -176,9 +175,9 @@ class _ChamferBoth(torch.autograd.Function):
             off += t.numel()
         gx, gy, gxf, gyf = views[0], views[1], views[2:2 + nfeat], views[2 + nfeat:]
         _C.chamfer_backward(x, y, idx1.view(N, P1), x_lengths, y_lengths, None, norm, xfs, yfs, point_reduction,
-                            abs_cosine, g_cham, g_feat, None, into=(gx, gy, gxf, gyf))
+                            abs_cosine, g_cham, g_feat, None, into=(gx, gy, gxf, gyf), g_broadcast=bcast, g_scale=g_scale)
         _C.chamfer_backward(y, x, idx2.view(N, P2), y_lengths, x_lengths, None, norm, yfs, xfs, point_reduction,
-                            abs_cosine, g_cham, g_feat, None, into=(gy, gx, gyf, gxf))
+                            abs_cosine, g_cham, g_feat, None, into=(gy, gx, gyf, gxf), g_broadcast=bcast, g_scale=g_scale)
         return (gx, gy) + (None,) * 7 + tuple(gxf) + tuple(gyf)
 
 
