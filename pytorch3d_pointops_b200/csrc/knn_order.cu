@@ -19,6 +19,7 @@
 //                           position in the sorted p2 (binary search of its code)
 //   5. box_kernel           bounding box of every block
 // Results never depend on the order: the exact 64-bit key (dist, ORIGINAL index) decides.
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cfloat>
@@ -416,6 +417,237 @@ __global__ void gather_pair_kernel(const float* __restrict__ pts, const int64_t*
   dst[4 * kBoxPoints] = __uint_as_float(orig);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused pre-pass for clouds that fit one CTA (<= 1024 * ITEMS = 8192 points per tensor): ONE launch does
+// what bbox + keys + device radix sort + gathers + boxes (11-14 launches) do -- these shapes are
+// launch-bound (chamfer: 26 launches per step), and a 16 K-key sort is a shared-memory job.
+//   grid (T, N), cluster (T, 1, 1): CTA t of the cluster orders tensor t of cloud n (t = 0: p2, the
+//   blocks of search `a`; t = 1: p1, the queries of `a` and, in pair mode, the blocks of `b`).
+//   1. box + max |coordinate| of the CTA's own points; the two CTAs exchange them over DSMEM (the
+//      grid of the curve codes spans both clouds);
+//   2. curve codes, cub::BlockRadixSort on (code, index) in shared memory (stable: padding entries
+//      carry the largest code and follow the valid points);
+//   3. straight from the sorted registers: block rows, per-block boxes (shuffle reduction over the
+//      64 / ITEMS threads of a block), sorted queries, sorted codes;
+//   4. cluster barrier, then every query's home = lower bound of its code among the OTHER tensor's
+//      sorted codes.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 1024;
+
+struct FusedOrderParams {
+  const float* p[2];         // [0] = p2, [1] = p1
+  const int64_t* len[2];
+  int P[2];
+  int mode;                  // 0 self (one tensor), 1 single search (a), 2 pair (a and b)
+  int axis_bits, hilbert;
+  KnnOrderBuffers a, b;
+  unsigned* codes[2];        // sorted codes per tensor: [N][P[t]]
+};
+
+template <int ITEMS>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+order_cloud_kernel(const FusedOrderParams prm) {
+  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS, unsigned>;
+  extern __shared__ __align__(16) unsigned char fsm[];
+  typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(fsm);
+  __shared__ float red[32];
+  __shared__ float part[2][8];  // per CTA of the cluster: min xyz, max xyz
+  __shared__ float bb[6];
+  const int T = gridDim.x;
+  const int t = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const int P = prm.P[t];
+  int64_t Ll = prm.len[t][n];
+  const int L = static_cast<int>(Ll < 0 ? 0 : (Ll > P ? P : Ll));
+  const float* pts = prm.p[t] + static_cast<size_t>(n) * P * 3;
+
+  // ---- 1. box of both tensors ---------------------------------------------------------------------
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int j = tid; j < L; j += kFusedThreads) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = pts[static_cast<size_t>(j) * 3 + d];
+      mn[d] = fminf(mn[d], v);
+      mx[d] = fmaxf(mx[d], v);
+    }
+  }
+  float out[6];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    out[d] = block_reduce(mn[d], false, red);
+    out[3 + d] = block_reduce(mx[d], true, red);
+  }
+  if (tid < 6) {
+    float v = out[0];
+#pragma unroll
+    for (int d = 1; d < 6; ++d) v = (tid == d) ? out[d] : v;
+    for (int r = 0; r < T; ++r) bb_st_remote(&part[t][tid], static_cast<uint32_t>(r), v);
+  }
+  if (T > 1) bb_cluster_barrier(); else __syncthreads();
+  if (tid < 3) {
+    float lo = part[0][tid], hi = part[0][3 + tid];
+    if (T > 1) {
+      lo = fminf(lo, part[1][tid]);
+      hi = fmaxf(hi, part[1][3 + tid]);
+    }
+    bb[tid] = lo;
+    bb[3 + tid] = hi;
+  }
+  __syncthreads();
+  if (t == 0 && tid == 0) {
+    float m = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) m = fmaxf(m, fmaxf(fabsf(bb[d]), fabsf(bb[3 + d])));
+    if (bb[0] == FLT_MAX) m = 0.0f;  // no valid point in either tensor
+#pragma unroll
+    for (int d = 0; d < 6; ++d) prm.a.bbox[n * 6 + d] = bb[d];
+    prm.a.maxabs_bits[n] = __float_as_uint(m);
+  }
+
+  // ---- 2. codes + sort (blocked arrangement: thread tid holds positions tid*ITEMS + i) ------------
+  const int code_bits = 3 * prm.axis_bits;
+  unsigned keys[ITEMS], vals[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int j = tid * ITEMS + i;
+    vals[i] = static_cast<unsigned>(j);
+    keys[i] = (1u << code_bits) - 1u;  // padding: largest code, kept behind the valid points by stability
+    if (j < L) keys[i] = curve_code(pts + static_cast<size_t>(j) * 3, bb, prm.axis_bits, prm.hilbert != 0);
+  }
+  Sort(temp).Sort(keys, vals, 0, code_bits);
+
+  // ---- 3. outputs from the sorted registers -----------------------------------------------------
+  const bool blocks_role = (t == 0) || prm.mode == 2;           // this tensor is scanned as blocks
+  const bool query_role = (t == 1) || prm.mode != 1;            // ... and / or asked as queries
+  const KnnOrderBuffers& blk = (t == 0) ? prm.a : prm.b;        // search that scans this tensor
+  const KnnOrderBuffers& qry = (t == 1 || prm.mode == 0) ? prm.a : prm.b;  // search that asks it
+  const int nbox = static_cast<int>((((P + kBoxPoints - 1) / kBoxPoints) + 31) / 32 * 32);
+  const float INF = __int_as_float(0x7f800000);
+  float bmn[3] = {INF, INF, INF}, bmx[3] = {-INF, -INF, -INF};
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int s = tid * ITEMS + i;
+    const unsigned o = vals[i];
+    float x = 0.f, y = 0.f, z = 0.f, w = INF;
+    unsigned orig = kNoPoint;
+    if (s < L) {
+      const float* src = pts + static_cast<size_t>(o) * 3;
+      x = src[0]; y = src[1]; z = src[2];
+      w = fmaf(z, z, fmaf(y, y, x * x));
+      orig = o;
+      bmn[0] = fminf(bmn[0], x); bmn[1] = fminf(bmn[1], y); bmn[2] = fminf(bmn[2], z);
+      bmx[0] = fmaxf(bmx[0], x); bmx[1] = fmaxf(bmx[1], y); bmx[2] = fmaxf(bmx[2], z);
+    }
+    if (blocks_role && s < nbox * kBoxPoints) {
+      float* dst = blk.blocks + (static_cast<size_t>(n) * nbox + s / kBoxPoints) * kBlockFloats + (s % kBoxPoints);
+      dst[0] = x;
+      dst[kBoxPoints] = y;
+      dst[2 * kBoxPoints] = z;
+      dst[3 * kBoxPoints] = w;
+      dst[4 * kBoxPoints] = __uint_as_float(orig);
+    }
+    if (s < P) {
+      if (query_role) qry.qsorted[static_cast<size_t>(n) * P + s] = make_float4(x, y, z, __uint_as_float(o));
+      prm.codes[t][static_cast<size_t>(n) * P + s] = keys[i];
+    }
+  }
+  if (blocks_role) {
+    constexpr int TPB = kBoxPoints / ITEMS;  // threads per block of 64 sorted points (consecutive lanes)
+    static_assert(TPB >= 1 && TPB <= 32 && (TPB & (TPB - 1)) == 0, "a block is a power-of-two run of lanes");
+#pragma unroll
+    for (int o2 = TPB / 2; o2 > 0; o2 >>= 1) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        bmn[d] = fminf(bmn[d], __shfl_xor_sync(0xffffffffu, bmn[d], o2));
+        bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(0xffffffffu, bmx[d], o2));
+      }
+    }
+    const int b0 = tid / TPB;
+    if (tid % TPB == 0 && b0 < nbox) {
+      float4* dst = blk.boxes + (static_cast<size_t>(n) * nbox + b0) * 2;
+      dst[0] = make_float4(bmn[0], bmn[1], bmn[2], 0.f);
+      dst[1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
+    }
+  }
+
+  // ---- 4. homes: lower bound of every query's code among the other tensor's sorted codes ----------
+  if (prm.mode == 0) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int s = tid * ITEMS + i;
+      if (s < P) prm.a.qhome[static_cast<size_t>(n) * P + s] = static_cast<unsigned>(s);
+    }
+    return;
+  }
+  __threadfence();
+  bb_cluster_barrier();
+  if (!query_role) return;
+  const int ot = 1 - t;
+  const int Po = prm.P[ot];
+  int64_t Lol = prm.len[ot][n];
+  const int Lo = static_cast<int>(Lol < 0 ? 0 : (Lol > Po ? Po : Lol));
+  const unsigned* ko = prm.codes[ot] + static_cast<size_t>(n) * Po;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int s = tid * ITEMS + i;
+    if (s >= P) continue;
+    unsigned home = 0;
+    if (s < L) {
+      int lo = 0, hi = Lo;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldcg(ko + mid) < keys[i]) lo = mid + 1; else hi = mid;
+      }
+      home = static_cast<unsigned>(lo);
+    }
+    qry.qhome[static_cast<size_t>(n) * P + s] = home;
+  }
+}
+
+template <int ITEMS>
+int launch_fused_order(const FusedOrderParams& prm, int N, cudaStream_t st) {
+  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS, unsigned>;
+  auto kern = order_cloud_kernel<ITEMS>;
+  const size_t smem = sizeof(typename Sort::TempStorage);
+  POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int T = prm.mode == 0 ? 1 : 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(T, static_cast<unsigned>(N));
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = T;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, prm));
+  POPS_LAUNCH_OK("order_cloud_kernel");
+  return POPS_OK;
+}
+
+// mode as in FusedOrderParams; returns POPS_OK, or -1 when the shape does not fit (caller falls back)
+int fused_order(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1, int P2,
+                int mode, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
+  const int Pmax = mode == 0 ? P2 : std::max(P1, P2);
+  // 8 items per thread: at 16 (clouds of up to 16384 points) the sort spills and N CTAs of 1024 threads
+  // are slower than the device-wide sort (T shape: 1.01 vs 0.95 ms per call); up to 8192 points the
+  // single launch wins (64 x 8192, K=16: 0.89 vs 0.92 ms; chamfer step, launch-bound: 0.50 vs 0.60 ms)
+  if (Pmax > kFusedThreads * 8 || get_option("knn_fused_prepass", 1) == 0) return -1;
+  FusedOrderParams prm;
+  prm.p[0] = p2; prm.p[1] = p1; prm.len[0] = len2; prm.len[1] = len1; prm.P[0] = P2; prm.P[1] = P1;
+  prm.mode = mode;
+  const int want = (clog2(std::max(Pmax, 1)) + 4 + 2) / 3;
+  const int forced = get_option("knn_axis_bits", 0);
+  prm.axis_bits = std::min(10, forced > 0 ? forced : std::max(4, want));
+  prm.hilbert = get_option("knn_curve", 1) != 0;
+  prm.a = a; prm.b = b;
+  prm.codes[0] = a.keys_out;                                   // [N][P2]
+  prm.codes[1] = a.keys_out + static_cast<size_t>(N) * P2;     // [N][P1]
+  return launch_fused_order<8>(prm, N, st);
+}
+
 size_t cub_temp_bytes_for(int64_t items) {
   size_t bytes = 0;
   unsigned* nul = nullptr;
@@ -457,6 +689,10 @@ size_t knn_order_workspace_bytes(int64_t N, int64_t P1, int64_t P2) {
 
 int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2,
                       int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st) {
+  {
+    const int rc = fused_order(p1, p2, len1, len2, N, P1, P2, self_knn ? 0 : 1, b, b, st);
+    if (rc >= 0) return rc;
+  }
   const int nbox = static_cast<int>(knn_order_num_boxes(P2));
   const KeyLayout kl = key_layout(N, P2, !self_knn);
   {
@@ -499,6 +735,10 @@ int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, con
 // buffers are used; b.maxabs_bits / b.bbox are not written (the caller points them at a's).
 int knn_order_prepass_pair(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
                            int P1, int P2, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
+  {
+    const int rc = fused_order(p1, p2, len1, len2, N, P1, P2, 2, a, b, st);
+    if (rc >= 0) return rc;
+  }
   const int nbox2 = static_cast<int>(knn_order_num_boxes(P2)), nbox1 = static_cast<int>(knn_order_num_boxes(P1));
   const KeyLayout kl = key_layout(N, std::max(P1, P2), true);
   {

@@ -286,8 +286,14 @@ def test_pair_search_matches_two_calls():
     _C, _, _ = _ops()
     gen = torch.Generator().manual_seed(33)
     cases = [(6, 3000, 2200, 3, 1, 2), (4, 1024, 5000, 3, 8, 2), (3, 1500, 1500, 3, 32, 2), (3, 700, 2000, 3, 1, 2),
-             (2, 1200, 1300, 3, 1, 1), (2, 300, 400, 5, 4, 2)]
-    for (N, P1, P2, D, K, norm) in cases:
+             (2, 1200, 1300, 3, 1, 1), (2, 300, 400, 5, 4, 2), (2, 1100, 9000, 3, 1, 2)]
+    from pytorch3d_pointops_b200 import _lib
+
+    lib = _lib.load()
+    # both pre-passes: the single-launch one (a CTA sorts a cloud of <= 8192 points in shared memory)
+    # and the device-wide sort (forced for the small shapes, natural for the 9000-point one)
+    for fused, (N, P1, P2, D, K, norm) in [(f, c) for f in (1, 0) for c in cases]:
+        lib.pops_set_option(b"knn_fused_prepass", fused)
         p1 = torch.rand(N, P1, D, generator=gen).to(DEV)
         p2 = (torch.rand(N, P2, D, generator=gen) * 0.7 + 0.4).to(DEV)  # partly overlapping boxes
         p2[:, : P2 // 8] = p2[:, P2 // 8 : 2 * (P2 // 8)]  # duplicated points
@@ -303,6 +309,13 @@ def test_pair_search_matches_two_calls():
         torch.cuda.synchronize()
         assert torch.equal(i12, ri) and torch.equal(d12, rd), (N, P1, P2, D, K, norm)
         assert torch.equal(i21, si) and torch.equal(d21, sd), (N, P1, P2, D, K, norm)
+    lib.pops_set_option(b"knn_fused_prepass", 1)
+
+
+def _lib_opt(name, value):
+    from pytorch3d_pointops_b200 import _lib
+
+    _lib.load().pops_set_option(name, value)
 
 
 @pytest.fixture
@@ -346,19 +359,28 @@ def test_pruned_search_adversarial(oracle, golden, force_ordered):
         Lc = torch.tensor([2500, 1301])
         for K in (1, 16, 32):
             oi, od = oracle.knn_points_idx(pts, pts, Lc, Lc, 2, K, threads=8)
-            gi, gd = _C.knn_points_idx(pts.to(DEV), pts.to(DEV), Lc.to(DEV), Lc.to(DEV), 2, K, -1)
-            assert torch.equal(gi.cpu(), oi), (name, K)
-            assert torch.equal(gd.cpu(), od), (name, K)
+            for fused in (1, 0):
+                _lib_opt(b"knn_fused_prepass", fused)
+                gi, gd = _C.knn_points_idx(pts.to(DEV), pts.to(DEV), Lc.to(DEV), Lc.to(DEV), 2, K, -1)
+                assert torch.equal(gi.cpu(), oi), (name, K, fused)
+                assert torch.equal(gd.cpu(), od), (name, K, fused)
+            _lib_opt(b"knn_fused_prepass", 1)
     # p1 != p2, ragged both sides, K > lengths2, empty and one-point clouds
     p1 = torch.randn(4, 700, 3, generator=gen)
     p2 = torch.randn(4, 1500, 3, generator=gen) * 0.5 + 0.3
     l1 = torch.tensor([700, 0, 13, 699])
     l2 = torch.tensor([1500, 900, 5, 0])
+    from pytorch3d_pointops_b200 import _lib
+
+    lib = _lib.load()
     for K in (1, 8, 16, 20):
         oi, od = oracle.knn_points_idx(p1, p2, l1, l2, 2, K)
-        gi, gd = _C.knn_points_idx(p1.to(DEV), p2.to(DEV), l1.to(DEV), l2.to(DEV), 2, K, -1)
-        assert torch.equal(gi.cpu(), oi), K
-        assert torch.equal(gd.cpu(), od), K
+        for fused in (1, 0):  # single-launch pre-pass / device-wide sort
+            lib.pops_set_option(b"knn_fused_prepass", fused)
+            gi, gd = _C.knn_points_idx(p1.to(DEV), p2.to(DEV), l1.to(DEV), l2.to(DEV), 2, K, -1)
+            assert torch.equal(gi.cpu(), oi), (K, fused)
+            assert torch.equal(gd.cpu(), od), (K, fused)
+    lib.pops_set_option(b"knn_fused_prepass", 1)
     one = torch.rand(1, 1, 3, generator=gen)
     gi, gd = _C.knn_points_idx(one.to(DEV), one.to(DEV), torch.tensor([1], device=DEV), torch.tensor([1], device=DEV), 2, 4, -1)
     oi, od = oracle.knn_points_idx(one, one, torch.tensor([1]), torch.tensor([1]), 2, 4)
