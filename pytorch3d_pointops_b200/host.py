@@ -3,9 +3,9 @@
 `knn_points` (functions/knn.py, the reference's API) takes device tensors.  When the clouds live
 in host memory and the (idx, dists) result is wanted back on the host -- 100 MB for the
 B=32 x P=16384 x K=16 shape, most of the end-to-end time -- the batch is independent per cloud
-(outer `for n` of knn_cpu.cpp:35), so the legs pipeline: the clouds go in with one copy (6 MB), the
-spatial pre-pass runs once for the whole batch, and while slice i is searched the results of slice
-i-1 are on their way out.  Copies run on two side streams, the kernels on the caller's current
+(outer `for n` of knn_cpu.cpp:35), so the legs pipeline: the first slice goes in, is ordered and
+searched on its own; the rest of the batch follows with one copy and ONE spatial pre-pass, and
+while slice i is searched the results of slice i-1 are on their way out.  Copies run on two side streams, the kernels on the caller's current
 stream; buffers are pinned once and reused.
 """
 from __future__ import annotations
@@ -23,14 +23,14 @@ class HostKnn:
     out_idx (N,P1,K) int64 and out_dists (N,P1,K) float32 are pinned host tensors owned by this
     object and overwritten by every call."""
 
-    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=6, graph: bool = True):
+    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=8, graph: bool = True):
         self.device = torch.device(device)
         self.N, self.P1, self.P2, self.D, self.K = N, P1, P2, D, K
         # `slices`: a count (equal slices) or an explicit list of slice sizes in clouds.  Measured on
-        # the B=32 x P=16384 x K=16 shape (D2H of the 100 MB result alone: 1.77-1.85 ms): 2 slices
-        # 2.52 ms, 3: 2.40, 4: 2.32, 5: 2.30, 6: 2.28, 8: 2.30 -- a slice below one wave of CTAs still
-        # costs one CTA's latency, so many slices stretch the search; searching the slices on 2-3
-        # alternating streams or uneven slice sizes end at the same floor.
+        # the B=32 x P=16384 x K=16 shape (D2H of the 100 MB result alone: 1.78 ms): 2 slices 2.47 ms,
+        # 4: 2.18, 6: 2.16, 8: 2.11, 10: 2.15 -- a slice below one wave of CTAs still costs one CTA's
+        # latency, so many slices stretch the search; uneven slice sizes and searching the slices on 2-3
+        # alternating streams end at the same floor.
         if isinstance(slices, (list, tuple)):
             sizes = [int(v) for v in slices if int(v) > 0]
             assert sum(sizes) == N, "slice sizes must add up to the batch"
@@ -90,33 +90,44 @@ class HostKnn:
         dev = self.device
         main = torch.cuda.current_stream(dev)
         self_knn = p2 is None
+        same_len = self_knn and lengths2 is lengths1
+        # Two groups of slices: the FIRST slice travels, is ordered and searched on its own, so that its
+        # results are on their way back while the rest of the batch is still going in; the remaining
+        # slices share one copy and one pre-pass (pointops_b200.h: pops_knn_points_prepare /
+        # pops_knn_points_idx_range).
+        groups = [self.ranges[:1], self.ranges[1:]] if len(self.ranges) > 2 else [self.ranges]
+        staged = []
         with torch.cuda.stream(self.h2d):
             self.h2d.wait_stream(main)
-            d1 = p1.to(dev, non_blocking=True)
-            d2 = d1 if self_knn else p2.to(dev, non_blocking=True)
-            l1 = lengths1.to(dev, non_blocking=True)
-            l2 = l1 if self_knn and lengths2 is lengths1 else lengths2.to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.h2d)
-        main.wait_event(ev)
-        if not recording:
-            for t in (d1, d2, l1, l2):
-                t.record_stream(main)
-        # one pre-pass for the whole batch, then the search slice by slice (pointops_b200.h:
-        # pops_knn_points_prepare / pops_knn_points_idx_range)
-        ks = _C.KnnSliced(d1, d2, l1, l2, norm, self.K)
-        ks.prepare()
-        for a, b in self.ranges:
-            ks.search(a, b)
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(self.d2h):
-                self.d2h.wait_event(done)
-                self.out_idx[a:b].copy_(ks.idx[a:b], non_blocking=True)
-                self.out_dists[a:b].copy_(ks.dists[a:b], non_blocking=True)
-        if not recording:
-            for t in (ks.idx, ks.dists, ks.ws):
-                t.record_stream(self.d2h)
-        keep = [d1, d2, l1, l2, ks]
+            for grp in groups:
+                g0, g1 = grp[0][0], grp[-1][1]
+                d1 = p1[g0:g1].to(dev, non_blocking=True)
+                d2 = d1 if self_knn else p2[g0:g1].to(dev, non_blocking=True)
+                l1 = lengths1[g0:g1].to(dev, non_blocking=True)
+                l2 = l1 if same_len else lengths2[g0:g1].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.h2d)
+                staged.append((d1, d2, l1, l2, ev))
+        keep = []
+        for grp, (d1, d2, l1, l2, ev) in zip(groups, staged):
+            g0 = grp[0][0]
+            main.wait_event(ev)
+            if not recording:
+                for t in (d1, d2, l1, l2):
+                    t.record_stream(main)
+            ks = _C.KnnSliced(d1, d2, l1, l2, norm, self.K)
+            ks.prepare()
+            for a, b in grp:
+                ks.search(a - g0, b - g0)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(done)
+                    self.out_idx[a:b].copy_(ks.idx[a - g0:b - g0], non_blocking=True)
+                    self.out_dists[a:b].copy_(ks.dists[a - g0:b - g0], non_blocking=True)
+            if not recording:
+                for t in (ks.idx, ks.dists, ks.ws):
+                    t.record_stream(self.d2h)
+            keep.append((d1, d2, l1, l2, ks))
         main.wait_stream(self.d2h)
         return keep

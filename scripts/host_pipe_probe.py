@@ -23,6 +23,6 @@ print("compute all   ", timeit(lambda: _C.knn_points_idx(pd, pd, Ld, Ld, 2, K, -
 print("compute 8 of32", timeit(lambda: _C.knn_points_idx(pd[:8], pd[:8], Ld[:8], Ld[:8], 2, K, -1)))
 print("d2h 100MB     ", timeit(lambda: (oi.copy_(idx, non_blocking=True), od.copy_(d, non_blocking=True))))
 print("h2d 6MB       ", timeit(lambda: p.to(dev, non_blocking=True)))
-for s in (2, 3, 4, 5, 6, 8):
+for s in (2, 4, 6, 8, 10, [3, 5, 6, 6, 6, 6], [2, 6, 6, 6, 6, 6], [4, 7, 7, 7, 7]):
     hk = HostKnn(B, P, P, 3, K, dev, slices=s)
     print(f"pipeline s={s}  ", timeit(lambda: hk(p, None, L)))
