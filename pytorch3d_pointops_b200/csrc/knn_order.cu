@@ -98,6 +98,14 @@ __device__ __forceinline__ uint32_t bb_cluster_rank() {
 __device__ __forceinline__ void bb_cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form: arrive at kernel entry, wait right before the first remote store -- a CTA's shared
+// memory may only be written from its peers once it is known to have started
+__device__ __forceinline__ void bb_cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bb_cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bb_st_remote(void* local_smem_ptr, uint32_t rank, float value) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
@@ -113,6 +121,7 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                    unsigned* __restrict__ maxabs_bits) {
   __shared__ float sm[32];
   __shared__ float part[kBboxCluster][8];  // per CTA: min xyz, max xyz, max |p1|
+  bb_cluster_arrive();
   const int n = blockIdx.y;
   const int rank = static_cast<int>(bb_cluster_rank());
   const int t0 = rank * kBboxThreads + threadIdx.x, stride = kBboxCluster * kBboxThreads;
@@ -157,6 +166,7 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     out[3 + d] = block_reduce(mx[d], true, sm);
   }
   out[6] = block_reduce(m1, true, sm);
+  bb_cluster_wait();  // every CTA of the cluster is running: its shared memory can be written
   if (threadIdx.x < 7) {
     float v = out[0];
 #pragma unroll
@@ -453,6 +463,7 @@ order_cloud_kernel(const FusedOrderParams prm) {
   __shared__ float red[32];
   __shared__ float part[2][8];  // per CTA of the cluster: min xyz, max xyz
   __shared__ float bb[6];
+  bb_cluster_arrive();
   const int T = gridDim.x;
   const int t = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
   const int P = prm.P[t];
@@ -476,6 +487,7 @@ order_cloud_kernel(const FusedOrderParams prm) {
     out[d] = block_reduce(mn[d], false, red);
     out[3 + d] = block_reduce(mx[d], true, red);
   }
+  bb_cluster_wait();  // the peer CTA is running: its shared memory can be written
   if (tid < 6) {
     float v = out[0];
 #pragma unroll
