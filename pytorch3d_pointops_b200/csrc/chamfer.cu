@@ -100,6 +100,7 @@ chamfer_fwd_kernel(const float* __restrict__ dists, const int64_t* __restrict__ 
   __shared__ int parti[C];
   const int n = blockIdx.y, tid = threadIdx.x;
   const int rank = static_cast<int>(ch_cluster_rank());
+  ch_cluster_barrier();  // every CTA of the cluster is running before any of them writes a peer's shared memory
   int64_t L1l = len1[n], L2l = len2[n];
   const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
   const bool y_empty = L2l <= 0;

@@ -107,6 +107,7 @@ fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ leng
   float ly = pts[static_cast<size_t>(last) * 3 + 1];
   float lz = pts[static_cast<size_t>(last) * 3 + 2];
 
+  if (C > 1) cluster_barrier();  // every CTA of the cluster is running before the first remote store
   for (int k = 1; k < kn; ++k) {
     const int par = k & 1;
     // ---- update min-distances; track only the maximum VALUE in the dense loop -----------------
