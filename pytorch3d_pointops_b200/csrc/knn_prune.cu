@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : ((Q == 1
 knn_prune_kernel(const KnnPruneParams prm) {
   constexpr int QPB = Q * THREADS, S = kRingSlots;
   constexpr bool REFINE = KT <= 4;  // per-query box test before a block is scanned
-  constexpr int NSEED = KT <= 4 ? 3 : (KT <= 16 ? 2 : 4);  // >= 4 seed points per tournament subset; small K: home +- 1 keeps the worst bound of the warp down
+  // seed blocks: home and its two neighbours in curve order (>= 4 seed points per tournament subset for
+  // K <= 16; with one query per thread 3 blocks beat 2 on the T shape: 0.914 vs 0.955 ms at K=16)
+  constexpr int NSEED = KT <= 16 ? 3 : 4;
   static_assert(NSEED <= S, "the seed blocks sit in the ring together");
   using SM = PruneSmem<Q, THREADS, CID, KT>;
   extern __shared__ __align__(128) unsigned char smem[];
