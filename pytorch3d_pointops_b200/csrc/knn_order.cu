@@ -457,7 +457,9 @@ struct FusedOrderParams {
 template <int ITEMS>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 order_cloud_kernel(const FusedOrderParams prm) {
-  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS, unsigned>;
+  // (code << IDX_BITS | index) in ONE 32-bit key, sorted on the code bits only: no value array to carry
+  constexpr int IDX_BITS = ITEMS == 8 ? 13 : 14;  // log2(1024 * ITEMS)
+  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS>;
   extern __shared__ __align__(16) unsigned char fsm[];
   typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(fsm);
   __shared__ float red[32];
@@ -517,15 +519,15 @@ order_cloud_kernel(const FusedOrderParams prm) {
 
   // ---- 2. codes + sort (blocked arrangement: thread tid holds positions tid*ITEMS + i) ------------
   const int code_bits = 3 * prm.axis_bits;
-  unsigned keys[ITEMS], vals[ITEMS];
+  unsigned keys[ITEMS];
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const int j = tid * ITEMS + i;
-    vals[i] = static_cast<unsigned>(j);
-    keys[i] = (1u << code_bits) - 1u;  // padding: largest code, kept behind the valid points by stability
-    if (j < L) keys[i] = curve_code(pts + static_cast<size_t>(j) * 3, bb, prm.axis_bits, prm.hilbert != 0);
+    unsigned code = (1u << code_bits) - 1u;  // padding: largest code, kept behind the valid points by stability
+    if (j < L) code = curve_code(pts + static_cast<size_t>(j) * 3, bb, prm.axis_bits, prm.hilbert != 0);
+    keys[i] = (code << IDX_BITS) | static_cast<unsigned>(j);
   }
-  Sort(temp).Sort(keys, vals, 0, code_bits);
+  Sort(temp).Sort(keys, IDX_BITS, IDX_BITS + code_bits);
 
   // ---- 3. outputs from the sorted registers -----------------------------------------------------
   const bool blocks_role = (t == 0) || prm.mode == 2;           // this tensor is scanned as blocks
@@ -538,7 +540,7 @@ order_cloud_kernel(const FusedOrderParams prm) {
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const int s = tid * ITEMS + i;
-    const unsigned o = vals[i];
+    const unsigned o = keys[i] & ((1u << IDX_BITS) - 1u);
     float x = 0.f, y = 0.f, z = 0.f, w = INF;
     unsigned orig = kNoPoint;
     if (s < L) {
@@ -559,7 +561,7 @@ order_cloud_kernel(const FusedOrderParams prm) {
     }
     if (s < P) {
       if (query_role) qry.qsorted[static_cast<size_t>(n) * P + s] = make_float4(x, y, z, __uint_as_float(o));
-      prm.codes[t][static_cast<size_t>(n) * P + s] = keys[i];
+      prm.codes[t][static_cast<size_t>(n) * P + s] = keys[i] >> IDX_BITS;
     }
   }
   if (blocks_role) {
@@ -607,7 +609,7 @@ order_cloud_kernel(const FusedOrderParams prm) {
       int lo = 0, hi = Lo;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (__ldcg(ko + mid) < keys[i]) lo = mid + 1; else hi = mid;
+        if (__ldcg(ko + mid) < (keys[i] >> IDX_BITS)) lo = mid + 1; else hi = mid;
       }
       home = static_cast<unsigned>(lo);
     }
@@ -617,7 +619,7 @@ order_cloud_kernel(const FusedOrderParams prm) {
 
 template <int ITEMS>
 int launch_fused_order(const FusedOrderParams& prm, int N, cudaStream_t st) {
-  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS, unsigned>;
+  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS>;
   auto kern = order_cloud_kernel<ITEMS>;
   const size_t smem = sizeof(typename Sort::TempStorage);
   POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -643,21 +645,24 @@ int launch_fused_order(const FusedOrderParams& prm, int N, cudaStream_t st) {
 int fused_order(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1, int P2,
                 int mode, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
   const int Pmax = mode == 0 ? P2 : std::max(P1, P2);
-  // 8 items per thread: at 16 (clouds of up to 16384 points) the sort spills and N CTAs of 1024 threads
-  // are slower than the device-wide sort (T shape: 1.01 vs 0.95 ms per call); up to 8192 points the
-  // single launch wins (64 x 8192, K=16: 0.89 vs 0.92 ms; chamfer step, launch-bound: 0.50 vs 0.60 ms)
-  if (Pmax > kFusedThreads * 8 || get_option("knn_fused_prepass", 1) == 0) return -1;
+  // up to 8 items per thread by default (knn_fused_items = 16 admits clouds of up to 16384 points): N or
+  // 2N CTAs leave most of the 148 SMs idle, which costs more GPU time than the launches it saves once the
+  // clouds are large (T shape, N = 32: 0.96 vs 0.915 ms per call); up to 8192 points the single launch
+  // wins on hosts where the step is launch-bound (chamfer step 0.50 vs 0.60 ms) and costs ~4 % where it
+  // is not (0.446 vs 0.427 ms)
+  if (Pmax > kFusedThreads * get_option("knn_fused_items", 8) || get_option("knn_fused_prepass", 1) == 0) return -1;
   FusedOrderParams prm;
   prm.p[0] = p2; prm.p[1] = p1; prm.len[0] = len2; prm.len[1] = len1; prm.P[0] = P2; prm.P[1] = P1;
   prm.mode = mode;
   const int want = (clog2(std::max(Pmax, 1)) + 4 + 2) / 3;
   const int forced = get_option("knn_axis_bits", 0);
-  prm.axis_bits = std::min(10, forced > 0 ? forced : std::max(4, want));
+  prm.axis_bits = std::min(6, forced > 0 ? forced : std::max(4, want));  // 18 code bits + 13-14 index bits = one key
   prm.hilbert = get_option("knn_curve", 1) != 0;
   prm.a = a; prm.b = b;
   prm.codes[0] = a.keys_out;                                   // [N][P2]
   prm.codes[1] = a.keys_out + static_cast<size_t>(N) * P2;     // [N][P1]
-  return launch_fused_order<8>(prm, N, st);
+  if (Pmax <= kFusedThreads * 8) return launch_fused_order<8>(prm, N, st);
+  return launch_fused_order<16>(prm, N, st);
 }
 
 size_t cub_temp_bytes_for(int64_t items) {

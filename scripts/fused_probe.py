@@ -32,9 +32,10 @@ def wall(fn, n=50):
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
 with torch.no_grad():
     xd, yd = ch['x'].detach(), ch['y'].detach()
-for f in (0, 1, 0, 1):
+for f, items in ((0, 8), (1, 8), (1, 16), (0, 8), (1, 8), (1, 16)):
     lib.pops_set_option(b"knn_fused_prepass", f)
+    lib.pops_set_option(b"knn_fused_items", items)
     tp = timeit(lambda: _C.knn_points_idx_pair(xd, yd, ch['xl'], ch['yl'], 2, 1))
     t16 = timeit(lambda: _C.knn_points_idx(p, p, L, L, 2, 16, -1))
     t8 = timeit(lambda: _C.knn_points_idx(p8, p8, L8, L8, 2, 16, -1))
-    print(f"fused={f}: chamfer pair {tp:.4f} ms  T shape K=16 {t16:.4f} ms  64x8192 K=16 {t8:.4f} ms  chamfer step wall {wall(step):.4f} ms", flush=True)
+    print(f"fused={f} items={items}: chamfer pair {tp:.4f} ms  T shape K=16 {t16:.4f} ms  64x8192 K=16 {t8:.4f} ms  chamfer step wall {wall(step):.4f} ms", flush=True)
