@@ -57,6 +57,7 @@ int64_t pops_launch_count(void);
  *               per axis of the curve codes (0 = sized to the cloud); knn_pair 1 | 0: one pre-pass for
  *               both directions in pops_knn_points_idx_pair; knn_fused_prepass 1 | 0: single-launch
  *               pre-pass (one CTA sorts a cloud in shared memory) for clouds of up to 8192 points
+ *               (knn_fused_items 16: up to 16384)
  *   knn_tc      -1 auto | 0 never | 1 whenever the shape allows: tensor-core path for 32 <= D <= 256
  *   tc_cluster  CTAs that share every p2 stage by TMA multicast (1 | 2 | 4) */
 void pops_set_option(const char* name, int value);
