@@ -139,6 +139,16 @@ int pops_knn_points_backward(const float* p1, const float* p2, const int64_t* le
                              const int64_t* lengths2, const int64_t* idx, const float* grad_dists,
                              int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K, int norm,
                              float* grad_p1, float* grad_p2, pops_stream_t stream);
+/* The same with caller-owned scratch of pops_knn_backward_workspace_bytes(N, P2, D) bytes (additive):
+ * for D = 3 the grad_p2 scatter then runs as one 16-byte vector reduction per (query, neighbour)
+ * into a float4-padded copy of grad_p2 that a second small kernel folds into the 12-byte rows -- a
+ * third of the L2 atomic operations of three scalar reductions.  workspace NULL = the call above. */
+size_t pops_knn_backward_workspace_bytes(int64_t N, int64_t P2, int64_t D);
+int pops_knn_points_backward_ws(const float* p1, const float* p2, const int64_t* lengths1,
+                                const int64_t* lengths2, const int64_t* idx, const float* grad_dists,
+                                int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K, int norm,
+                                float* grad_p1, float* grad_p2, void* workspace,
+                                size_t workspace_bytes, pops_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Ball query.  Replaces _C.ball_query (ext.cpp:23; ball_query.h:62-93; ball_query_cpu.cpp:12-54):

@@ -208,10 +208,12 @@ def knn_points_backward(p1, p2, lengths1, lengths2, idxs, norm, grad_dists):
     grad_p1 = torch.empty_like(p1)
     grad_p2 = torch.empty_like(p2)
     with _on_device(p1.device):
-        st = lib.pops_knn_points_backward(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
-                                          lengths2.data_ptr(), idxs.data_ptr(),
-                                          grad_dists.data_ptr(), N, P1, P2, D, K, int(norm),
-                                          grad_p1.data_ptr(), grad_p2.data_ptr(), _stream(p1))
+        ws = _ws(lib.pops_knn_backward_workspace_bytes(N, P2, D), p1.device)
+        st = lib.pops_knn_points_backward_ws(p1.data_ptr(), p2.data_ptr(), lengths1.data_ptr(),
+                                             lengths2.data_ptr(), idxs.data_ptr(),
+                                             grad_dists.data_ptr(), N, P1, P2, D, K, int(norm),
+                                             grad_p1.data_ptr(), grad_p2.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _stream(p1))
     _lib.check(st, "knn_points_backward")
     return grad_p1, grad_p2
 
@@ -373,6 +375,23 @@ def _chan_array(tensors):
     return arr
 
 
+def _check_feature_shapes(xfs, yfs, N, P1, P2):
+    """The kernels index features with (N, P1) / (N, P2) of the points and ONE channel count per pair;
+    anything else would read or write out of bounds (the reference fails in knn_gather /
+    cosine_similarity broadcasting, functions/chamfer.py:143-160)."""
+    if len(xfs) != len(yfs):
+        raise ValueError("x and y must bring the same number of feature tensors")
+    for f, (a, b) in enumerate(zip(xfs, yfs)):
+        if a.dim() != 3 or b.dim() != 3:
+            raise ValueError(f"feature {f}: expected tensors of shape (N, P, C)")
+        if a.shape[0] != N or a.shape[1] != P1:
+            raise ValueError(f"feature {f}: x feature has shape {tuple(a.shape)}, expected ({N}, {P1}, C)")
+        if b.shape[0] != N or b.shape[1] != P2:
+            raise ValueError(f"feature {f}: y feature has shape {tuple(b.shape)}, expected ({N}, {P2}, C)")
+        if a.shape[2] != b.shape[2]:
+            raise ValueError(f"feature {f}: x and y features differ in channels ({a.shape[2]} vs {b.shape[2]})")
+
+
 def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point_reduction, abs_cosine,
                     out=None):
     """Fused per-direction chamfer post-processing (see include/pointops_b200.h).
@@ -387,6 +406,11 @@ def chamfer_forward(dists, idx, lengths1, lengths2, weights, P2, xfs, yfs, point
     F = len(xfs)
     xfs = [_cuda_f32(t, "x_feature") for t in xfs]
     yfs = [_cuda_f32(t, "y_feature") for t in yfs]
+    _check_feature_shapes(xfs, yfs, N, P1, int(P2))
+    if idx.shape != dists.shape:
+        raise ValueError("dists and idx must both be (N, P1)")
+    lengths1 = _cuda_i64(lengths1, "lengths1", dists)
+    lengths2 = _cuda_i64(lengths2, "lengths2", dists)
     red = RED[point_reduction]
     shape = (N, P1) if red == 0 else (N,)
     if out is not None:
@@ -422,6 +446,14 @@ def chamfer_backward(x, y, idx, lengths1, lengths2, weights, norm, xfs, yfs, poi
     N, P1, D = x.shape
     P2 = y.shape[1]
     F = len(xfs)
+    xfs = [_cuda_f32(t, "x_feature") for t in xfs]
+    yfs = [_cuda_f32(t, "y_feature") for t in yfs]
+    _check_feature_shapes(xfs, yfs, N, P1, P2)
+    idx = _cuda_i64(idx, "idx", x)
+    if idx.numel() != N * P1:
+        raise ValueError("idx must be (N, P1)")
+    lengths1 = _cuda_i64(lengths1, "lengths1", x)
+    lengths2 = _cuda_i64(lengths2, "lengths2", x)
     if into is not None:
         grad_x, grad_y, gxf, gyf = into
         for t, r in [(grad_x, x), (grad_y, y)] + list(zip(gxf, xfs)) + list(zip(gyf, yfs)):

@@ -35,6 +35,8 @@ SIGNATURES = {
     "pops_knn_points_idx_pair": (c_int, [_P, _P, _P, _P] + [c_int64] * 5 + [c_int] + [_P] * 5 + [c_size_t, _P]),
     "pops_knn_check_version": (c_int, [c_int, c_int64, c_int64]),
     "pops_knn_points_backward": (c_int, [_P] * 6 + [c_int64] * 5 + [c_int, _P, _P, _P]),
+    "pops_knn_backward_workspace_bytes": (c_size_t, [c_int64] * 3),
+    "pops_knn_points_backward_ws": (c_int, [_P] * 6 + [c_int64] * 5 + [c_int, _P, _P, _P, c_size_t, _P]),
     "pops_ball_query_workspace_bytes": (c_size_t, [c_int64] * 5),
     "pops_ball_query": (c_int, [_P] * 4 + [c_int64] * 5 + [c_float, _P, _P, _P, c_size_t, _P]),
     "pops_fps_workspace_bytes": (c_size_t, [c_int64] * 4),

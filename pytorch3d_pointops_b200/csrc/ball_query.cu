@@ -132,7 +132,10 @@ ball_query_d3_kernel(const BqParams prm) {
     if (valid && count < K) {
       const float M = fmaxf(s_maxabs, qmax);
       const float E = fmaf(M * M, 1.52587890625e-05f, 1e-37f);
-      const float T = __fadd_rn(__fsub_rn(prm.radius2, qq), E);
+      // beyond 1e18 (or +inf) the expanded form proves nothing: every group goes to the exact test.
+      // NaN coordinates need no care: fmaxf / fminf drop them and the exact test d2 < r2 is false,
+      // as in the reference (ball_query_cpu.cpp:44)
+      const float T = (M < 1e18f) ? __fadd_rn(__fsub_rn(prm.radius2, qq), E) : inf;
       for (int g = 0; g < pts4 / 4 && count < K; ++g) {
         const float4 X = reinterpret_cast<const float4*>(tx)[g];
         const float4 Y = reinterpret_cast<const float4*>(ty)[g];
@@ -280,7 +283,9 @@ ball_query_scan_kernel(const BqParams prm) {
     for (int t = 0; t < Q; ++t) {
       const float M = fmaxf(s_maxabs, qmax[t]);
       const float E = fmaf(M * M, 1.52587890625e-05f, 1e-37f);
-      T[t] = (valid[t] && count[t] < K) ? __fadd_rn(__fsub_rn(r2, qq[t]), E) : -INF;
+      // beyond 1e18 (or +inf) the expanded form proves nothing: every group goes to the exact test
+      // (NaN: dropped by fmaxf / fminf, and d2 < r2 is false for it, as in ball_query_cpu.cpp:44)
+      T[t] = (valid[t] && count[t] < K) ? ((M < 1e18f) ? __fadd_rn(__fsub_rn(r2, qq[t]), E) : INF) : -INF;
     }
     const float4* tp = reinterpret_cast<const float4*>(tile);
     float4 Xc[4];

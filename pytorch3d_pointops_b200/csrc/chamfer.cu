@@ -162,8 +162,10 @@ chamfer_fwd_kernel(const float* __restrict__ dists, const int64_t* __restrict__ 
       float fd = 0.0f;
       if (i < L1) {
         float na, nb;
-        const int64_t j = in[i];
-        const float c = cosine(xf + static_cast<size_t>(i) * Cf, yf + static_cast<size_t>(j) * Cf, Cf, &na, &nb, y_empty);
+        int64_t j = in[i];
+        const bool no_nb = y_empty || j < 0 || j >= P2;  // an index the search never returns: treat as "no neighbour", never dereference
+        if (no_nb) j = 0;
+        const float c = cosine(xf + static_cast<size_t>(i) * Cf, yf + static_cast<size_t>(j) * Cf, Cf, &na, &nb, no_nb);
         fd = (1.0f - (abs_cosine ? fabsf(c) : c)) * w;
       }
       if (reduction == kRedNone) feat_out[(static_cast<size_t>(f) * N + n) * P1 + i] = fd;
@@ -230,8 +232,10 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
     if (reduction == kRedNone) gd = g_cham[static_cast<size_t>(n) * P1 + i] * w;
     else if (reduction == kRedMax) gd = (i == amax) ? g_cham[n] * w : 0.0f;
     else gd = g_cham[g_bcast ? 0 : n] * g_scale * w * (reduction == kRedMean ? inv_len : 1.0f);  // g_bcast: one upstream scalar for every cloud
-    const int64_t j = in[i];
-    if (gd != 0.0f && !y_empty) {
+    int64_t j = in[i];
+    const bool y_none = y_empty || j < 0 || j >= P2;  // out-of-range index: no neighbour, nothing read or scattered
+    if (y_none) j = 0;
+    if (gd != 0.0f && !y_none) {
       for (int d = 0; d < D; ++d) {
         const float a = xn[static_cast<size_t>(i) * D + d], b = yn[static_cast<size_t>(j) * D + d];
         const float diff = (NORM == 1) ? gd * ((a > b) ? 1.0f : -1.0f) : 2.0f * gd * (a - b);
@@ -250,13 +254,13 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
       const float* a = ft.xf[f] + (static_cast<size_t>(n) * P1 + i) * C;
       const float* b = ft.yf[f] + (static_cast<size_t>(n) * P2 + j) * C;
       float na, nb;
-      const float c = cosine(a, b, C, &na, &nb, y_empty);
+      const float c = cosine(a, b, C, &na, &nb, y_none);
       float dc = -gf;  // d(1 - c)/dc
       if (abs_cosine) dc = (c > 0.0f) ? -gf : ((c < 0.0f) ? gf : 0.0f);
       // raw norms decide whether the clamp is active (then the norm is a constant)
       float sa = 0.f, sb = 0.f;
       for (int k = 0; k < C; ++k) {
-        const float bv = y_empty ? 0.0f : b[k];
+        const float bv = y_none ? 0.0f : b[k];
         sa = fmaf(a[k], a[k], sa);
         sb = fmaf(bv, bv, sb);
       }
@@ -264,12 +268,12 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
       float* ga = ft.gxf[f] + (static_cast<size_t>(n) * P1 + i) * C;
       float* gb = ft.gyf[f] + (static_cast<size_t>(n) * P2 + j) * C;
       for (int k = 0; k < C; ++k) {
-        const float bv = y_empty ? 0.0f : b[k];
+        const float bv = y_none ? 0.0f : b[k];
         const float ah = a[k] / na, bh = bv / nb;
         const float da = (bh - (a_free ? c * ah : 0.0f)) / na;
         const float db = (ah - (b_free ? c * bh : 0.0f)) / nb;
         ga[k] = acc ? ga[k] + dc * da : dc * da;
-        if (!y_empty) atomicAdd(gb + k, dc * db);
+        if (!y_none) atomicAdd(gb + k, dc * db);
       }
     }
   }

@@ -149,6 +149,24 @@ __device__ __forceinline__ float key_dist(uint64_t k) {
   return __uint_as_float(static_cast<uint32_t>(k >> 32));
 }
 
+// ---- non-finite / out-of-range inputs ------------------------------------------------------------
+// The filtered searches (expanded-form filter, box pruning, tensor-core filter) are proven for finite
+// coordinates with |c| < 1e18.  Every pre-pass therefore records, per cloud, the
+// largest |coordinate| as an unsigned BIT PATTERN (integer max: +inf and every NaN compare above all
+// finite values, unlike fmaxf, which drops NaN); a cloud at or above kDirtyBits is skipped by the fast
+// kernels and answered by the exact generic kernel, whose keys order  finite < +inf < NaN, ties by
+// lower index.  Where the reference's result is well defined (NaN query: the first K points; +inf
+// distances: ordinary values) this is the reference's result (knn_cpu.cpp:40-65); a NaN POINT makes
+// the reference's heap comparator inconsistent -- there NaN simply ranks last here.
+constexpr unsigned kDirtyBits = 0x5d5e0b6bu;      // 1e18f
+constexpr unsigned kDirtyNormBits = 0x7b4097ceu;  // 1e36f: squared norms (tensor-core path)
+__device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+// key with the total order above: NaN distances are canonicalised so that they tie among themselves
+__device__ __forceinline__ uint64_t make_key_total(float d, uint32_t j) {
+  const uint32_t b = (d != d) ? 0x7fffffffu : __float_as_uint(d);
+  return (static_cast<uint64_t>(b) << 32) | j;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -44,7 +44,7 @@ __global__ void knn_pack_kernel(const float* __restrict__ p2, const int64_t* __r
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   int64_t L = len2[n];
   L = L < 0 ? 0 : (L > P2 ? P2 : L);
-  float m = 0.0f;
+  unsigned m = 0u;  // max |coordinate| as a bit pattern: +inf and NaN rank above every finite value
   if (j < P2pad) {
     float v[DT];
     float w = 0.0f;
@@ -53,7 +53,7 @@ __global__ void knn_pack_kernel(const float* __restrict__ p2, const int64_t* __r
 #pragma unroll
       for (int d = 0; d < DT; ++d) {
         v[d] = src[d];
-        m = fmaxf(m, fabsf(v[d]));
+        m = max(m, abs_bits(v[d]));
         w = fmaf(v[d], v[d], w);
       }
     } else {
@@ -70,8 +70,8 @@ __global__ void knn_pack_kernel(const float* __restrict__ p2, const int64_t* __r
     for (int d = 0; d < DT; ++d) dst[static_cast<size_t>(d) * P2pad] = v[d];
     if (EXP) dst[static_cast<size_t>(DT) * P2pad] = w;
   }
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(maxabs_bits + n, __float_as_uint(m));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m > 0u) atomicMax(maxabs_bits + n, m);
 }
 
 // max |coord| over the valid rows of p (N,P,D) -> atomicMax into maxabs_bits[n]
@@ -82,12 +82,12 @@ __global__ void maxabs_kernel(const float* __restrict__ p, const int64_t* __rest
   L = L < 0 ? 0 : (L > P ? P : L);
   const size_t total = static_cast<size_t>(L) * D;
   const float* src = p + static_cast<size_t>(n) * P * D;
-  float m = 0.0f;
+  unsigned m = 0u;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    m = fmaxf(m, fabsf(src[i]));
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(maxabs_bits + n, __float_as_uint(m));
+    m = max(m, abs_bits(src[i]));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m > 0u) atomicMax(maxabs_bits + n, m);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -142,6 +142,7 @@ knn_scan_kernel(const KnnScanParams prm) {
 
   int64_t* out_idx = prm.idx + (static_cast<size_t>(n) * prm.P1) * K;
   float* out_d = prm.dists + (static_cast<size_t>(n) * prm.P1) * K;
+  if (prm.maxabs_bits[n] >= kDirtyBits) return;  // non-finite / huge coordinates: the exact generic kernel answers this cloud
 
   // CTA entirely beyond lengths1[n] (or nothing to search): rows are (0, 0).
   if (q_base >= L1 || L2 == 0) {
@@ -373,6 +374,8 @@ struct KnnGenericParams {
   const unsigned char* flags;  // [N][P1] or nullptr: when set, only flagged queries are (re)computed
   const unsigned* flag_count;  // with flags: number of flagged queries; this kernel runs only above
   unsigned flag_limit;         //   flag_limit of them (below, knn_exact_rows_kernel has done the work)
+  const unsigned* dirty_bits;  // [N] or nullptr: when set, only clouds with dirty_bits[n] >= kDirtyBits
+                               //   (non-finite or huge coordinates, skipped by the filtered search) are computed
 };
 
 template <int NORM, int THREADS>
@@ -387,6 +390,7 @@ knn_generic_kernel(const KnnGenericParams prm) {
   const int qi = q_base + tid;
   const bool valid = qi < L1;
   bool wanted = true;
+  if (prm.dirty_bits && prm.dirty_bits[n] < kDirtyBits) return;
   if (prm.flags) {  // exact recomputation of the queries the tensor-core path could not certify
     if (*prm.flag_count <= prm.flag_limit) return;
     wanted = qi < prm.P1 && prm.flags[static_cast<size_t>(n) * prm.P1 + qi] != 0;
@@ -402,7 +406,6 @@ knn_generic_kernel(const KnnGenericParams prm) {
     qsm[d * THREADS + tid] = valid ? prm.p1[(static_cast<size_t>(n) * prm.P1 + qi) * D + d] : 0.0f;
   for (int k = 0; k < K; ++k) lists[static_cast<size_t>(k) * THREADS + tid] = kEmptyKey;
   uint64_t worst = kEmptyKey;
-  float dk = __int_as_float(0x7f800000);
 
   const float* p2n = prm.p2 + static_cast<size_t>(n) * prm.P2 * D;
   for (int j0 = 0; j0 < L2; j0 += TP) {
@@ -418,20 +421,18 @@ knn_generic_kernel(const KnnGenericParams prm) {
         const float term = dist_term<NORM>(qsm[dd * THREADS + tid], pt[dd]);
         d = __fadd_rn(d, term);
       }
-      if (d <= dk) {
-        const uint64_t key = make_key(d, static_cast<uint32_t>(j0 + jl));
-        if (key < worst) {
-          int k = K - 1;
-          while (k > 0) {
-            const uint64_t prev = lists[static_cast<size_t>(k - 1) * THREADS + tid];
-            if (prev <= key) break;
-            lists[static_cast<size_t>(k) * THREADS + tid] = prev;
-            --k;
-          }
-          lists[static_cast<size_t>(k) * THREADS + tid] = key;
-          worst = lists[static_cast<size_t>(K - 1) * THREADS + tid];
-          if (worst != kEmptyKey) dk = key_dist(worst);
+      // total order on (dist, idx): finite < +inf < NaN, ties by lower index (common.cuh)
+      const uint64_t key = make_key_total(d, static_cast<uint32_t>(j0 + jl));
+      if (key < worst) {
+        int k = K - 1;
+        while (k > 0) {
+          const uint64_t prev = lists[static_cast<size_t>(k - 1) * THREADS + tid];
+          if (prev <= key) break;
+          lists[static_cast<size_t>(k) * THREADS + tid] = prev;
+          --k;
         }
+        lists[static_cast<size_t>(k) * THREADS + tid] = key;
+        worst = lists[static_cast<size_t>(K - 1) * THREADS + tid];
       }
     }
   }
@@ -492,6 +493,89 @@ __global__ void knn_backward_kernel(const float* __restrict__ p1, const float* _
   }
 }
 
+// D <= 4, K <= 1024: one thread per (row, k) ENTRY.  The CTA owns whole rows (rows_per_cta * K entries):
+// idx / grad_dists are read once, perfectly coalesced; the entry's diff vector goes to shared memory
+// and to grad_p2 -- for D = 3 as ONE 16-byte vector reduction (red.global.add.v4.f32) into a
+// (N*P2) float4 scratch that knn_backward_compact_kernel folds into the 12-byte rows afterwards: a
+// third of the L2 atomic operations, which are what bounds this kernel.  Then one thread per
+// (row, d) sums the row's K diffs in k order: grad_p1 is bit-exact vs knn_cpu.cpp:104-124.
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float2* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+template <int NORM, int DT>
+__global__ void __launch_bounds__(256)
+knn_backward_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                         const int64_t* __restrict__ len1, const int64_t* __restrict__ len2,
+                         const int64_t* __restrict__ idx, const float* __restrict__ grad_dists,
+                         int64_t total_rows, int P1, int P2, int K, int rows_per_cta,
+                         float* __restrict__ grad_p1, float* __restrict__ grad_p2,
+                         float4* __restrict__ scratch /* D = 3: (N*P2) float4, else nullptr */) {
+  extern __shared__ float diffs[];  // [rows_per_cta * K][DT]
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
+  const int rows = static_cast<int>(min(static_cast<int64_t>(rows_per_cta), total_rows - row0));
+  const int items = rows * K;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int r = it / K, k = it - r * K;
+    const int64_t row = row0 + r;
+    const int n = static_cast<int>(row / P1);
+    const int i1 = static_cast<int>(row - static_cast<int64_t>(n) * P1);
+    float df[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) df[d] = 0.0f;
+    const int64_t L1 = len1[n], L2 = len2[n];
+    if (i1 < L1 && k < L2) {  // k < min(L2, K)
+      const int64_t i2 = idx[row0 * K + it];
+      if (i2 >= 0 && i2 < P2) {  // -1 = padding (ball query)
+        const float g = grad_dists[row0 * K + it];
+        const float* a = p1 + row * DT;
+        const float* b = p2 + (static_cast<int64_t>(n) * P2 + i2) * DT;
+#pragma unroll
+        for (int d = 0; d < DT; ++d) {
+          // same float ops, same order as knn_cpu.cpp:113-122; intrinsics forbid contraction
+          if (NORM == 1) df[d] = __fmul_rn(g, (a[d] > b[d]) ? 1.0f : -1.0f);
+          else df[d] = __fmul_rn(__fmul_rn(2.0f, g), __fsub_rn(a[d], b[d]));
+        }
+        if (DT == 3 && scratch != nullptr) {
+          red_add_v4(scratch + static_cast<int64_t>(n) * P2 + i2, -df[0], -df[1 % DT], -df[2 % DT], 0.0f);
+        } else if (DT == 4 && (reinterpret_cast<uintptr_t>(grad_p2) & 15) == 0) {
+          red_add_v4(reinterpret_cast<float4*>(grad_p2) + static_cast<int64_t>(n) * P2 + i2, -df[0], -df[1 % DT],
+                     -df[2 % DT], -df[3 % DT]);
+        } else if (DT == 2 && (reinterpret_cast<uintptr_t>(grad_p2) & 7) == 0) {
+          red_add_v2(reinterpret_cast<float2*>(grad_p2) + static_cast<int64_t>(n) * P2 + i2, -df[0], -df[1 % DT]);
+        } else {
+          float* gp = grad_p2 + (static_cast<int64_t>(n) * P2 + i2) * DT;
+#pragma unroll
+          for (int d = 0; d < DT; ++d) atomicAdd(gp + d, -df[d]);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DT; ++d) diffs[it * DT + d] = df[d];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < rows * DT; t += blockDim.x) {
+    const int r = t / DT, d = t - r * DT;
+    const float* src = diffs + static_cast<size_t>(r) * K * DT + d;
+    float acc = 0.0f;
+    for (int k = 0; k < K; ++k) acc = __fadd_rn(acc, src[k * DT]);  // +0 for skipped entries: exact
+    grad_p1[row0 * DT + t] = acc;
+  }
+}
+
+// grad_p2 (rows of 3 floats) <- scratch (rows of 4 floats), flat over floats: coalesced both ways
+__global__ void knn_backward_compact_kernel(const float* __restrict__ scratch, int64_t total_floats,
+                                            float* __restrict__ grad_p2) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total_floats;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = e / 3;
+    grad_p2[e] = scratch[row * 4 + (e - row * 3)];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -499,6 +583,54 @@ namespace {
 
 constexpr int kTiledThreads = 128;
 constexpr size_t kMaxSmem = 227 * 1024;
+
+constexpr int kGenericThreads = 128;
+
+inline void generic_layout(int D, int K, int* TP, int* lists_in_smem, size_t* smem) {
+  const size_t qbytes = size_t(D) * kGenericThreads * 4;
+  int tp = static_cast<int>(std::max<size_t>(8, std::min<size_t>(256, (32 * 1024) / (size_t(D) * 4))));
+  size_t base = align_up(qbytes + size_t(tp) * D * 4, 8);
+  while (base > 96 * 1024 && tp > 1) {
+    tp /= 2;
+    base = align_up(qbytes + size_t(tp) * D * 4, 8);
+  }
+  const size_t lbytes = size_t(K) * kGenericThreads * 8;
+  *TP = tp;
+  *lists_in_smem = (base + lbytes <= 160 * 1024) ? 1 : 0;
+  *smem = base + (*lists_in_smem ? lbytes : 0);
+}
+
+// The exact thread-per-query kernel: the search itself for shapes no filtered path covers, the
+// recomputation pass behind the tensor-core path (flags), and -- gated per cloud by dirty_bits -- the
+// answer for clouds with non-finite or huge coordinates that the filtered searches skip.
+int run_generic(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1, int P2,
+                int D, int K, int norm, int64_t* idx, float* dists, uint64_t* glists, const unsigned char* flags,
+                const unsigned* flag_count, unsigned flag_limit, const unsigned* dirty_bits, cudaStream_t st) {
+  KnnGenericParams prm;
+  prm.flags = flags; prm.flag_count = flag_count; prm.flag_limit = flag_limit; prm.dirty_bits = dirty_bits;
+  prm.p1 = p1; prm.p2 = p2; prm.len1 = len1; prm.len2 = len2; prm.idx = idx; prm.dists = dists;
+  prm.glists = glists;
+  prm.P1 = P1; prm.P2 = P2; prm.D = D; prm.K = K;
+  size_t smem = 0;
+  generic_layout(D, K, &prm.TP, &prm.lists_in_smem, &smem);
+  if (smem > 227 * 1024) return fail(POPS_ERR_UNSUPPORTED, "knn: D too large for the generic kernel");
+  if (!prm.lists_in_smem && glists == nullptr)
+    return fail(POPS_ERR_UNSUPPORTED, "knn: K too large for the exact fallback of this path");
+  dim3 grid(static_cast<unsigned>(ceil_div(P1, kGenericThreads)), N);
+  profile_begin("knn_generic", st);
+  if (norm == 2) {
+    auto kern = knn_generic_kernel<2, kGenericThreads>;
+    POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<grid, kGenericThreads, smem, st>>>(prm);
+  } else {
+    auto kern = knn_generic_kernel<1, kGenericThreads>;
+    POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<grid, kGenericThreads, smem, st>>>(prm);
+  }
+  profile_end("knn_generic", st);
+  POPS_LAUNCH_OK("knn_generic_kernel");
+  return POPS_OK;
+}
 
 inline int pad_points(int64_t P2) {
   return static_cast<int>((P2 + kPadPoints - 1) / kPadPoints * kPadPoints);
@@ -536,9 +668,11 @@ int launch_ordered(const float* p1, const float* p2, const int64_t* len1, const 
   KnnOrderBuffers ob;
   knn_order_carve(ws, N, P1, P2, &ob);
   const bool self_knn = (p1 == p2) && (len1 == len2) && (P1 == P2);
-  const int rc = knn_order_prepass(p1, p2, len1, len2, N, P1, P2, self_knn, ob, st);
+  int rc = knn_order_prepass(p1, p2, len1, len2, N, P1, P2, self_knn, ob, st);
   if (rc != POPS_OK) return rc;
-  return knn_prune_search(ob, len1, len2, N, P1, P2, K, idx, dists, st);
+  rc = knn_prune_search(ob, len1, len2, N, P1, P2, K, idx, dists, st);
+  if (rc != POPS_OK) return rc;
+  return run_generic(p1, p2, len1, len2, N, P1, P2, 3, K, 2, idx, dists, nullptr, nullptr, nullptr, 0, ob.maxabs_bits, st);
 }
 
 template <int DT, int NORM, bool EXP>
@@ -553,41 +687,30 @@ int launch_tiled(const float* p1, const float* p2, const int64_t* len1, const in
     dim3 grid(static_cast<unsigned>(ceil_div(P2pad, 256)), N);
     knn_pack_kernel<DT, EXP><<<grid, 256, 0, st>>>(p2, len2, P2, P2pad, soa, maxabs);
     POPS_LAUNCH_OK("knn_pack_kernel");
-    if (EXP) {
-      dim3 g2(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, ceil_div(int64_t(P1) * DT, 1024)))), N);
-      maxabs_kernel<<<g2, 256, 0, st>>>(p1, len1, P1, DT, maxabs);
-      POPS_LAUNCH_OK("maxabs_kernel");
-    }
+    // p1 too: its magnitude enters the filter's error bound (EXP) and, for every variant, decides
+    // whether the cloud takes the exact generic kernel instead (non-finite / huge coordinates)
+    dim3 g2(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, ceil_div(int64_t(P1) * DT, 1024)))), N);
+    maxabs_kernel<<<g2, 256, 0, st>>>(p1, len1, P1, DT, maxabs);
+    POPS_LAUNCH_OK("maxabs_kernel");
   }
   KnnScanParams prm;
   prm.p1 = p1; prm.soa = soa; prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = maxabs;
   prm.idx = idx; prm.dists = dists; prm.P1 = P1; prm.P2 = P2; prm.P2pad = P2pad; prm.K = K;
+  int rc;
   if (EXP) {
     // register-merge buckets (KT = next power of two >= K)
-    if (K == 1) return launch_scan<DT, NORM, EXP, 4, EXP ? 1 : 0, 2048>(prm, N, st);
-    if (K <= 4) return launch_scan<DT, NORM, EXP, 4, EXP ? 4 : 0, 2048>(prm, N, st);
-    if (K <= 16) return launch_scan<DT, NORM, EXP, 4, EXP ? 16 : 0, 2048>(prm, N, st);
-    if (K <= 32) return launch_scan<DT, NORM, EXP, EXP ? 4 : 1, EXP ? 32 : 0, EXP ? 2048 : 1024>(prm, N, st);
-    return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
+    if (K == 1) rc = launch_scan<DT, NORM, EXP, 4, EXP ? 1 : 0, 2048>(prm, N, st);
+    else if (K <= 4) rc = launch_scan<DT, NORM, EXP, 4, EXP ? 4 : 0, 2048>(prm, N, st);
+    else if (K <= 16) rc = launch_scan<DT, NORM, EXP, 4, EXP ? 16 : 0, 2048>(prm, N, st);
+    else if (K <= 32) rc = launch_scan<DT, NORM, EXP, EXP ? 4 : 1, EXP ? 32 : 0, EXP ? 2048 : 1024>(prm, N, st);
+    else rc = launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
+  } else if (K <= 12) {
+    rc = launch_scan<DT, NORM, EXP, 4, 0, 2048>(prm, N, st);
+  } else {
+    rc = launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
   }
-  if (K <= 12) return launch_scan<DT, NORM, EXP, 4, 0, 2048>(prm, N, st);
-  return launch_scan<DT, NORM, EXP, 1, 0, 1024>(prm, N, st);
-}
-
-constexpr int kGenericThreads = 128;
-
-inline void generic_layout(int D, int K, int* TP, int* lists_in_smem, size_t* smem) {
-  const size_t qbytes = size_t(D) * kGenericThreads * 4;
-  int tp = static_cast<int>(std::max<size_t>(8, std::min<size_t>(256, (32 * 1024) / (size_t(D) * 4))));
-  size_t base = align_up(qbytes + size_t(tp) * D * 4, 8);
-  while (base > 96 * 1024 && tp > 1) {
-    tp /= 2;
-    base = align_up(qbytes + size_t(tp) * D * 4, 8);
-  }
-  const size_t lbytes = size_t(K) * kGenericThreads * 8;
-  *TP = tp;
-  *lists_in_smem = (base + lbytes <= 160 * 1024) ? 1 : 0;
-  *smem = base + (*lists_in_smem ? lbytes : 0);
+  if (rc != POPS_OK) return rc;
+  return run_generic(p1, p2, len1, len2, N, P1, P2, DT, K, NORM, idx, dists, nullptr, nullptr, nullptr, 0, maxabs, st);
 }
 
 }  // namespace
@@ -648,37 +771,19 @@ extern "C" int pops_knn_points_idx(const float* p1, const float* p2, const int64
   POPS_TILED(1, 1, false)
 #undef POPS_TILED
   // generic (also the exact recomputation pass behind the tensor-core path)
-  KnnGenericParams prm;
-  prm.flags = nullptr; prm.flag_count = nullptr; prm.flag_limit = 0;
+  const unsigned char* flags = nullptr;
+  const unsigned* flag_count = nullptr;
+  unsigned flag_limit = 0;
   if (knn_tc_supported(P1, P2, D, K, norm)) {
     const size_t goff = align_up(size_t(N) * ceil_div(P1, kGenericThreads) * K * kGenericThreads * 8, 256);
-    unsigned char* flags = nullptr;
+    unsigned char* f = nullptr;
     const int rc = knn_tc_search(p1, p2, lengths1, lengths2, n, p1n, p2n, int(D), k, idx, dists,
-                                 reinterpret_cast<char*>(workspace) + goff, &flags, &prm.flag_count,
-                                 &prm.flag_limit, st);
+                                 reinterpret_cast<char*>(workspace) + goff, &f, &flag_count, &flag_limit, st);
     if (rc != POPS_OK) return rc;
-    prm.flags = flags;
+    flags = f;
   }
-  prm.p1 = p1; prm.p2 = p2; prm.len1 = lengths1; prm.len2 = lengths2; prm.idx = idx; prm.dists = dists;
-  prm.glists = reinterpret_cast<uint64_t*>(workspace);
-  prm.P1 = p1n; prm.P2 = p2n; prm.D = int(D); prm.K = k;
-  size_t smem = 0;
-  generic_layout(int(D), k, &prm.TP, &prm.lists_in_smem, &smem);
-  if (smem > kMaxSmem) return fail(POPS_ERR_UNSUPPORTED, "knn: D too large for the generic kernel");
-  dim3 grid(static_cast<unsigned>(ceil_div(P1, kGenericThreads)), n);
-  profile_begin("knn_generic", st);
-  if (norm == 2) {
-    auto kern = knn_generic_kernel<2, kGenericThreads>;
-    POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<grid, kGenericThreads, smem, st>>>(prm);
-  } else {
-    auto kern = knn_generic_kernel<1, kGenericThreads>;
-    POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<grid, kGenericThreads, smem, st>>>(prm);
-  }
-  profile_end("knn_generic", st);
-  POPS_LAUNCH_OK("knn_generic_kernel");
-  return POPS_OK;
+  return run_generic(p1, p2, lengths1, lengths2, n, p1n, p2n, int(D), k, norm, idx, dists,
+                     reinterpret_cast<uint64_t*>(workspace), flags, flag_count, flag_limit, nullptr, st);
 }
 
 // ---- two-phase form for host pipelines (host.py: HostKnn) ---------------------------------------
@@ -737,8 +842,12 @@ extern "C" int pops_knn_points_idx_range(const float* p1, const float* p2, const
   ob.boxes += size_t(n0) * nbox * 2;
   ob.qsorted += size_t(n0) * P1;
   ob.qhome += size_t(n0) * P1;
-  return knn_prune_search(ob, lengths1 + n0, lengths2 + n0, int(n1 - n0), int(P1), int(P2), int(K), idx_r, dists_r,
-                          static_cast<cudaStream_t>(stream));
+  const int rc = knn_prune_search(ob, lengths1 + n0, lengths2 + n0, int(n1 - n0), int(P1), int(P2), int(K), idx_r,
+                                  dists_r, static_cast<cudaStream_t>(stream));
+  if (rc != POPS_OK) return rc;
+  return run_generic(p1 + size_t(n0) * P1 * D, p2 + size_t(n0) * P2 * D, lengths1 + n0, lengths2 + n0, int(n1 - n0),
+                     int(P1), int(P2), 3, int(K), 2, idx_r, dists_r, nullptr, nullptr, nullptr, 0, ob.maxabs_bits,
+                     static_cast<cudaStream_t>(stream));
 }
 
 // ---- both directions of a two-sided search (chamfer) ------------------------------------------------
@@ -785,22 +894,41 @@ extern "C" int pops_knn_points_idx_pair(const float* p1, const float* p2, const 
   if (rc != POPS_OK) return rc;
   rc = knn_prune_search(a, lengths1, lengths2, int(N), int(P1), int(P2), int(K), idx12, dists12, st);
   if (rc != POPS_OK) return rc;
-  return knn_prune_search(b, lengths2, lengths1, int(N), int(P2), int(P1), int(K), idx21, dists21, st);
+  rc = knn_prune_search(b, lengths2, lengths1, int(N), int(P2), int(P1), int(K), idx21, dists21, st);
+  if (rc != POPS_OK) return rc;
+  // clouds with non-finite / huge coordinates (a.maxabs_bits spans both tensors) take the exact kernel
+  rc = run_generic(p1, p2, lengths1, lengths2, int(N), int(P1), int(P2), 3, int(K), 2, idx12, dists12, nullptr, nullptr,
+                   nullptr, 0, a.maxabs_bits, st);
+  if (rc != POPS_OK) return rc;
+  return run_generic(p2, p1, lengths2, lengths1, int(N), int(P2), int(P1), 3, int(K), 2, idx21, dists21, nullptr,
+                     nullptr, nullptr, 0, a.maxabs_bits, st);
 }
 
-extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const int64_t* lengths1,
-                                        const int64_t* lengths2, const int64_t* idx,
-                                        const float* grad_dists, int64_t N, int64_t P1, int64_t P2,
-                                        int64_t D, int64_t K, int norm, float* grad_p1,
-                                        float* grad_p2, pops_stream_t stream) {
+extern "C" size_t pops_knn_backward_workspace_bytes(int64_t N, int64_t P2, int64_t D) {
+  return (D == 3 && N > 0 && P2 > 0) ? size_t(N) * size_t(P2) * 16 + 256 : 256;
+}
+
+extern "C" int pops_knn_points_backward_ws(const float* p1, const float* p2, const int64_t* lengths1,
+                                           const int64_t* lengths2, const int64_t* idx,
+                                           const float* grad_dists, int64_t N, int64_t P1, int64_t P2,
+                                           int64_t D, int64_t K, int norm, float* grad_p1,
+                                           float* grad_p2, void* workspace, size_t workspace_bytes,
+                                           pops_stream_t stream) {
   POPS_CHECK_ARG(norm == 1 || norm == 2, "Norm must be 1 or 2.");
   POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0 && K >= 0, "negative size");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t total = size_t(N) * P1 * D;
+  const bool rows_path = D >= 1 && D <= 4 && K >= 1 && K <= 1024 && get_option("knn_backward_rows", 1) != 0;
+  float4* scratch = nullptr;
+  if (rows_path && D == 3 && workspace != nullptr &&
+      workspace_bytes >= pops_knn_backward_workspace_bytes(N, P2, D) &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && total > 0 && P2 > 0)
+    scratch = reinterpret_cast<float4*>(workspace);
   if (N * P2 * D > 0) {
     POPS_CHECK_ARG(grad_p2, "null grad_p2");
-    POPS_CUDA_OK(cudaMemsetAsync(grad_p2, 0, size_t(N) * P2 * D * 4, st));
+    if (scratch) POPS_CUDA_OK(cudaMemsetAsync(scratch, 0, size_t(N) * P2 * 16, st));
+    else POPS_CUDA_OK(cudaMemsetAsync(grad_p2, 0, size_t(N) * P2 * D * 4, st));
   }
-  const size_t total = size_t(N) * P1 * D;
   if (total == 0) return POPS_OK;
   POPS_CHECK_ARG(p1 && lengths1 && lengths2 && grad_p1, "null pointer argument");
   if (K == 0 || P2 == 0) {
@@ -808,9 +936,38 @@ extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const 
     return POPS_OK;
   }
   POPS_CHECK_ARG(p2 && idx && grad_dists, "null pointer argument");
+  profile_begin("knn_backward", st);
+  if (rows_path) {
+    const int rows_per_cta = std::max(1, 1024 / int(K));
+    const int64_t rows = N * P1;
+    const unsigned grid = static_cast<unsigned>(ceil_div(rows, rows_per_cta));
+    const size_t smem = size_t(rows_per_cta) * K * D * 4;
+#define POPS_BWD(NORM, DT)                                                                                  \
+  knn_backward_rows_kernel<NORM, DT><<<grid, 256, smem, st>>>(p1, p2, lengths1, lengths2, idx, grad_dists,  \
+                                                              rows, int(P1), int(P2), int(K), rows_per_cta, \
+                                                              grad_p1, grad_p2, scratch)
+#define POPS_BWD_D(NORM)                 \
+  switch (D) {                           \
+    case 1: POPS_BWD(NORM, 1); break;    \
+    case 2: POPS_BWD(NORM, 2); break;    \
+    case 3: POPS_BWD(NORM, 3); break;    \
+    default: POPS_BWD(NORM, 4); break;   \
+  }
+    if (norm == 2) { POPS_BWD_D(2) } else { POPS_BWD_D(1) }
+#undef POPS_BWD_D
+#undef POPS_BWD
+    POPS_LAUNCH_OK("knn_backward_rows_kernel");
+    if (scratch) {
+      const int64_t floats = N * P2 * 3;
+      const int blocks = int(std::min<int64_t>(ceil_div(floats, 256), int64_t(num_sms()) * 16));
+      knn_backward_compact_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), floats, grad_p2);
+      POPS_LAUNCH_OK("knn_backward_compact_kernel");
+    }
+    profile_end("knn_backward", st);
+    return POPS_OK;
+  }
   const int threads = 256;
   const int blocks = int(std::min<int64_t>(ceil_div(int64_t(total), threads), int64_t(num_sms()) * 16));
-  profile_begin("knn_backward", st);
   if (norm == 2)
     knn_backward_kernel<2><<<blocks, threads, 0, st>>>(p1, p2, lengths1, lengths2, idx, grad_dists,
                                                        int(N), int(P1), int(P2), int(D), int(K),
@@ -822,4 +979,13 @@ extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const 
   profile_end("knn_backward", st);
   POPS_LAUNCH_OK("knn_backward_kernel");
   return POPS_OK;
+}
+
+extern "C" int pops_knn_points_backward(const float* p1, const float* p2, const int64_t* lengths1,
+                                        const int64_t* lengths2, const int64_t* idx,
+                                        const float* grad_dists, int64_t N, int64_t P1, int64_t P2,
+                                        int64_t D, int64_t K, int norm, float* grad_p1,
+                                        float* grad_p2, pops_stream_t stream) {
+  return pops_knn_points_backward_ws(p1, p2, lengths1, lengths2, idx, grad_dists, N, P1, P2, D, K, norm, grad_p1,
+                                     grad_p2, nullptr, 0, stream);
 }

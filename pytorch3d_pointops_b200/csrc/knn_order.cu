@@ -87,6 +87,16 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sm) {
   return v;
 }
 
+__device__ __forceinline__ unsigned block_reduce_umax(unsigned v, unsigned* sm) {
+  v = __reduce_max_sync(0xffffffffu, v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  v = (lane < nw) ? sm[lane] : 0u;
+  return __reduce_max_sync(0xffffffffu, v);
+}
+
 constexpr int kBboxCluster = 8;   // CTAs per cloud (one thread-block cluster)
 constexpr int kBboxThreads = 256;
 
@@ -129,19 +139,19 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > P2 ? P2 : L2l));
   const float* b = p2 + static_cast<size_t>(n) * P2 * 3;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  unsigned mb = 0u;  // max |coordinate| of everything read, as a bit pattern (+inf and NaN rank highest)
   for (int j = t0; j < L2; j += stride) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const float v = b[static_cast<size_t>(j) * 3 + d];
       mn[d] = fminf(mn[d], v);
       mx[d] = fmaxf(mx[d], v);
+      mb = max(mb, abs_bits(v));
     }
   }
-  bool none = L2 == 0;
   if (union_box) {  // pair pre-pass: one grid over both clouds
     int64_t L1l = len1[n];
     const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
-    none = none && L1 == 0;
     const float* a = p1 + static_cast<size_t>(n) * P1 * 3;
     for (int j = t0; j < L1; j += stride) {
 #pragma unroll
@@ -149,15 +159,15 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         const float v = a[static_cast<size_t>(j) * 3 + d];
         mn[d] = fminf(mn[d], v);
         mx[d] = fmaxf(mx[d], v);
+        mb = max(mb, abs_bits(v));
       }
     }
   }
-  float m1 = 0.0f;  // max |coordinate| of p1 when it is not part of the box
-  if (!self_knn && !union_box) {
+  if (!self_knn && !union_box) {  // p1 is not part of the box, but its magnitude counts
     int64_t L1l = len1[n];
     const int L1 = static_cast<int>(L1l < 0 ? 0 : (L1l > P1 ? P1 : L1l));
     const float* a = p1 + static_cast<size_t>(n) * P1 * 3;
-    for (int e = t0; e < L1 * 3; e += stride) m1 = fmaxf(m1, fabsf(a[e]));
+    for (int e = t0; e < L1 * 3; e += stride) mb = max(mb, abs_bits(a[e]));
   }
   float out[7];
 #pragma unroll
@@ -165,7 +175,7 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     out[d] = block_reduce(mn[d], false, sm);
     out[3 + d] = block_reduce(mx[d], true, sm);
   }
-  out[6] = block_reduce(m1, true, sm);
+  out[6] = __uint_as_float(block_reduce_umax(mb, reinterpret_cast<unsigned*>(sm)));  // bits carried through, never used as a float
   bb_cluster_wait();  // every CTA of the cluster is running: its shared memory can be written
   if (threadIdx.x < 7) {
     float v = out[0];
@@ -183,16 +193,11 @@ bbox_maxabs_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         out[d] = fminf(out[d], part[r][d]);
         out[3 + d] = fmaxf(out[3 + d], part[r][3 + d]);
       }
-      out[6] = fmaxf(out[6], part[r][6]);
+      out[6] = __uint_as_float(max(__float_as_uint(out[6]), __float_as_uint(part[r][6])));
     }
-    float m = 0.0f;  // from the REDUCED box: threads that saw no point still hold the +-FLT_MAX seeds
-#pragma unroll
-    for (int d = 0; d < 3; ++d) m = fmaxf(m, fmaxf(fabsf(out[d]), fabsf(out[3 + d])));
-    if (none) m = 0.0f;
-    m = fmaxf(m, out[6]);
 #pragma unroll
     for (int d = 0; d < 6; ++d) bbox[n * 6 + d] = out[d];
-    maxabs_bits[n] = __float_as_uint(m);
+    maxabs_bits[n] = __float_as_uint(out[6]);
   }
 }
 
@@ -475,25 +480,28 @@ order_cloud_kernel(const FusedOrderParams prm) {
 
   // ---- 1. box of both tensors ---------------------------------------------------------------------
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  unsigned mb = 0u;  // max |coordinate| as a bit pattern (+inf and NaN rank highest)
   for (int j = tid; j < L; j += kFusedThreads) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const float v = pts[static_cast<size_t>(j) * 3 + d];
       mn[d] = fminf(mn[d], v);
       mx[d] = fmaxf(mx[d], v);
+      mb = max(mb, abs_bits(v));
     }
   }
-  float out[6];
+  float out[7];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     out[d] = block_reduce(mn[d], false, red);
     out[3 + d] = block_reduce(mx[d], true, red);
   }
+  out[6] = __uint_as_float(block_reduce_umax(mb, reinterpret_cast<unsigned*>(red)));  // bits, never used as a float
   bb_cluster_wait();  // the peer CTA is running: its shared memory can be written
-  if (tid < 6) {
+  if (tid < 7) {
     float v = out[0];
 #pragma unroll
-    for (int d = 1; d < 6; ++d) v = (tid == d) ? out[d] : v;
+    for (int d = 1; d < 7; ++d) v = (tid == d) ? out[d] : v;
     for (int r = 0; r < T; ++r) bb_st_remote(&part[t][tid], static_cast<uint32_t>(r), v);
   }
   if (T > 1) bb_cluster_barrier(); else __syncthreads();
@@ -508,13 +516,11 @@ order_cloud_kernel(const FusedOrderParams prm) {
   }
   __syncthreads();
   if (t == 0 && tid == 0) {
-    float m = 0.0f;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) m = fmaxf(m, fmaxf(fabsf(bb[d]), fabsf(bb[3 + d])));
-    if (bb[0] == FLT_MAX) m = 0.0f;  // no valid point in either tensor
+    unsigned m = __float_as_uint(part[0][6]);
+    if (T > 1) m = max(m, __float_as_uint(part[1][6]));
 #pragma unroll
     for (int d = 0; d < 6; ++d) prm.a.bbox[n * 6 + d] = bb[d];
-    prm.a.maxabs_bits[n] = __float_as_uint(m);
+    prm.a.maxabs_bits[n] = m;
   }
 
   // ---- 2. codes + sort (blocked arrangement: thread tid holds positions tid*ITEMS + i) ------------
@@ -650,7 +656,8 @@ int fused_order(const float* p1, const float* p2, const int64_t* len1, const int
   // clouds are large (T shape, N = 32: 0.96 vs 0.915 ms per call); up to 8192 points the single launch
   // wins on hosts where the step is launch-bound (chamfer step 0.50 vs 0.60 ms) and costs ~4 % where it
   // is not (0.446 vs 0.427 ms)
-  if (Pmax > kFusedThreads * get_option("knn_fused_items", 8) || get_option("knn_fused_prepass", 1) == 0) return -1;
+  const int items = get_option("knn_fused_items", 8) <= 8 ? 8 : 16;  // the two compiled forms; nothing larger exists
+  if (Pmax > kFusedThreads * items || get_option("knn_fused_prepass", 1) == 0) return -1;
   FusedOrderParams prm;
   prm.p[0] = p2; prm.p[1] = p1; prm.len[0] = len2; prm.len[1] = len1; prm.P[0] = P2; prm.P[1] = P1;
   prm.mode = mode;

@@ -244,6 +244,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   float* out_d = prm.dists + (static_cast<size_t>(n) * prm.P1) * K;
   const float4* qs = prm.qsorted + static_cast<size_t>(n) * prm.P1;
   const float INF = __int_as_float(0x7f800000);
+  if (prm.maxabs_bits[n] >= kDirtyBits) return;  // non-finite / huge coordinates: the exact generic kernel answers this cloud
 
   // CTA entirely beyond lengths1[n] (or nothing to search): rows are (0, 0).
   if (q_base >= L1 || L2 == 0) {

@@ -637,6 +637,7 @@ struct TcRerankParams {
   const float* tfin;      // [N][P1]
   const float* xq;        // [N][P1pad]
   const unsigned* maxw_bits;
+  const unsigned* maxq_bits;  // max |x|^2 per cloud (bits), like maxw_bits for p2
   int64_t* idx;
   float* dists;
   unsigned char* flags;  // [N][P1]: 1 = recompute exactly
@@ -673,6 +674,9 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
   for (int d = lane; d < D; d += 32) x[d] = xg[d];
   __syncwarp();
   const float E = tc_error_bound(prm.xq[static_cast<size_t>(n) * prm.P1pad + qi], __uint_as_float(prm.maxw_bits[n]), D);
+  // a squared norm that is +inf, NaN or beyond 1e36 voids the filter's error bound for the whole cloud
+  // (common.cuh): every one of its queries goes to the exact recomputation
+  const bool dirty = prm.maxw_bits[n] >= kDirtyNormBits || prm.maxq_bits[n] >= kDirtyNormBits;
 
   // the 32 smallest (s, j) among the query's candidates, ascending along the lanes: every chunk of
   // 32 candidates is sorted (bitonic network over shuffles); min(run[i], chunk[31-i]) holds the 32
@@ -705,9 +709,9 @@ __global__ void __launch_bounds__(128) knn_tc_rerank_kernel(const TcRerankParams
   const float Tfin = prm.tfin[qrow];
   const unsigned lt_mask = (1u << lane) - 1u;
   uint64_t run = kEmptyKey;
-  bool unsure = false;
+  bool unsure = dirty;
   unsigned total = 0, fill = 0;
-  for (int h = 0; h < TC_HALVES; ++h) {
+  for (int h = 0; h < (dirty ? 0 : TC_HALVES); ++h) {
     const unsigned raw = prm.counts[qrow * TC_HALVES + h];
     unsure = unsure || (raw >> 31) != 0;  // the candidate array overflowed
     const unsigned cnt = raw & 0x7fffffffu;
@@ -856,7 +860,7 @@ knn_exact_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2
       }
       const int j = base + lane;
       if (j < L2) {
-        const uint64_t key = make_key(dist, static_cast<uint32_t>(j));
+        const uint64_t key = make_key_total(dist, static_cast<uint32_t>(j));  // finite < +inf < NaN (common.cuh)
         if (key < Lr[KT - 1]) insert_network<KT>(Lr, key);
       }
     }
@@ -1047,7 +1051,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
     POPS_LAUNCH_OK("knn_tc_scan_kernel");
   }
   TcRerankParams rp;
-  rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.cands = cands; rp.counts = counts; rp.tfin = tfin; rp.xq = xq; rp.maxw_bits = maxw;
+  rp.p1 = p1; rp.p2 = p2; rp.len1 = len1; rp.len2 = len2; rp.cands = cands; rp.counts = counts; rp.tfin = tfin; rp.xq = xq; rp.maxw_bits = maxw; rp.maxq_bits = maxq;
   rp.idx = idx; rp.dists = dists; rp.flags = flags; rp.flag_rows = flag_rows; rp.P1 = P1; rp.P2 = P2; rp.P1pad = l.P1pad; rp.D = D; rp.K = K;
   rp.debug = get_option("knn_stats", 0);
   {

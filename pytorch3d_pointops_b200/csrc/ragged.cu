@@ -12,82 +12,153 @@
 
 namespace pops {
 
+// Both copies are batches of contiguous segment copies: cloud b owns the packed floats
+// [first[b]*D, first[b+1]*D) and the padded floats [b*max*D, (b+1)*max*D).  grid.y walks the clouds,
+// so no thread divides by D or max_size; the destination is written as aligned 16-byte chunks
+// (chunk c of the cloud's segment covers floats [4c - a, 4c - a + 4), a = misalignment of the
+// segment start in floats), the source with 4-byte loads (its alignment differs from the
+// destination's; the four loads of a chunk hit the same L1 lines).  Every destination float is
+// written exactly once, zero padding included.
+__device__ __forceinline__ void store_chunk(float* __restrict__ dst_seg, int64_t f0, int64_t F, const float (&v)[4]) {
+  if (f0 >= 0 && f0 + 4 <= F) {
+    *reinterpret_cast<float4*>(dst_seg + f0) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (f0 + e >= 0 && f0 + e < F) dst_seg[f0 + e] = v[e];
+  }
+}
+
 // padded[b, i, :] = i < num_b ? packed[first[b] + i, :] : 0
-__global__ void packed_to_padded_kernel(const float* __restrict__ packed,
-                                        const int64_t* __restrict__ first, int64_t num_inputs,
-                                        int B, int64_t max_size, int D, float* __restrict__ padded) {
-  const int64_t total = static_cast<int64_t>(B) * max_size * D;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int d = static_cast<int>(e % D);
-    const int64_t row = e / D;
-    const int b = static_cast<int>(row / max_size);
-    const int64_t i = row % max_size;
+__global__ void __launch_bounds__(256)
+packed_to_padded_kernel(const float* __restrict__ packed, const int64_t* __restrict__ first,
+                        int64_t num_inputs, int B, int64_t max_size, int D, float* __restrict__ padded) {
+  const int64_t F = max_size * D;  // floats per padded cloud
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const int64_t start = first[b];
     const int64_t end = (b + 1 < B) ? first[b + 1] : num_inputs;
-    float v = 0.0f;
-    if (i < end - start && start + i < num_inputs && start + i >= 0) v = packed[(start + i) * D + d];
-    padded[e] = v;
-  }
-}
-
-// packed[f, :] = padded[b(f), f - first[b], :]  (0 when the row is not covered by any cloud or
-// lies beyond max_size).  b(f) by binary search over first_idxs (non-decreasing).
-__global__ void padded_to_packed_kernel(const float* __restrict__ padded,
-                                        const int64_t* __restrict__ first, int64_t num_inputs,
-                                        int B, int64_t max_size, int D, float* __restrict__ packed) {
-  const int64_t total = num_inputs * D;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int d = static_cast<int>(e % D);
-    const int64_t f = e / D;
-    // last b with first[b] <= f  (for equal starts the LAST cloud is the non-empty one)
-    int lo = 0, hi = B;  // invariant: first[lo] <= f (if any), answer in [lo, hi)
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (first[mid] <= f) lo = mid; else hi = mid;
-    }
-    float v = 0.0f;
-    const int64_t start = first[lo];
-    const int64_t i = f - start;
-    if (i >= 0 && i < max_size) v = padded[(static_cast<int64_t>(lo) * max_size + i) * D + d];
-    packed[e] = v;
-  }
-}
-
-// out[n, l, k, :] = x[n, idx[n,l,k], :] with masking.  One thread per (row, 4-float chunk) when
-// U % 4 == 0 and rows are 16-byte aligned, else one thread per element.
-template <int MODE, int VEC>
-__global__ void gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
-                              const int64_t* __restrict__ lengths, int64_t rows_per_cloud /*L*K*/,
-                              int K, int M, int U, int64_t total_rows, float* __restrict__ out,
-                              int32_t* __restrict__ oob) {
-  const int UV = U / VEC;
-  const int64_t total = total_rows * UV;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int u = static_cast<int>(e % UV);
-    const int64_t row = e / UV;  // (n*L + l)*K + k
-    const int n = static_cast<int>(row / rows_per_cloud);
-    const int k = static_cast<int>(row % K);
-    int64_t j = idx[row];
-    bool take = true;
-    if (MODE == POPS_GATHER_KNN) {
-      if (lengths != nullptr && k >= lengths[n]) take = false;
-      if (take && (j < 0 || j >= M)) {
-        take = false;
-        if (oob != nullptr) *oob = 1;
+    // rows [start, start + num) exist in packed; clamp against garbage first_idxs
+    int64_t num = end - start;
+    if (start < 0 || num < 0) num = 0;
+    if (num > max_size) num = max_size;
+    if (start + num > num_inputs) num = num_inputs - start > 0 ? num_inputs - start : 0;
+    const int64_t live = num * D;  // floats copied; the rest of the segment is zero
+    float* dst = padded + static_cast<int64_t>(b) * F;
+    const float* src = packed + start * D;
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
+    const int64_t nchunks = (F + a + 3) >> 2;
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks;
+         c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t f0 = 4 * c - a;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t f = f0 + e;
+        v[e] = (f >= 0 && f < live) ? __ldg(src + f) : 0.0f;
       }
-    } else {
-      if (j < 0 || j >= M) take = false;  // -1 = padding
+      store_chunk(dst, f0, F, v);
     }
-    const float* src = x + (static_cast<int64_t>(n) * M + (take ? j : 0)) * U;
-    if (VEC == 4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (take) v = reinterpret_cast<const float4*>(src)[u];
-      reinterpret_cast<float4*>(out + row * U)[u] = v;
-    } else {
-      out[row * U + u] = take ? src[u] : 0.0f;
+  }
+}
+
+// packed[f, :] = padded[b(f), f - first[b], :] for first[b] <= f < first[b+1], 0 beyond max_size and
+// for rows no cloud covers (f < first[0]); cloud 0 also zero-fills the rows before first[0].
+__global__ void __launch_bounds__(256)
+padded_to_packed_kernel(const float* __restrict__ padded, const int64_t* __restrict__ first,
+                        int64_t num_inputs, int B, int64_t max_size, int D, float* __restrict__ packed) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    int64_t start = first[b];
+    int64_t end = (b + 1 < B) ? first[b + 1] : num_inputs;
+    start = start < 0 ? 0 : (start > num_inputs ? num_inputs : start);
+    end = end < start ? start : (end > num_inputs ? num_inputs : end);
+    int64_t num = end - start;
+    if (num > max_size) num = max_size;
+    const int64_t live = num * D;
+    const int64_t lead = (b == 0) ? start * D : 0;  // zero rows in front of the first cloud
+    const int64_t F = (end - start) * D + lead;
+    float* dst = packed + start * D - lead;
+    const float* src = padded + static_cast<int64_t>(b) * max_size * D;
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
+    const int64_t nchunks = (F + a + 3) >> 2;
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks;
+         c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t f0 = 4 * c - a;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t f = f0 + e - lead;
+        v[e] = (f >= 0 && f < live) ? __ldg(src + f) : 0.0f;
+      }
+      store_chunk(dst, f0, F, v);
+    }
+  }
+}
+
+// out[n, l, k, :] = x[n, idx[n,l,k], :] with masking.  grid.y walks the clouds; within a cloud the
+// OUTPUT is a flat float stream written as aligned 16-byte chunks (perfectly coalesced stores for
+// any U, e.g. the 12-byte rows of U = 3); a chunk spans at most 4 rows, whose indices are read as
+// the stream advances.  The gathered reads hit L1/L2 (a cloud's x is small).  UT: compile-time U
+// (0 = runtime).  V4: U % 4 == 0 and 16-byte aligned x -> one 16-byte source load per chunk.
+template <int MODE, int UT, bool V4>
+__global__ void __launch_bounds__(256)
+gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
+              const int64_t* __restrict__ lengths, unsigned LK /*L*K rows per cloud*/, unsigned K, int M,
+              unsigned U_rt, int N, float* __restrict__ out, int32_t* __restrict__ oob) {
+  const unsigned U = UT ? UT : U_rt;
+  const int64_t F = static_cast<int64_t>(LK) * U;  // floats of one cloud's output (< 2^31, host-checked)
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    float* dst = out + static_cast<int64_t>(n) * F;
+    const int64_t* idx_n = idx + static_cast<int64_t>(n) * LK;
+    const float* x_n = x + static_cast<int64_t>(n) * M * U;
+    // knn_gather zeroes slots k >= lengths[n]; only clouds shorter than K need k at all
+    unsigned klim = K;
+    if (MODE == POPS_GATHER_KNN && lengths != nullptr) {
+      const int64_t len = lengths[n];
+      klim = len < 0 ? 0u : (len < static_cast<int64_t>(K) ? static_cast<unsigned>(len) : K);
+    }
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
+    const unsigned nchunks = static_cast<unsigned>((F + a + 3) >> 2);
+    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.x * blockDim.x) {
+      const int f0 = static_cast<int>(4u * c) - a;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const unsigned fs = f0 < 0 ? 0u : static_cast<unsigned>(f0);
+      unsigned row = fs / U, u = fs - row * U;
+      if (V4) {  // chunk = 4 consecutive floats of ONE row, a == 0
+        if (row < LK) {
+          const int64_t j = idx_n[row];
+          bool take = (j >= 0 && j < M);
+          if (MODE == POPS_GATHER_KNN) {
+            const bool live = klim == K || (row % K) < klim;
+            if (live && !take && oob != nullptr) *oob = 1;
+            take = take && live;
+          }
+          if (take) {
+            const float4 s = *reinterpret_cast<const float4*>(x_n + j * U + u);
+            v[0] = s.x; v[1] = s.y; v[2] = s.z; v[3] = s.w;
+          }
+        }
+      } else {
+        int64_t j = -1;
+        bool take = false, fresh = true;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int f = f0 + e;
+          if (f < 0 || f >= F) continue;
+          if (fresh) {
+            j = idx_n[row];
+            take = (j >= 0 && j < M);
+            if (MODE == POPS_GATHER_KNN) {
+              const bool live = klim == K || (row % K) < klim;
+              if (live && !take && oob != nullptr) *oob = 1;
+              take = take && live;
+            }
+            fresh = false;
+          }
+          if (take) v[e] = __ldg(x_n + j * U + u);
+          if (++u == U) { u = 0; ++row; fresh = true; }
+        }
+      }
+      store_chunk(dst, f0, F, v);
     }
   }
 }
@@ -170,6 +241,15 @@ inline int flat_grid(int64_t total, int threads) {
   return int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, threads), int64_t(num_sms()) * 32)));
 }
 
+// grid for a batch of per-cloud segments: y = clouds, x = enough CTAs for the longest segment, capped so
+// that the whole grid is a few waves of the machine (threads loop over the rest)
+inline dim3 segment_grid(int64_t chunks_per_cloud, int64_t clouds, int threads) {
+  const int64_t gy = std::max<int64_t>(1, std::min<int64_t>(clouds, 65535));
+  const int64_t want = std::max<int64_t>(1, ceil_div(chunks_per_cloud, threads));
+  const int64_t cap = std::max<int64_t>(1, ceil_div(int64_t(num_sms()) * 32, gy));
+  return dim3(static_cast<unsigned>(std::min(want, cap)), static_cast<unsigned>(gy));
+}
+
 }  // namespace pops
 
 using namespace pops;
@@ -182,8 +262,13 @@ extern "C" int pops_packed_to_padded(const float* packed, const int64_t* first_i
   if (total == 0) return POPS_OK;
   POPS_CHECK_ARG(first_idxs && padded && (packed || num_inputs == 0), "null pointer argument");
   POPS_CHECK_ARG(B < (int64_t(1) << 31) && D < (int64_t(1) << 31), "size too large");
-  packed_to_padded_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  POPS_CHECK_ARG(reinterpret_cast<uintptr_t>(padded) % 4 == 0 && reinterpret_cast<uintptr_t>(packed) % 4 == 0,
+                 "float buffers must be 4-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  profile_begin("packed_to_padded", st);
+  packed_to_padded_kernel<<<segment_grid(ceil_div(max_size * D + 3, 4), B, 256), 256, 0, st>>>(
       packed, first_idxs, num_inputs, int(B), max_size, int(D), padded);
+  profile_end("packed_to_padded", st);
   POPS_LAUNCH_OK("packed_to_padded_kernel");
   return POPS_OK;
 }
@@ -202,8 +287,14 @@ extern "C" int pops_padded_to_packed(const float* padded, const int64_t* first_i
   }
   POPS_CHECK_ARG(first_idxs && padded, "null pointer argument");
   POPS_CHECK_ARG(B < (int64_t(1) << 31) && D < (int64_t(1) << 31), "size too large");
-  padded_to_packed_kernel<<<flat_grid(total, 256), 256, 0, st>>>(padded, first_idxs, num_inputs,
-                                                                 int(B), max_size, int(D), packed);
+  POPS_CHECK_ARG(reinterpret_cast<uintptr_t>(padded) % 4 == 0 && reinterpret_cast<uintptr_t>(packed) % 4 == 0,
+                 "float buffers must be 4-byte aligned");
+  // a cloud's packed segment is at most num_inputs rows; size x for the padded capacity (the usual case)
+  // and let threads loop when first_idxs hands one cloud more rows than that
+  profile_begin("padded_to_packed", st);
+  padded_to_packed_kernel<<<segment_grid(ceil_div(std::min(max_size, num_inputs) * D + 3, 4), B, 256), 256, 0, st>>>(
+      padded, first_idxs, num_inputs, int(B), max_size, int(D), packed);
+  profile_end("padded_to_packed", st);
   POPS_LAUNCH_OK("padded_to_packed_kernel");
   return POPS_OK;
 }
@@ -217,17 +308,27 @@ extern "C" int pops_gather(const float* x, const int64_t* idx, const int64_t* le
   if (rows * U == 0) return POPS_OK;
   POPS_CHECK_ARG(idx && out && (x || M == 0), "null pointer argument");
   POPS_CHECK_ARG(M < (int64_t(1) << 31) && U < (int64_t(1) << 31) && K < (int64_t(1) << 31), "size too large");
+  POPS_CHECK_ARG(L * K * U < (int64_t(1) << 31) - 8 && N < (int64_t(1) << 31), "gather: one cloud's output must stay below 2^31 floats");
+  POPS_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 4 == 0,
+                 "float buffers must be 4-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool vec = (U % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
-                   (reinterpret_cast<uintptr_t>(out) % 16 == 0);
-  const int64_t total = rows * (vec ? U / 4 : U);
-  const int grid = flat_grid(total, 256);
-#define POPS_GATHER(MODE, VEC)                                                                  \
-  gather_kernel<MODE, VEC><<<grid, 256, 0, st>>>(x, idx, lengths, L * K, int(K), int(M), int(U), \
-                                                 rows, out, oob_flag)
-  if (mode == POPS_GATHER_KNN) { if (vec) POPS_GATHER(POPS_GATHER_KNN, 4); else POPS_GATHER(POPS_GATHER_KNN, 1); }
-  else { if (vec) POPS_GATHER(POPS_GATHER_MASKED, 4); else POPS_GATHER(POPS_GATHER_MASKED, 1); }
+  const bool v4 = (U % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+                  (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const dim3 grid = segment_grid(ceil_div(L * K * U + 3, 4), N, 256);
+  profile_begin("gather", st);
+#define POPS_GATHER(MODE, UT, V4)                                                                        \
+  gather_kernel<MODE, UT, V4><<<grid, 256, 0, st>>>(x, idx, lengths, unsigned(L * K), unsigned(K), int(M), \
+                                                    unsigned(U), int(N), out, oob_flag)
+#define POPS_GATHER_MODE(MODE)                        \
+  do {                                                \
+    if (v4) POPS_GATHER(MODE, 0, true);               \
+    else if (U == 3) POPS_GATHER(MODE, 3, false);     \
+    else POPS_GATHER(MODE, 0, false);                 \
+  } while (0)
+  if (mode == POPS_GATHER_KNN) POPS_GATHER_MODE(POPS_GATHER_KNN); else POPS_GATHER_MODE(POPS_GATHER_MASKED);
+#undef POPS_GATHER_MODE
 #undef POPS_GATHER
+  profile_end("gather", st);
   POPS_LAUNCH_OK("gather_kernel");
   return POPS_OK;
 }

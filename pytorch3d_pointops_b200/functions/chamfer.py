@@ -218,10 +218,17 @@ def _chamfer_distance_single_direction(
         raise ValueError("at most 8 feature names are supported per call")
     xfs = [x_features[n].contiguous() for n in names]
     yfs = [y_features[n].contiguous() for n in names]
+    # learned per-cloud weights: the reference's `cham_x *= weights.view(N, 1)` (:150-151, :175-176) is
+    # differentiable in `weights`; the kernel takes them as constants, so in that case the per-cloud
+    # results are computed unweighted and scaled by torch (w >= 0 commutes with sum / mean / max)
+    w_grad = weights is not None and weights.requires_grad and torch.is_grad_enabled()
     out = _ChamferDirection.apply(
         x.contiguous(), y.contiguous(), x_lengths, y_lengths,
-        None if weights is None else weights.detach().float().contiguous(),
+        None if (weights is None or w_grad) else weights.detach().float().contiguous(),
         norm, point_reduction, bool(abs_cosine), len(names), *xfs, *yfs)
+    if w_grad:
+        w = weights.view(N, 1) if point_reduction is None else weights.view(N)
+        out = tuple(o * w for o in out)
     cham_feat = {n: out[1 + i] for i, n in enumerate(names)} if with_features else None
     return out[0], cham_feat
 

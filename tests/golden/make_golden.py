@@ -56,8 +56,37 @@ def save(name, **arrays):
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
 
 
+def utils_cases():
+    """get_point_covariances / wmean (functions/utils.py:68-153 of the reference) on the reference's
+    own CPU KNN: ragged clouds, K above the shortest cloud, D = 2 and 3, weighted means."""
+    from pytorch3d_pointops.functions.utils import get_point_covariances, wmean
+
+    g = torch.Generator().manual_seed(31)
+    cases = {}
+    pts = torch.rand(3, 120, 3, generator=g)
+    L = torch.tensor([120, 5, 77])
+    for K in (8, 16):  # K = 8 exceeds the 5-point cloud: its slots k >= 5 gather zeros (knn_gather)
+        cov, nn = get_point_covariances(pts, L, K)
+        cases.update({f"cov3.K{K}.cov": cov, f"cov3.K{K}.nn": nn})
+    cases.update({"cov3.points": pts, "cov3.lengths": L})
+    pts2 = torch.randn(2, 64, 2, generator=g)
+    L2 = torch.tensor([64, 33])
+    cov, nn = get_point_covariances(pts2, L2, 6)
+    cases.update({"cov2.points": pts2, "cov2.lengths": L2, "cov2.K6.cov": cov, "cov2.K6.nn": nn})
+    x = torch.randn(4, 50, 3, generator=g)
+    w = torch.rand(4, 50, generator=g)
+    w[1] = 0.0  # an all-zero weight row: the eps clamp decides
+    cases.update({"wmean.x": x, "wmean.w": w, "wmean.plain": wmean(x), "wmean.weighted": wmean(x, w),
+                  "wmean.nokeep": wmean(x, w, keepdim=False), "wmean.dim01": wmean(x, w, dim=(0, 1)),
+                  "wmean.bcast": wmean(x, w[:, :1])})
+    save("utils_cases", **cases)
+
+
 def main():
     cref = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "utils":  # only the fixtures added in round 2
+        utils_cases()
+        return
     from pytorch3d_pointops.functions import (ball_query, knn_gather, knn_points,
                                               masked_gather, packed_to_padded,
                                               padded_to_packed, sample_farthest_points)
@@ -344,6 +373,7 @@ def main():
         cref.sample_pdf(edges.reshape(-1, n_bins + 1), w.reshape(-1, n_bins), out.view(-1, n_samples), 1e-5)
         cases[f"{name}.u"], cases[f"{name}.rand"] = u, out
     save("sample_pdf_cases", **cases)
+    utils_cases()
 
 
 if __name__ == "__main__":

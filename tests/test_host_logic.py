@@ -198,3 +198,49 @@ def test_alias_package_is_a_drop_in():
     for name in ("packed_to_padded", "padded_to_packed", "knn_check_version", "knn_points_idx",
                  "knn_points_backward", "ball_query", "sample_farthest_points"):
         assert callable(getattr(pytorch3d_pointops._C, name))  # ext.cpp:16-24
+
+
+def test_wmean_vs_reference_golden(golden):
+    """functions/utils.py:68-108 of the reference (pure torch on both sides)."""
+    from pytorch3d_pointops_b200.functions.utils import wmean
+
+    g = golden("utils_cases")
+    x, w = g.t("wmean.x"), g.t("wmean.w")
+    assert torch.equal(wmean(x), g.t("wmean.plain"))
+    assert torch.equal(wmean(x, w), g.t("wmean.weighted"))
+    assert torch.equal(wmean(x, w, keepdim=False), g.t("wmean.nokeep"))
+    assert torch.equal(wmean(x, w, dim=(0, 1)), g.t("wmean.dim01"))
+    assert torch.equal(wmean(x, w[:, :1]), g.t("wmean.bcast"))
+    with pytest.raises(ValueError):
+        wmean(x, torch.rand(4, 49))
+
+
+def test_naive_fps_cpu_vs_reference_golden(golden):
+    """The repo's sample_farthest_points_naive (reference functions/sample_farthest_points.py:99-197)
+    is device-agnostic torch: on CPU tensors it must reproduce the reference's indices (big.idx was
+    asserted equal to the reference's naive output at generation time)."""
+    from pytorch3d_pointops_b200.functions.sample_farthest_points import sample_farthest_points_naive
+
+    g = golden("fps_cases")
+    sp, si = sample_farthest_points_naive(g.t("big.points"), K=200)
+    assert torch.equal(si, g.t("big.idx")) and torch.equal(sp, g.t("big.sampled"))
+    sp, si = sample_farthest_points_naive(g.t("ragged.points"), g.t("ragged.lengths"), g.t("ragged.K").tolist())
+    assert torch.equal(si, g.t("ragged.idx")) and torch.equal(sp, g.t("ragged.sampled"))
+    with pytest.raises(ValueError):
+        sample_farthest_points_naive(g.t("ragged.points"), torch.tensor([1, 2]))
+
+
+def test_chamfer_feature_shape_validation():
+    """mis-shaped features must raise before any pointer reaches a kernel."""
+    from pytorch3d_pointops_b200 import _C
+
+    N, P1, P2 = 2, 5, 7
+    ok_x, ok_y = torch.zeros(N, P1, 3), torch.zeros(N, P2, 3)
+    _C._check_feature_shapes([ok_x], [ok_y], N, P1, P2)
+    for bad_x, bad_y in [(torch.zeros(N, P1 - 1, 3), ok_y), (ok_x, torch.zeros(N, P2, 4)),
+                         (torch.zeros(N + 1, P1, 3), ok_y), (ok_x, torch.zeros(N, P2 + 1, 3)),
+                         (torch.zeros(N, P1), ok_y)]:
+        with pytest.raises(ValueError):
+            _C._check_feature_shapes([bad_x], [bad_y], N, P1, P2)
+    with pytest.raises(ValueError):
+        _C._check_feature_shapes([ok_x], [], N, P1, P2)

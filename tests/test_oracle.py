@@ -245,3 +245,34 @@ def test_sample_pdf_oracle_vs_golden_and_ref(golden):
             ref.sample_pdf(bins, w, a, 1e-5)
             O.sample_pdf_(bins, w, b, 1e-5)
             assert torch.equal(a, b)
+
+
+def test_oracle_point_covariances_vs_reference_golden(oracle, golden):
+    """get_point_covariances (functions/utils.py:111-153) restated on the oracle's KNN + gather."""
+    g = golden("utils_cases")
+    for case, K in (("cov3", 8), ("cov3", 16), ("cov2", 6)):
+        pts, L = g.t(f"{case}.points"), g.t(f"{case}.lengths")
+        nn = oracle.knn_points(pts, pts, L, L, K=K, return_nn=True)[2]
+        assert torch.equal(nn, g.t(f"{case}.K{K}.nn"))
+        c = nn - nn.mean(2, keepdim=True)
+        cov = (c.unsqueeze(4) * c.unsqueeze(3)).mean(2)
+        assert torch.allclose(cov, g.t(f"{case}.K{K}.cov"), rtol=1e-6, atol=1e-8)
+
+
+def test_oracle_non_finite_well_defined_cases(oracle, ref_module):
+    """Where the reference's heap is well defined on non-finite data the oracle restates it: a NaN query
+    keeps the first K points (push rule `size < K || dist < top`, knn_cpu.cpp:52), +inf distances are
+    ordinary values."""
+    gen = torch.Generator().manual_seed(5)
+    p1, p2 = torch.rand(1, 6, 3, generator=gen), torch.rand(1, 40, 3, generator=gen)
+    p1[0, 2, 1] = float("nan")
+    p2[0, 3, 0] = float("inf")
+    L1, L2 = torch.tensor([6]), torch.tensor([40])
+    oi, od = oracle.knn_points_idx(p1, p2, L1, L2, 2, 5)
+    assert oi[0, 2].tolist() == [0, 1, 2, 3, 4] and torch.isnan(od[0, 2]).all()
+    oi40, od40 = oracle.knn_points_idx(p1, p2, L1, L2, 2, 40)
+    assert oi40[0, 0, -1] == 3 and torch.isinf(od40[0, 0, -1])
+    if ref_module is not None:
+        ri, rd = ref_module.knn_points_idx(p1, p2, L1, L2, 2, 40, -1)
+        assert torch.equal(ri, oi40)
+        assert torch.equal(torch.isnan(rd), torch.isnan(od40)) and torch.equal(rd[~torch.isnan(rd)], od40[~torch.isnan(od40)])
