@@ -31,137 +31,13 @@
 #include <cfloat>
 #include <cstdlib>
 
-#include "knn_core.cuh"
+#include "knn_prune_common.cuh"
 
 namespace pops {
 
-namespace {
-
-constexpr int kRingSlots = 4;   // blocks resident per warp
-constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
-// candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total)
-constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : 24); }
-constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
-constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
-constexpr uint32_t kBlockBytes = kBlockFloats * 4;
-static_assert((kRingSlots & (kRingSlots - 1)) == 0 && kRingSlots <= 32, "slot metadata sits in lanes");
-
-struct KnnPruneParams {
-  const float4* qsorted;
-  const unsigned* qhome;
-  const float* blocks;
-  const float4* boxes;
-  const int64_t* len1;
-  const int64_t* len2;
-  const unsigned* maxabs_bits;
-  int64_t* idx;
-  float* dists;
-  int P1, P2, K, nbox;
-  int prune;  // 0: visit every block (brute force in the same order); measurement aid
-  unsigned long long* stats;  // development counters (POPS_KNN_STATS=1), else nullptr
-};
-
 __device__ unsigned long long g_knn_stats[8];
 
-// CID: candidate id type -- unsigned short while the cloud has at most 65536 groups (262144 points)
-template <int Q, int THREADS, typename CID, int KT>
-struct PruneSmem {
-  static constexpr int WARPS = THREADS / 32;
-  static constexpr int QPB = Q * THREADS;
-  static constexpr size_t bars_off = 0;
-  static constexpr size_t ring_off = 256;
-  static constexpr size_t ring_bytes = size_t(WARPS) * kRingSlots * kBlockBytes;
-  static constexpr size_t cand_off = ring_off + ring_bytes;
-  static constexpr size_t cand_bytes = size_t(prune_buf_cap(KT)) * QPB * sizeof(CID);  // global group ids
-  static constexpr size_t surv_off = (cand_off + cand_bytes + 15) / 16 * 16;
-  static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
-  static constexpr size_t cold_off = surv_off + surv_bytes;
-  static constexpr size_t cold_bytes = size_t(3) * QPB * 4;  // qq, dk, output row per query
-  static constexpr size_t total = cold_off + cold_bytes;
-  static_assert(WARPS * kRingSlots * 8 <= ring_off, "mbarriers overlap the ring");
-};
-
-// Lower bound of the reference distance between ANY query in the box [qlo, qhi] and ANY point in
-// the box [lo, hi].  Same unfused operations in the same order as the reference distance
-// (knn_cpu.cpp:42-50); rounding is monotone, so for every such pair and every axis
-// |fl(q - p)| >= gap, fl(gap^2) <= fl(diff^2), and the rounded sums keep the order: the bound
-// holds exactly.  Empty boxes (+inf, -inf) give +inf.
-__device__ __forceinline__ float box_lower_bound(float4 lo, float4 hi, const float (&qlo)[3],
-                                                 const float (&qhi)[3]) {
-  const float gx = fmaxf(fmaxf(__fsub_rn(lo.x, qhi[0]), __fsub_rn(qlo[0], hi.x)), 0.0f);
-  const float gy = fmaxf(fmaxf(__fsub_rn(lo.y, qhi[1]), __fsub_rn(qlo[1], hi.y)), 0.0f);
-  const float gz = fmaxf(fmaxf(__fsub_rn(lo.z, qhi[2]), __fsub_rn(qlo[2], hi.z)), 0.0f);
-  return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-}
-
-// exact unfused distances of q to the 4 points of one group (packed sub / mul, scalar adds:
-// ptxas fuses packed mul + packed add into FFMA2, which would break bit parity -- knn_core.cuh)
-__device__ __forceinline__ void exact4(float q0, float q1, float q2, float4 X, float4 Y, float4 Z,
-                                       float (&d4)[4]) {
-  const float2 x01 = __fadd2_rn(make_float2(q0, q0), make_float2(-X.x, -X.y));
-  const float2 x23 = __fadd2_rn(make_float2(q0, q0), make_float2(-X.z, -X.w));
-  const float2 y01 = __fadd2_rn(make_float2(q1, q1), make_float2(-Y.x, -Y.y));
-  const float2 y23 = __fadd2_rn(make_float2(q1, q1), make_float2(-Y.z, -Y.w));
-  const float2 z01 = __fadd2_rn(make_float2(q2, q2), make_float2(-Z.x, -Z.y));
-  const float2 z23 = __fadd2_rn(make_float2(q2, q2), make_float2(-Z.z, -Z.w));
-  const float2 xx01 = __fmul2_rn(x01, x01), xx23 = __fmul2_rn(x23, x23);
-  const float2 yy01 = __fmul2_rn(y01, y01), yy23 = __fmul2_rn(y23, y23);
-  const float2 zz01 = __fmul2_rn(z01, z01), zz23 = __fmul2_rn(z23, z23);
-  d4[0] = __fadd_rn(__fadd_rn(xx01.x, yy01.x), zz01.x);
-  d4[1] = __fadd_rn(__fadd_rn(xx01.y, yy01.y), zz01.y);
-  d4[2] = __fadd_rn(__fadd_rn(xx23.x, yy23.x), zz23.x);
-  d4[3] = __fadd_rn(__fadd_rn(xx23.y, yy23.y), zz23.y);
-}
-
-// Seed bound of one query: exact distances to the `nseed` blocks at the start of the warp's ring;
-// minimum over each of NS interleaved subsets of the points (NS distinct points: the subsets are
-// disjoint), then the KT-th smallest of those minima.  KT distinct points lie within the result,
-// so it bounds the K-th distance (K <= KT) from above.  +inf when fewer than KT subsets hold a
-// valid point.  NS = 2 KT subsets of >= 4 points put the bound near the (1.1 KT)-th nearest seed
-// point.  Not inlined: runs once per query.
-template <int KT>
-__device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q0, float q1, float q2) {
-  constexpr int NS = KT == 1 ? 1 : (KT == 4 ? 16 : 2 * KT);
-  constexpr int UG = NS >= 4 ? NS / 4 : 1;  // groups per unrolled step: subset index stays static
-  static_assert(UG <= kBlockGroups, "a step stays inside one block");
-  const float INF = __int_as_float(0x7f800000);
-  float mins[NS];
-#pragma unroll
-  for (int i = 0; i < NS; ++i) mins[i] = INF;
-  for (int s = 0; s < nseed; ++s) {
-    const float4* tp = ring4 + s * kBlockF4;
-#pragma unroll 1
-    for (int g0 = 0; g0 < kBlockGroups; g0 += UG) {
-#pragma unroll
-      for (int u = 0; u < UG; ++u) {
-        const int g = g0 + u;
-        const float4 W = tp[3 * kBlockGroups + g];
-        float d4[4];
-        exact4(q0, q1, q2, tp[g], tp[kBlockGroups + g], tp[2 * kBlockGroups + g], d4);
-        const float w4[4] = {W.x, W.y, W.z, W.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float dv = (w4[i] == INF) ? INF : d4[i];  // padding entries carry w = +inf
-          float& m = mins[(u * 4 + i) % NS];
-          m = fminf(m, dv);
-        }
-      }
-    }
-  }
-  if (NS == 1) return mins[0];
-  if (NS != 2 * KT) {  // KT = 4: 4th smallest of 16
-    sort_floats<NS, 0, NS>(mins);
-    return mins[KT - 1];
-  }
-  // KT-th smallest of 2 KT values: sort both halves, then max_i min(A[i], B[KT-1-i])
-  constexpr int H = NS / 2;
-  sort_floats<H, 0, NS>(mins);
-  sort_floats<H, H, NS>(mins);
-  float U = fminf(mins[0], mins[H + H - 1]);
-#pragma unroll
-  for (int i = 1; i < H; ++i) U = fmaxf(U, fminf(mins[i], mins[H + H - 1 - i]));
-  return U;
-}
+namespace {
 
 // Drain ONE query's candidate buffer (u32 global group ids, column stride CSTRIDE words).  Not
 // inlined, called warp-converged and kept converged.  The groups are re-read from the sorted

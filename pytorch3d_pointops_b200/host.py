@@ -23,7 +23,14 @@ class HostKnn:
     out_idx (N,P1,K) int64 and out_dists (N,P1,K) float32 are pinned host tensors owned by this
     object and overwritten by every call."""
 
-    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=8, graph: bool = True):
+    def __init__(self, N: int, P1: int, P2: int, D: int, K: int, device, slices=8, graph: bool = True,
+                 idx_dtype: torch.dtype = torch.int64):
+        # idx_dtype: dtype of the HOST index buffer.  int64 is the reference's contract (knn.h:59-66);
+        # int32 (additive) narrows each slice on the device before it travels -- a third less D2H
+        # traffic, which is what bounds this pipeline -- for callers that widen on the host or do not
+        # need 64-bit indices (P2 < 2^31 always holds).
+        assert idx_dtype in (torch.int64, torch.int32)
+        self.idx_dtype = idx_dtype
         self.device = torch.device(device)
         self.N, self.P1, self.P2, self.D, self.K = N, P1, P2, D, K
         # `slices`: a count (equal slices) or an explicit list of slice sizes in clouds.  Measured on
@@ -41,7 +48,7 @@ class HostKnn:
         else:
             self.slices = max(1, min(int(slices), N))
             bounds = [round(i * N / self.slices) for i in range(self.slices + 1)]
-        self.out_idx = torch.empty((N, P1, K), dtype=torch.int64).pin_memory()
+        self.out_idx = torch.empty((N, P1, K), dtype=idx_dtype).pin_memory()
         self.out_dists = torch.empty((N, P1, K), dtype=torch.float32).pin_memory()
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
@@ -108,7 +115,7 @@ class HostKnn:
                 ev = torch.cuda.Event()
                 ev.record(self.h2d)
                 staged.append((d1, d2, l1, l2, ev))
-        keep = []
+        keep, narrow = [], []
         for grp, (d1, d2, l1, l2, ev) in zip(groups, staged):
             g0 = grp[0][0]
             main.wait_event(ev)
@@ -119,15 +126,22 @@ class HostKnn:
             ks.prepare()
             for a, b in grp:
                 ks.search(a - g0, b - g0)
+                idx_src = ks.idx[a - g0:b - g0]
+                if self.idx_dtype != torch.int64:
+                    idx_src = idx_src.to(self.idx_dtype)  # narrowed on the device, on the search stream
+                    if not recording:
+                        idx_src.record_stream(self.d2h)
+                    narrow.append(idx_src)
                 done = torch.cuda.Event()
                 done.record(main)
                 with torch.cuda.stream(self.d2h):
                     self.d2h.wait_event(done)
-                    self.out_idx[a:b].copy_(ks.idx[a - g0:b - g0], non_blocking=True)
+                    self.out_idx[a:b].copy_(idx_src, non_blocking=True)
                     self.out_dists[a:b].copy_(ks.dists[a - g0:b - g0], non_blocking=True)
             if not recording:
                 for t in (ks.idx, ks.dists, ks.ws):
                     t.record_stream(self.d2h)
             keep.append((d1, d2, l1, l2, ks))
+        keep.append(narrow)
         main.wait_stream(self.d2h)
         return keep

@@ -84,3 +84,63 @@ def test_sharded_chamfer_and_gather_world2():
             p.join(180)
             assert p.exitcode == 0
         assert dict(ret) == {0: True, 1: True}
+
+
+def _nccl_worker(rank, world, port, ret):
+    """One rank = one GPU: the CUDA chamfer on this rank's clouds + the NCCL all-reduce; the global
+    loss must equal the single-GPU loss on the whole batch, the gradients the matching slices."""
+    import sys
+
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from pytorch3d_pointops_b200.distributed import all_gather_clouds, chamfer_distance_sharded, my_slice
+    from pytorch3d_pointops_b200.functions import knn_points
+    from pytorch3d_pointops_b200.functions.chamfer import chamfer_distance
+
+    g = torch.Generator().manual_seed(33)
+    N, P = 6, 3000
+    x, y = torch.rand(N, P, 3, generator=g).to(dev), torch.rand(N, P, 3, generator=g).to(dev)
+    xl = torch.tensor([3000, 1300, 1, 2999, 2048, 77], device=dev)
+    yl = torch.tensor([3000, 3000, 700, 3, 2500, 1024], device=dev)
+    xn, yn = torch.randn(N, P, 3, generator=g).to(dev), torch.randn(N, P, 3, generator=g).to(dev)
+    ok = True
+    for br in ("mean", "sum"):
+        xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        full, full_f = chamfer_distance(xr, yr, xl, yl, {"n": xn}, {"n": yn}, batch_reduction=br, feature_names=["n"])
+        (full + full_f["n"]).backward()
+        lo, hi = my_slice(N, costs=(xl * yl).tolist())
+        xs, ys = x[lo:hi].clone().requires_grad_(True), y[lo:hi].clone().requires_grad_(True)
+        loss, lf = chamfer_distance_sharded(xs, ys, xl[lo:hi], yl[lo:hi], {"n": xn[lo:hi]}, {"n": yn[lo:hi]},
+                                            batch_reduction=br, feature_names=["n"], n_clouds_global=N)
+        (loss + lf["n"]).backward()
+        ok &= bool(torch.allclose(loss.detach(), full.detach(), rtol=1e-5))
+        ok &= bool(torch.allclose(lf["n"].detach(), full_f["n"].detach(), rtol=1e-5))
+        scale = float(xr.grad.abs().max())
+        ok &= bool(torch.allclose(xs.grad, xr.grad[lo:hi], rtol=1e-5, atol=1e-5 * scale))
+        ok &= bool(torch.allclose(ys.grad, yr.grad[lo:hi], rtol=1e-5, atol=1e-5 * scale))
+    lo, hi = my_slice(N)
+    idx = knn_points(x[lo:hi], y[lo:hi], xl[lo:hi], yl[lo:hi], K=3).idx
+    ok &= bool(torch.equal(all_gather_clouds(idx), knn_points(x, y, xl, yl, K=3).idx))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_chamfer_nccl_two_gpus():
+    """The path's one collective on real NCCL hardware (needs >= 2 visible GPUs: `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as m:
+        ret = m.dict()
+        port = 29500 + (os.getpid() % 500)
+        procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0
+        assert dict(ret) == {0: True, 1: True}
