@@ -518,43 +518,74 @@ knn_backward_rows_kernel(const float* __restrict__ p1, const float* __restrict__
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
   const int rows = static_cast<int>(min(static_cast<int64_t>(rows_per_cta), total_rows - row0));
   const int items = rows * K;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int r = it / K, k = it - r * K;
-    const int64_t row = row0 + r;
-    const int n = static_cast<int>(row / P1);
-    const int i1 = static_cast<int>(row - static_cast<int64_t>(n) * P1);
-    float df[DT];
+  // UNB entries per thread at once: their indices and upstream gradients are requested first, then the
+  // p2 rows they point at, then the arithmetic -- the chain idx -> p2[idx] is two dependent loads and
+  // one entry per thread leaves the memory system idle most of the time
+  constexpr int UNB = 4;
+  for (int it0 = threadIdx.x; it0 < items; it0 += blockDim.x * UNB) {
+    long long i2[UNB];
+    float g[UNB];
 #pragma unroll
-    for (int d = 0; d < DT; ++d) df[d] = 0.0f;
-    const int64_t L1 = len1[n], L2 = len2[n];
-    if (i1 < L1 && k < L2) {  // k < min(L2, K)
-      const int64_t i2 = idx[row0 * K + it];
-      if (i2 >= 0 && i2 < P2) {  // -1 = padding (ball query)
-        const float g = grad_dists[row0 * K + it];
-        const float* a = p1 + row * DT;
-        const float* b = p2 + (static_cast<int64_t>(n) * P2 + i2) * DT;
+    for (int u = 0; u < UNB; ++u) {
+      const int it = min(it0 + u * static_cast<int>(blockDim.x), items - 1);
+      i2[u] = __ldg(idx + row0 * K + it);
+      g[u] = __ldg(grad_dists + row0 * K + it);
+    }
+    int nn[UNB];
+    int64_t rw[UNB];
+    bool ok[UNB];
 #pragma unroll
-        for (int d = 0; d < DT; ++d) {
-          // same float ops, same order as knn_cpu.cpp:113-122; intrinsics forbid contraction
-          if (NORM == 1) df[d] = __fmul_rn(g, (a[d] > b[d]) ? 1.0f : -1.0f);
-          else df[d] = __fmul_rn(__fmul_rn(2.0f, g), __fsub_rn(a[d], b[d]));
-        }
+    for (int u = 0; u < UNB; ++u) {
+      const int it = it0 + u * static_cast<int>(blockDim.x);
+      const int itc = min(it, items - 1);
+      const int r = itc / K, k = itc - r * K;
+      rw[u] = row0 + r;
+      nn[u] = static_cast<int>(rw[u] / P1);
+      const int i1 = static_cast<int>(rw[u] - static_cast<int64_t>(nn[u]) * P1);
+      const int64_t L1v = __ldg(len1 + nn[u]), L2v = __ldg(len2 + nn[u]);  // both, unconditionally: no branch between loads
+      ok[u] = (it < items) & (i1 < L1v) & (k < L2v)       // k < min(L2, K)
+              & (i2[u] >= 0) & (i2[u] < P2);               // -1 = padding (ball query)
+    }
+    float av[UNB][DT], bv[UNB][DT];
+#pragma unroll
+    for (int u = 0; u < UNB; ++u) {
+      const float* a = p1 + rw[u] * DT;
+      const float* b = p2 + (static_cast<int64_t>(nn[u]) * P2 + (ok[u] ? i2[u] : 0)) * DT;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        av[u][d] = __ldg(a + d);
+        bv[u][d] = __ldg(b + d);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNB; ++u) {
+      const int it = it0 + u * static_cast<int>(blockDim.x);
+      if (it >= items) continue;
+      float df[DT];
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        // same float ops, same order as knn_cpu.cpp:113-122; intrinsics forbid contraction
+        if (NORM == 1) df[d] = __fmul_rn(g[u], (av[u][d] > bv[u][d]) ? 1.0f : -1.0f);
+        else df[d] = __fmul_rn(__fmul_rn(2.0f, g[u]), __fsub_rn(av[u][d], bv[u][d]));
+        if (!ok[u]) df[d] = 0.0f;
+      }
+      if (ok[u]) {
+        const int64_t prow = static_cast<int64_t>(nn[u]) * P2 + i2[u];
         if (DT == 3 && scratch != nullptr) {
-          red_add_v4(scratch + static_cast<int64_t>(n) * P2 + i2, -df[0], -df[1 % DT], -df[2 % DT], 0.0f);
+          red_add_v4(scratch + prow, -df[0], -df[1 % DT], -df[2 % DT], 0.0f);
         } else if (DT == 4 && (reinterpret_cast<uintptr_t>(grad_p2) & 15) == 0) {
-          red_add_v4(reinterpret_cast<float4*>(grad_p2) + static_cast<int64_t>(n) * P2 + i2, -df[0], -df[1 % DT],
-                     -df[2 % DT], -df[3 % DT]);
+          red_add_v4(reinterpret_cast<float4*>(grad_p2) + prow, -df[0], -df[1 % DT], -df[2 % DT], -df[3 % DT]);
         } else if (DT == 2 && (reinterpret_cast<uintptr_t>(grad_p2) & 7) == 0) {
-          red_add_v2(reinterpret_cast<float2*>(grad_p2) + static_cast<int64_t>(n) * P2 + i2, -df[0], -df[1 % DT]);
+          red_add_v2(reinterpret_cast<float2*>(grad_p2) + prow, -df[0], -df[1 % DT]);
         } else {
-          float* gp = grad_p2 + (static_cast<int64_t>(n) * P2 + i2) * DT;
+          float* gp = grad_p2 + prow * DT;
 #pragma unroll
           for (int d = 0; d < DT; ++d) atomicAdd(gp + d, -df[d]);
         }
       }
-    }
 #pragma unroll
-    for (int d = 0; d < DT; ++d) diffs[it * DT + d] = df[d];
+      for (int d = 0; d < DT; ++d) diffs[it * DT + d] = df[d];
+    }
   }
   __syncthreads();
   for (int t = threadIdx.x; t < rows * DT; t += blockDim.x) {

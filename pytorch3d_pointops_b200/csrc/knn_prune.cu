@@ -380,44 +380,55 @@ knn_prune_kernel(const KnnPruneParams prm) {
       if (prm.stats && lane == 0) atomicAdd(prm.stats + 1, 1ull);
       const float4* tp = ring4 + s * kBlockF4;
       const unsigned gid0 = static_cast<unsigned>(__shfl_sync(FULL, slot_blk, s)) * kBlockGroups;
-      float4 Xc[4];
+      // The flush is a real function call and must not sit inside the dense loop: the current and the
+      // prefetched group (32 registers) and the loop's addresses would be parked in local memory around
+      // it on EVERY pass (r1 profile: three LDL per chunk, 9 % of all stall samples).  On overflow the
+      // loop is left, the buffers are drained, and the scan resumes at the next group with its rows
+      // re-read from shared memory.
+      int g = 0;
+      unsigned gid = gid0;
+      do {
+        float4 Xc[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) Xc[r] = tp[r * kBlockGroups];
+        for (int r = 0; r < 4; ++r) Xc[r] = tp[r * kBlockGroups + g];
+        bool over = false;
 #pragma unroll 1
-      for (int g = 0; g < kBlockGroups; g += kChunk) {
+        for (; g < kBlockGroups && !over; g += kChunk) {
 #pragma unroll
-        for (int c = 0; c < kChunk; ++c) {
-          // next group's rows (the last prefetch of a block reads the index row: in bounds, unused)
-          float4 Xn[4];
+          for (int c = 0; c < kChunk; ++c) {
+            // next group's rows (the last prefetch of a block reads the index row: in bounds, unused)
+            float4 Xn[4];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) Xn[r] = tp[r * kBlockGroups + g + c + 1];
-          const unsigned gid = gid0 + g + c;
+            for (int r = 0; r < 4; ++r) Xn[r] = tp[r * kBlockGroups + g + c + 1];
 #pragma unroll
-          for (int t = 0; t < Q; ++t) {
-            float2 s01 = make_float2(Xc[3].x, Xc[3].y), s23 = make_float2(Xc[3].z, Xc[3].w);
+            for (int t = 0; t < Q; ++t) {
+              float2 s01 = make_float2(Xc[3].x, Xc[3].y), s23 = make_float2(Xc[3].z, Xc[3].w);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const float2 ad = make_float2(a[t][d], a[t][d]);
-              s01 = __ffma2_rn(ad, make_float2(Xc[d].x, Xc[d].y), s01);
-              s23 = __ffma2_rn(ad, make_float2(Xc[d].z, Xc[d].w), s23);
+              for (int d = 0; d < 3; ++d) {
+                const float2 ad = make_float2(a[t][d], a[t][d]);
+                s01 = __ffma2_rn(ad, make_float2(Xc[d].x, Xc[d].y), s01);
+                s23 = __ffma2_rn(ad, make_float2(Xc[d].z, Xc[d].w), s23);
+              }
+              const float m = fminf(fminf(s01.x, s01.y), fminf(s23.x, s23.y));
+              if (m <= T[t]) {  // predicated: one STS + one IADD
+                if (sizeof(CID) == 2)
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(cw[t]), "h"(static_cast<unsigned short>(gid)) : "memory");
+                else
+                  asm volatile("st.shared.u32 [%0], %1;" ::"r"(cw[t]), "r"(gid) : "memory");
+                cw[t] += CBYTES;
+              }
             }
-            const float m = fminf(fminf(s01.x, s01.y), fminf(s23.x, s23.y));
-            if (m <= T[t]) {  // predicated: one STS + one IADD
-              if (sizeof(CID) == 2)
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(cw[t]), "h"(static_cast<unsigned short>(gid)) : "memory");
-              else
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(cw[t]), "r"(gid) : "memory");
-              cw[t] += CBYTES;
-            }
+            ++gid;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) Xc[r] = Xn[r];
           }
+          uint32_t mx = cw[0];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) Xc[r] = Xn[r];
+          for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (32u * CB));
+          over = __any_sync(FULL, mx > cw_limit);
         }
-        uint32_t mx = cw[0];
-#pragma unroll
-        for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (32u * CB));
-        if (__any_sync(FULL, mx > cw_limit)) flush_all(true);
-      }
+        if (over) flush_all(true);
+      } while (g < kBlockGroups);
     }
     ++tail;
   }

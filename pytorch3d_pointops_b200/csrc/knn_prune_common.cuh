@@ -1,5 +1,5 @@
-// Pieces shared by the two generations of the Hilbert-ordered, box-pruned D = 3 search
-// (knn_prune.cu, knn_prune2.cu): launch parameters, the exact lower bound between boxes, the exact
+// Pieces of the Hilbert-ordered, box-pruned D = 3 search (knn_prune.cu) that do not depend on its
+// template parameters: launch parameters, the exact lower bound between boxes, the exact
 // distance of one query to a group of four points, and the seed bound.
 #pragma once
 #include <cfloat>
@@ -7,17 +7,6 @@
 #include "knn_core.cuh"
 
 namespace pops {
-
-namespace {
-
-constexpr int kRingSlots = 4;   // blocks resident per warp
-constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
-// candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total)
-constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : 24); }
-constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
-constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
-constexpr uint32_t kBlockBytes = kBlockFloats * 4;
-static_assert((kRingSlots & (kRingSlots - 1)) == 0 && kRingSlots <= 32, "slot metadata sits in lanes");
 
 struct KnnPruneParams {
   const float4* qsorted;
@@ -34,7 +23,18 @@ struct KnnPruneParams {
   unsigned long long* stats;  // development counters (POPS_KNN_STATS=1), else nullptr
 };
 
-extern __device__ unsigned long long g_knn_stats[8];  // defined in knn_prune.cu
+namespace {
+
+constexpr int kRingSlots = 4;   // blocks resident per warp
+constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
+// candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total)
+constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : 24); }
+constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
+constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
+constexpr uint32_t kBlockBytes = kBlockFloats * 4;
+static_assert((kRingSlots & (kRingSlots - 1)) == 0 && kRingSlots <= 32, "slot metadata sits in lanes");
+
+
 
 // CID: candidate id type -- unsigned short while the cloud has at most 65536 groups (262144 points)
 template <int Q, int THREADS, typename CID, int KT>
@@ -92,7 +92,7 @@ __device__ __forceinline__ void exact4(float q0, float q1, float q2, float4 X, f
 // so it bounds the K-th distance (K <= KT) from above.  +inf when fewer than KT subsets hold a
 // valid point.  NS = 2 KT subsets of >= 4 points put the bound near the (1.1 KT)-th nearest seed
 // point.  Not inlined: runs once per query.
-template <int KT>
+template <int KT, int SLOTF4 = kBlockF4>
 __device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q0, float q1, float q2) {
   constexpr int NS = KT == 1 ? 1 : (KT == 4 ? 16 : 2 * KT);
   constexpr int UG = NS >= 4 ? NS / 4 : 1;  // groups per unrolled step: subset index stays static
@@ -102,7 +102,7 @@ __device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q
 #pragma unroll
   for (int i = 0; i < NS; ++i) mins[i] = INF;
   for (int s = 0; s < nseed; ++s) {
-    const float4* tp = ring4 + s * kBlockF4;
+    const float4* tp = ring4 + s * SLOTF4;  // SLOTF4: float4 between consecutive ring slots
 #pragma unroll 1
     for (int g0 = 0; g0 < kBlockGroups; g0 += UG) {
 #pragma unroll

@@ -96,14 +96,19 @@ padded_to_packed_kernel(const float* __restrict__ padded, const int64_t* __restr
 
 // out[n, l, k, :] = x[n, idx[n,l,k], :] with masking.  grid.y walks the clouds; within a cloud the
 // OUTPUT is a flat float stream written as aligned 16-byte chunks (perfectly coalesced stores for
-// any U, e.g. the 12-byte rows of U = 3); a chunk spans at most 4 rows, whose indices are read as
-// the stream advances.  The gathered reads hit L1/L2 (a cloud's x is small).  UT: compile-time U
-// (0 = runtime).  V4: U % 4 == 0 and 16-byte aligned x -> one 16-byte source load per chunk.
+// any U, e.g. the 12-byte rows of U = 3); a chunk spans at most RMAX rows.  The kernel is a chain of
+// two dependent loads (index from HBM, then the row from L1/L2), so every thread works on UN chunks
+// at once: all their indices are requested first, then all their rows, then the stores -- without
+// that the SMs sit at full occupancy waiting (measured: 0.26 of HBM with one chunk per thread).
+// UT: compile-time U (0 = runtime).  V4: U % 4 == 0 and 16-byte aligned x -> one 16-byte source
+// load per chunk.
 template <int MODE, int UT, bool V4>
 __global__ void __launch_bounds__(256)
 gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
               const int64_t* __restrict__ lengths, unsigned LK /*L*K rows per cloud*/, unsigned K, int M,
               unsigned U_rt, int N, float* __restrict__ out, int32_t* __restrict__ oob) {
+  constexpr int UN = 4;
+  constexpr int RMAX = V4 ? 1 : (UT == 0 || UT == 1 ? 4 : (UT == 2 ? 3 : 2));  // rows a 4-float chunk can touch
   const unsigned U = UT ? UT : U_rt;
   const int64_t F = static_cast<int64_t>(LK) * U;  // floats of one cloud's output (< 2^31, host-checked)
   for (int n = blockIdx.y; n < N; n += gridDim.y) {
@@ -118,47 +123,73 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
     }
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
     const unsigned nchunks = static_cast<unsigned>((F + a + 3) >> 2);
-    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.x * blockDim.x) {
-      const int f0 = static_cast<int>(4u * c) - a;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      const unsigned fs = f0 < 0 ? 0u : static_cast<unsigned>(f0);
-      unsigned row = fs / U, u = fs - row * U;
-      if (V4) {  // chunk = 4 consecutive floats of ONE row, a == 0
-        if (row < LK) {
-          const int64_t j = idx_n[row];
-          bool take = (j >= 0 && j < M);
+    const unsigned step = gridDim.x * blockDim.x * UN;
+    for (unsigned cb = blockIdx.x * blockDim.x * UN + threadIdx.x; cb < nchunks; cb += step) {
+      int f0[UN];
+      unsigned row[UN], u[UN];
+      long long jraw[UN][RMAX];
+      // ---- all indices first: unconditional loads from clamped addresses, no branch between them ----
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        const unsigned c = cb + k * blockDim.x;
+        f0[k] = static_cast<int>(4u * c) - a;
+        const unsigned fs = f0[k] < 0 ? 0u : static_cast<unsigned>(f0[k]);
+        row[k] = fs / U;
+        u[k] = fs - row[k] * U;
+#pragma unroll
+        for (int i = 0; i < RMAX; ++i) jraw[k][i] = __ldg(idx_n + min(row[k] + i, LK - 1u));
+      }
+      int jv[UN][RMAX];  // source row of the chunk's i-th output row, -1 = zeros
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        const unsigned c = cb + k * blockDim.x;
+        const unsigned span = u[k] + 4u - (f0[k] < 0 ? static_cast<unsigned>(-f0[k]) : 0u);  // floats from the start of row[k] to the chunk's end
+#pragma unroll
+        for (int i = 0; i < RMAX; ++i) {
+          const unsigned r = row[k] + i;
+          const long long j = jraw[k][i];
+          const bool need = c < nchunks && r < LK && static_cast<unsigned>(i) * U < span;
+          bool take = need && j >= 0 && j < M;
           if (MODE == POPS_GATHER_KNN) {
-            const bool live = klim == K || (row % K) < klim;
-            if (live && !take && oob != nullptr) *oob = 1;
+            const bool live = klim == K || (r % K) < klim;
+            bad = bad || (need && live && !take);
             take = take && live;
           }
-          if (take) {
-            const float4 s = *reinterpret_cast<const float4*>(x_n + j * U + u);
-            v[0] = s.x; v[1] = s.y; v[2] = s.z; v[3] = s.w;
-          }
-        }
-      } else {
-        int64_t j = -1;
-        bool take = false, fresh = true;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int f = f0 + e;
-          if (f < 0 || f >= F) continue;
-          if (fresh) {
-            j = idx_n[row];
-            take = (j >= 0 && j < M);
-            if (MODE == POPS_GATHER_KNN) {
-              const bool live = klim == K || (row % K) < klim;
-              if (live && !take && oob != nullptr) *oob = 1;
-              take = take && live;
-            }
-            fresh = false;
-          }
-          if (take) v[e] = __ldg(x_n + j * U + u);
-          if (++u == U) { u = 0; ++row; fresh = true; }
+          jv[k][i] = take ? static_cast<int>(j) : -1;
         }
       }
-      store_chunk(dst, f0, F, v);
+      if (MODE == POPS_GATHER_KNN && bad && oob != nullptr) *oob = 1;
+      // ---- then all rows (row 0 of the cloud stands in for "zeros": always a valid address) ----
+      float v[UN][4];
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        if (V4) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(x_n + static_cast<int64_t>(max(jv[k][0], 0)) * U + u[k]));
+          const bool t = jv[k][0] >= 0;
+          v[k][0] = t ? s4.x : 0.0f; v[k][1] = t ? s4.y : 0.0f; v[k][2] = t ? s4.z : 0.0f; v[k][3] = t ? s4.w : 0.0f;
+        } else {
+          const int lead = f0[k] < 0 ? -f0[k] : 0;  // floats of this chunk in front of the cloud's segment
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            unsigned off = u[k] + static_cast<unsigned>(e >= lead ? e - lead : 0);  // float offset from the start of row[k]
+            int i = 0;
+#pragma unroll
+            for (int t = 1; t < RMAX; ++t)
+              if (off >= U) { off -= U; i = t; }
+            int j = jv[k][0];
+#pragma unroll
+            for (int t = 1; t < RMAX; ++t) j = (i == t) ? jv[k][t] : j;
+            const bool t = e >= lead && j >= 0 && off < U;
+            const float val = __ldg(x_n + static_cast<int64_t>(t ? j : 0) * U + (t ? off : 0u));
+            v[k][e] = t ? val : 0.0f;
+          }
+        }
+      }
+      // ---- then the stores ----
+#pragma unroll
+      for (int k = 0; k < UN; ++k)
+        if (cb + k * blockDim.x < nchunks) store_chunk(dst, f0[k], F, v[k]);
     }
   }
 }
@@ -312,9 +343,13 @@ extern "C" int pops_gather(const float* x, const int64_t* idx, const int64_t* le
   POPS_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 4 == 0,
                  "float buffers must be 4-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M == 0) {  // nothing to gather from: every row is zeros (the kernel may always read row 0 of a cloud)
+    POPS_CUDA_OK(cudaMemsetAsync(out, 0, size_t(rows) * U * 4, st));
+    return POPS_OK;
+  }
   const bool v4 = (U % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
                   (reinterpret_cast<uintptr_t>(out) % 16 == 0);
-  const dim3 grid = segment_grid(ceil_div(L * K * U + 3, 4), N, 256);
+  const dim3 grid = segment_grid(ceil_div(ceil_div(L * K * U + 3, 4), 4), N, 256);  // 4 chunks per thread and pass
   profile_begin("gather", st);
 #define POPS_GATHER(MODE, UT, V4)                                                                        \
   gather_kernel<MODE, UT, V4><<<grid, 256, 0, st>>>(x, idx, lengths, unsigned(L * K), unsigned(K), int(M), \
