@@ -594,7 +594,7 @@ def run_ours(args, rank, world, local_rank):
             "collective": f"NCCL all-reduce (sum) of 4 fp32 scalars over {world} ranks, inside the timed region",
             "collective_us": ar_ms * 1e3, "added_us_vs_local_step": (cs_ms - c_ms) * 1e3,
             "loss_equals_single_gpu_loss_on_gathered_batch_rtol_1e-5": ok,
-            "loss": float(loss_s), "loss_gathered": float(loss_f)}
+            "loss": float(loss_s.detach()), "loss_gathered": float(loss_f)}
         del cat, full
 
     # ---- secondary: the HBM-bound rows (SURVEY 8d byte formulas) -------------------------------------

@@ -99,17 +99,26 @@ def chamfer_distance_sharded(x, y, x_lengths=None, y_lengths=None, x_features=No
     names = sorted(feats) if feats is not None else []
     local = torch.stack([loss] + [feats[k] for k in names])
     n_local = x.shape[0] if torch.is_tensor(x) else len(x)
-    div_local = float(n_local) if weights is None else float(weights.sum())
-    packed = torch.cat([local.detach(), local.new_tensor([div_local])])
-    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    total, div = packed[:-1], packed[-1]
-    if batch_reduction == "mean":
-        if weights is None:
-            div = local.new_tensor(float(max(n_clouds_global, 1))) if n_clouds_global is not None else div.clamp(min=1)
-        else:
-            div = torch.where(div == 0, torch.ones_like(div), div)
+    # what travels: the (1 + F) partial sums, plus the divisor's share of this rank when it is not known
+    # up front.  Everything stays on the device: no host <-> device copy or sync on this path (the first
+    # version built the divisor with new_tensor(), two blocking copies per step: 0.47 ms on a 0.47 ms step)
+    need_div = batch_reduction == "mean" and (weights is not None or n_clouds_global is None)
+    if need_div:
+        div_local = weights.sum().reshape(1).to(local.dtype) if weights is not None else local.new_full((1,), float(n_local))
+        packed = torch.cat([local.detach(), div_local.detach()])
     else:
-        div = torch.ones_like(div)
+        packed = local.detach().clone()
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    total = packed[:local.shape[0]]
+    if batch_reduction == "mean":
+        if not need_div:
+            div = float(max(n_clouds_global, 1))
+        elif weights is None:
+            div = packed[-1].clamp(min=1)
+        else:
+            div = torch.where(packed[-1] == 0, torch.ones_like(packed[-1]), packed[-1])
+    else:
+        div = 1.0
     # value = global sum / div;  gradient = d(local sum)/div  (other ranks' terms are constants)
     out = (local + (total - local.detach())) / div
     out_feats = {k: out[1 + i] for i, k in enumerate(names)} if feats is not None else None

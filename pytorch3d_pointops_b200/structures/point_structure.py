@@ -618,9 +618,9 @@ def all_close(pcd1: Pointclouds, pcd2: Pointclouds, rtol=1e-05, atol=1e-08, verb
     points_ok = torch.allclose(pcd1.points_packed(), pcd2.points_packed(), rtol, atol)
     if verbose:
         print("Points all close:", points_ok)
-    keys1, keys2 = set(pcd1.features_packed().keys()), set(pcd2.features_packed().keys())
-    if keys1 != keys2:
-        if verbose:
+    keys1, keys2 = pcd1.features_packed().keys(), pcd2.features_packed().keys()
+    if set(keys1) != set(keys2):
+        if verbose:  # the key views themselves, as the reference prints them (:1399-1406)
             print("Features keys mismatch:", "Keys in pcd1:", keys1, "Keys in pcd2:", keys2)
         return False
     feats_ok = {

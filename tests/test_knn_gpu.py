@@ -79,6 +79,32 @@ SWEEP = [
 ]
 
 
+@pytest.fixture
+def force_tiled():
+    """Keep D=3 L2 calls on the tiled brute-force kernel (the default route only for P2 < 64 and K > 32)."""
+    from pytorch3d_pointops_b200 import _lib
+
+    lib = _lib.load()
+    lib.pops_set_option(b"knn_order", 0)
+    yield
+    lib.pops_set_option(b"knn_order", -1)
+
+
+@pytest.mark.parametrize("N,P1,P2,K", [(2, 700, 900, 16), (3, 513, 2049, 1), (2, 100, 5000, 32), (1, 300, 3000, 4)])
+def test_tiled_d3_kernel_vs_oracle(oracle, force_tiled, N, P1, P2, K):
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(N * 77 + P1 + P2 + K)
+    p1 = torch.randn(N, P1, 3, generator=gen)
+    p2 = torch.randn(N, P2, 3, generator=gen)
+    l1 = torch.randint(0, P1 + 1, (N,), generator=gen)
+    l2 = torch.randint(0, P2 + 1, (N,), generator=gen)
+    l1[0], l2[0] = P1, P2
+    oi, od = oracle.knn_points_idx(p1, p2, l1, l2, 2, K)
+    gi, gd = _C.knn_points_idx(p1.to(DEV), p2.to(DEV), l1.to(DEV), l2.to(DEV), 2, K, -1)
+    assert torch.equal(gi.cpu(), oi)
+    assert torch.equal(gd.cpu(), od)
+
+
 @pytest.mark.parametrize("N,P1,P2,D,K,norm", SWEEP)
 def test_oracle_sweep(oracle, N, P1, P2, D, K, norm):
     _C, _, _ = _ops()
