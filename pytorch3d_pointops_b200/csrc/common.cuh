@@ -167,6 +167,17 @@ __device__ __forceinline__ uint64_t make_key_total(float d, uint32_t j) {
   return (static_cast<uint64_t>(b) << 32) | j;
 }
 
+// One 12-byte row (x, y, z) with two loads instead of three: an 8-byte and a 4-byte one, whichever order
+// the row's alignment allows.  Row gathers are bound by L1 sector lookups per instruction, not by bytes.
+__device__ __forceinline__ void ldg_row3(const float* row, float& x, float& y, float& z) {
+  const bool al = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
+  const float2 a = __ldg(reinterpret_cast<const float2*>(al ? row : row + 1));
+  const float b = __ldg(al ? row + 2 : row);
+  x = al ? a.x : b;
+  y = al ? a.y : a.x;
+  z = al ? b : a.y;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

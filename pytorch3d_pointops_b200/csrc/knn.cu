@@ -551,10 +551,15 @@ knn_backward_rows_kernel(const float* __restrict__ p1, const float* __restrict__
     for (int u = 0; u < UNB; ++u) {
       const float* a = p1 + rw[u] * DT;
       const float* b = p2 + (static_cast<int64_t>(nn[u]) * P2 + (ok[u] ? i2[u] : 0)) * DT;
+      if (DT == 3) {  // two loads per 12-byte row instead of three
+        ldg_row3(a, av[u][0], av[u][1 % DT], av[u][2 % DT]);
+        ldg_row3(b, bv[u][0], bv[u][1 % DT], bv[u][2 % DT]);
+      } else {
 #pragma unroll
-      for (int d = 0; d < DT; ++d) {
-        av[u][d] = __ldg(a + d);
-        bv[u][d] = __ldg(b + d);
+        for (int d = 0; d < DT; ++d) {
+          av[u][d] = __ldg(a + d);
+          bv[u][d] = __ldg(b + d);
+        }
       }
     }
 #pragma unroll

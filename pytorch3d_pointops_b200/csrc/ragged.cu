@@ -194,6 +194,69 @@ gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
   }
 }
 
+// U = 3 (xyz rows, the shape of every knn_gather / masked_gather on points) with L*K % 4 == 0 and
+// 16-byte aligned buffers: one thread owns FOUR consecutive output rows = 48 bytes = three aligned
+// 16-byte stores, reads their four indices as two 16-byte loads, and fetches every 12-byte source row
+// with one 8-byte and one 4-byte load (which of the two comes first depends on the row's parity).
+// The gather is bound by L1 sector lookups, not by HBM (ncu: l1tex 63 %, dram 21 % for the generic
+// kernel): this form needs 2.5 lookups per row instead of 4.5.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+gather_rows3_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
+                    const int64_t* __restrict__ lengths, unsigned LK, unsigned K, int M, int N,
+                    float* __restrict__ out, int32_t* __restrict__ oob) {
+  const unsigned quads = LK >> 2;
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    float* dst = out + static_cast<int64_t>(n) * LK * 3;
+    const int64_t* idx_n = idx + static_cast<int64_t>(n) * LK;
+    const float* x_n = x + static_cast<int64_t>(n) * M * 3;
+    unsigned klim = K;
+    if (MODE == POPS_GATHER_KNN && lengths != nullptr) {
+      const int64_t len = lengths[n];
+      klim = len < 0 ? 0u : (len < static_cast<int64_t>(K) ? static_cast<unsigned>(len) : K);
+    }
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < quads; t += gridDim.x * blockDim.x) {
+      const unsigned r0 = t << 2;
+      const longlong2 ja = __ldg(reinterpret_cast<const longlong2*>(idx_n + r0));
+      const longlong2 jb = __ldg(reinterpret_cast<const longlong2*>(idx_n + r0 + 2));
+      const long long j[4] = {ja.x, ja.y, jb.x, jb.y};
+      bool take[4];
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        take[i] = j[i] >= 0 && j[i] < M;
+        if (MODE == POPS_GATHER_KNN) {
+          const bool live = klim == K || ((r0 + i) % K) < klim;
+          bad = bad || (live && !take[i]);
+          take[i] = take[i] && live;
+        }
+      }
+      if (MODE == POPS_GATHER_KNN && bad && oob != nullptr) *oob = 1;
+      float2 a[4];
+      float b[4];
+      bool al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // all eight loads first (row 0 of the cloud stands in for "zeros")
+        const float* row = x_n + (take[i] ? j[i] : 0) * 3;
+        al[i] = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
+        a[i] = __ldg(reinterpret_cast<const float2*>(al[i] ? row : row + 1));
+        b[i] = __ldg(al[i] ? row + 2 : row);
+      }
+      float v[12];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[3 * i + 0] = take[i] ? (al[i] ? a[i].x : b[i]) : 0.0f;
+        v[3 * i + 1] = take[i] ? (al[i] ? a[i].y : a[i].x) : 0.0f;
+        v[3 * i + 2] = take[i] ? (al[i] ? b[i] : a[i].y) : 0.0f;
+      }
+      float4* o = reinterpret_cast<float4*>(dst + static_cast<int64_t>(r0) * 3);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+      o[2] = make_float4(v[8], v[9], v[10], v[11]);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void gather_backward_kernel(const float* __restrict__ grad_out,
                                        const int64_t* __restrict__ idx,
@@ -353,6 +416,17 @@ extern "C" int pops_gather(const float* x, const int64_t* idx, const int64_t* le
                   (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   const dim3 grid = segment_grid(ceil_div(ceil_div(L * K * U + 3, 4), 4), N, 256);  // 4 chunks per thread and pass
   profile_begin("gather", st);
+  if (U == 3 && (L * K) % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && reinterpret_cast<uintptr_t>(idx) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(x) % 8 == 0 && get_option("gather_rows3", 1) != 0) {
+    const dim3 g3 = segment_grid(L * K / 4, N, 256);
+    if (mode == POPS_GATHER_KNN)
+      gather_rows3_kernel<POPS_GATHER_KNN><<<g3, 256, 0, st>>>(x, idx, lengths, unsigned(L * K), unsigned(K), int(M), int(N), out, oob_flag);
+    else
+      gather_rows3_kernel<POPS_GATHER_MASKED><<<g3, 256, 0, st>>>(x, idx, lengths, unsigned(L * K), unsigned(K), int(M), int(N), out, oob_flag);
+    profile_end("gather", st);
+    POPS_LAUNCH_OK("gather_rows3_kernel");
+    return POPS_OK;
+  }
 #define POPS_GATHER(MODE, UT, V4)                                                                        \
   gather_kernel<MODE, UT, V4><<<grid, 256, 0, st>>>(x, idx, lengths, unsigned(L * K), unsigned(K), int(M), \
                                                     unsigned(U), int(N), out, oob_flag)

@@ -50,6 +50,12 @@ def main():
     for mode, nm in ((_C.GATHER_MASKED, "masked"), (_C.GATHER_KNN, "knn")):
         ms = timed(lambda: _C.gather(x, idx, None, mode))
         report(f"gather {nm} C4 U=3", ms, rows * (8 + 12 + 12), rows * (8 + 12) + x.numel() * 4)
+    x3 = torch.rand(32, 16384, 3, generator=g).to(DEV)
+    L3 = torch.full((32,), 16384, dtype=torch.int64, device=DEV)
+    idx3, _ = _C.knn_points_idx(x3, x3, L3, L3, 2, 16, -1)
+    r3 = 32 * 16384 * 16
+    ms = timed(lambda: _C.gather(x3, idx3, L3, _C.GATHER_KNN))
+    report("gather knn T U=3 (KNN indices)", ms, r3 * (8 + 12 + 12), r3 * (8 + 12) + x3.numel() * 4)
     x16 = torch.rand(32, 16384, 16, generator=g).to(DEV)
     idx16 = torch.randint(0, 16384, (32, 16384, 16), generator=g).to(DEV)
     r16 = 32 * 16384 * 16
