@@ -56,8 +56,9 @@ int64_t pops_launch_count(void);
  *   knn_curve   1 Hilbert (default) | 0 Morton order in the spatial pre-pass; knn_axis_bits n: grid bits
  *               per axis of the curve codes (0 = sized to the cloud); knn_pair 1 | 0: one pre-pass for
  *               both directions in pops_knn_points_idx_pair; knn_fused_prepass 1 | 0: single-launch
- *               pre-pass (one CTA sorts a cloud in shared memory) for clouds of up to 8192 points
- *               (knn_fused_items 16: up to 16384)
+ *               pre-pass (a thread-block cluster sorts a cloud, or the two clouds of a pair, in
+ *               distributed shared memory) for clouds of up to 65536 points (32768 with two tensors);
+ *               knn_cluster_items 0 auto | 2 | 4 | 8: sort keys per thread of that kernel
  *   knn_tc      -1 auto | 0 never | 1 whenever the shape allows: tensor-core path for 32 <= D <= 256
  *   tc_cluster  CTAs that share every p2 stage by TMA multicast (1 | 2 | 4) */
 void pops_set_option(const char* name, int value);

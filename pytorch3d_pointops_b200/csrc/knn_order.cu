@@ -19,7 +19,6 @@
 //                           position in the sorted p2 (binary search of its code)
 //   5. box_kernel           bounding box of every block
 // Results never depend on the order: the exact 64-bit key (dist, ORIGINAL index) decides.
-#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cfloat>
@@ -261,6 +260,44 @@ __device__ __forceinline__ unsigned curve_code(const float* p, const float* bb, 
   return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
 }
 
+// Same curve, grid cell from a precomputed scale = cells / extent per axis (0 for a flat axis): a
+// multiplication instead of a division per coordinate.  Cells may differ from curve_code's by one at
+// cell borders; the order only steers the search, never its results.
+__device__ __forceinline__ unsigned curve_code_scaled(float x, float y, float z, const float* lo, const float* scale,
+                                                      int axis_bits, bool hilbert) {
+  const float top = static_cast<float>((1u << axis_bits) - 1u);
+  const float p[3] = {x, y, z};
+  unsigned X[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float t = (p[d] - lo[d]) * scale[d];
+    t = fminf(fmaxf(t, 0.0f), top);  // NaN -> 0
+    X[d] = static_cast<unsigned>(t);
+  }
+  if (!hilbert) return spread3(X[0]) | (spread3(X[1]) << 1) | (spread3(X[2]) << 2);
+  const unsigned M = 1u << (axis_bits - 1);
+  for (unsigned Q = M; Q > 1u; Q >>= 1) {  // inverse undo
+    const unsigned P = Q - 1u;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q) {
+        X[0] ^= P;
+      } else {
+        const unsigned t = (X[0] ^ X[i]) & P;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];  // Gray encode
+  X[2] ^= X[1];
+  unsigned t = 0u;
+  for (unsigned Q = M; Q > 1u; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1u;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
+}
+
 // element e in [0, N*P2) -> tensor 0 (p2); [N*P2, N*(P1+P2)) -> tensor 1 (p1)
 __global__ void morton_keys_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                    const int64_t* __restrict__ len1, const int64_t* __restrict__ len2,
@@ -433,243 +470,467 @@ __global__ void gather_pair_kernel(const float* __restrict__ pts, const int64_t*
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused pre-pass for clouds that fit one CTA (<= 1024 * ITEMS = 8192 points per tensor): ONE launch does
-// what bbox + keys + device radix sort + gathers + boxes (11-14 launches) do -- these shapes are
-// launch-bound (chamfer: 26 launches per step), and a 16 K-key sort is a shared-memory job.
-//   grid (T, N), cluster (T, 1, 1): CTA t of the cluster orders tensor t of cloud n (t = 0: p2, the
-//   blocks of search `a`; t = 1: p1, the queries of `a` and, in pair mode, the blocks of `b`).
-//   1. box + max |coordinate| of the CTA's own points; the two CTAs exchange them over DSMEM (the
-//      grid of the curve codes spans both clouds);
-//   2. curve codes, cub::BlockRadixSort on (code, index) in shared memory (stable: padding entries
-//      carry the largest code and follow the valid points);
-//   3. straight from the sorted registers: block rows, per-block boxes (shuffle reduction over the
-//      64 / ITEMS threads of a block), sorted queries, sorted codes;
-//   4. cluster barrier, then every query's home = lower bound of its code among the OTHER tensor's
-//      sorted codes.
+// Cluster pre-pass: ONE launch, one thread-block cluster per cloud (pair), C CTAs per tensor.
+//   grid (T*C, N), cluster (T*C, 1, 1); CTA x of the cluster: tensor t = x / C (0: p2, 1: p1), slice
+//   r = x % C of S = 1024 * ITEMS input positions.  Every exchange between the CTAs goes through
+//   distributed shared memory; global memory sees the points once on the way in and the ordered
+//   buffers once on the way out.
+//   1. box + max |coordinate| of the slice, all-to-all over DSMEM (the grid spans both tensors);
+//   2. curve codes in registers;
+//   3. stable LSD radix sort of (code, index) ACROSS the C CTAs of the tensor, one or two passes of
+//      <= 9 bits: per-warp digit counters (match.any ranks inside the warp), prefix over warps, the CTA
+//      totals to every peer, bases from the cluster-wide digit histogram, then each key is stored
+//      straight into the shared memory of the CTA that owns its destination;
+//   4. outputs from the sorted slice: block rows, one bounding box per 64 points (a warp owns whole
+//      blocks), sorted queries;
+//   5. homes: one lower bound per 16 sorted queries among the OTHER tensor's sorted codes, read from
+//      its CTAs' shared memory (the search uses one home per warp, as the start of its outward walk).
+// Same order as the multi-launch path (stable by index among equal codes), so the search does the
+// same work; 16384-point clouds of the T shape use 4 CTAs each = 128 CTAs on 148 SMs.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFusedThreads = 1024;
+constexpr int kOcThreads = 1024;
+constexpr int kOcWarps = kOcThreads / 32;
+constexpr int kOcDigitBits = 9;             // 18 code bits in two passes
+constexpr int kOcBins = 1 << kOcDigitBits;
+constexpr int kOcWcStride = kOcBins + 2;    // u16 row stride of the per-warp counters: column reads hit 32 banks
+constexpr int kOcMaxCtas = 8;               // portable cluster size
 
-struct FusedOrderParams {
+struct ClusterOrderParams {
   const float* p[2];         // [0] = p2, [1] = p1
   const int64_t* len[2];
   int P[2];
   int mode;                  // 0 self (one tensor), 1 single search (a), 2 pair (a and b)
   int axis_bits, hilbert;
+  int C;                     // CTAs per tensor
+  int idx_bits;              // log2(C * S): a key is (code << idx_bits) | index
   KnnOrderBuffers a, b;
-  unsigned* codes[2];        // sorted codes per tensor: [N][P[t]]
 };
 
-template <int ITEMS>
-__global__ void __launch_bounds__(kFusedThreads, 1)
-order_cloud_kernel(const FusedOrderParams prm) {
-  // (code << IDX_BITS | index) in ONE 32-bit key, sorted on the code bits only: no value array to carry
-  constexpr int IDX_BITS = ITEMS == 8 ? 13 : 14;  // log2(1024 * ITEMS)
-  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS>;
-  extern __shared__ __align__(16) unsigned char fsm[];
-  typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(fsm);
-  __shared__ float red[32];
-  __shared__ float part[2][8];  // per CTA of the cluster: min xyz, max xyz
-  __shared__ float bb[6];
+// KeyT: unsigned while code and index fit 32 bits together (18 + 14: clouds of up to 16384 points), else 64 bits
+template <int ITEMS, typename KeyT>
+struct OcSmem {
+  static constexpr int S = kOcThreads * ITEMS;
+  KeyT buf[2][S];                            // ping / pong of the radix passes; the idle one stages the local order
+  unsigned short wc[kOcWarps][kOcWcStride];  // per-warp digit counts, then their exclusive prefix over warps
+  unsigned short ctot[kOcMaxCtas][kOcBins];  // digit totals of every CTA of this tensor (written by the peers)
+  unsigned base[kOcBins];                    // first destination of (digit, this CTA) in the tensor's order
+  unsigned lbase[kOcBins];                   // first position of the digit in this CTA's local order
+  uint2 wsum[kOcWarps];
+  float redw[kOcWarps][8];
+  float part[kOcMaxCtas][8];                 // per CTA of the cluster: min xyz, max xyz, max |coordinate| bits
+  float bb[6];
+  float scale[3];                            // grid cells per unit length, per axis
+};
+
+__device__ __forceinline__ uint32_t oc_remote(const void* local_smem_ptr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void oc_st(uint32_t addr, unsigned v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void oc_st(uint32_t addr, unsigned long long v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void oc_st_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void oc_ld(uint32_t addr, unsigned& v) {
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void oc_ld(uint32_t addr, unsigned long long& v) {
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+}
+
+template <int ITEMS, typename KeyT>
+__global__ void __launch_bounds__(kOcThreads, 1)
+order_cluster_kernel(const ClusterOrderParams prm) {
+  using SM = OcSmem<ITEMS, KeyT>;
+  constexpr int S = SM::S;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char ocsm[];
+  SM& sm = *reinterpret_cast<SM*>(ocsm);
   bb_cluster_arrive();
-  const int T = gridDim.x;
-  const int t = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const int C = prm.C;
+  const int CT = gridDim.x;  // CTAs per cluster
+  const int t = blockIdx.x / C, r = blockIdx.x % C, n = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = prm.P[t];
   int64_t Ll = prm.len[t][n];
   const int L = static_cast<int>(Ll < 0 ? 0 : (Ll > P ? P : Ll));
   const float* pts = prm.p[t] + static_cast<size_t>(n) * P * 3;
+  const float INF = __int_as_float(0x7f800000);
+  const int IB = prm.idx_bits;
+  // local position q of (warp, item i, lane): runs of 32 consecutive points per warp and item; the sort is
+  // stable with respect to this order, which is the index order
+  const int q0 = warp * (32 * ITEMS) + lane;
 
-  // ---- 1. box of both tensors ---------------------------------------------------------------------
-  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  unsigned mb = 0u;  // max |coordinate| as a bit pattern (+inf and NaN rank highest)
-  for (int j = tid; j < L; j += kFusedThreads) {
+  // ---- 1. the slice in registers, box of every tensor of the cluster --------------------------------
+  float px[ITEMS], py[ITEMS], pz[ITEMS];
+  {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    unsigned mb = 0u;  // max |coordinate| as a bit pattern (+inf and NaN rank highest)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float v = pts[static_cast<size_t>(j) * 3 + d];
-      mn[d] = fminf(mn[d], v);
-      mx[d] = fmaxf(mx[d], v);
-      mb = max(mb, abs_bits(v));
+    for (int i = 0; i < ITEMS; ++i) {
+      const int j = r * S + q0 + i * 32;
+      px[i] = py[i] = pz[i] = 0.0f;
+      if (j < L) {
+        const float* src = pts + static_cast<size_t>(j) * 3;
+        px[i] = src[0]; py[i] = src[1]; pz[i] = src[2];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int j = r * S + q0 + i * 32;
+      if (j < L) {
+        mn[0] = fminf(mn[0], px[i]); mn[1] = fminf(mn[1], py[i]); mn[2] = fminf(mn[2], pz[i]);
+        mx[0] = fmaxf(mx[0], px[i]); mx[1] = fmaxf(mx[1], py[i]); mx[2] = fmaxf(mx[2], pz[i]);
+        mb = max(mb, max(abs_bits(px[i]), max(abs_bits(py[i]), abs_bits(pz[i]))));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], o));
+        mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], o));
+      }
+    }
+    mb = __reduce_max_sync(FULL, mb);
+    if (lane == 0) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        sm.redw[warp][d] = mn[d];
+        sm.redw[warp][3 + d] = mx[d];
+      }
+      sm.redw[warp][6] = __uint_as_float(mb);
+    }
+    __syncthreads();
+    bb_cluster_wait();  // every CTA of the cluster is running: its shared memory can be written
+    if (warp < 7) {     // warp k reduces value k over the 32 warps, then lanes < CT send it to every CTA
+      float v = sm.redw[lane][warp];
+      if (warp < 3) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+      } else if (warp < 6) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+      } else {
+        v = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(v)));  // bits, never used as a float
+      }
+      if (lane < CT) oc_st(oc_remote(&sm.part[blockIdx.x][warp], static_cast<uint32_t>(lane)), __float_as_uint(v));
+    }
+    bb_cluster_barrier();
+    if (tid < 3) {
+      float lo = sm.part[0][tid], hi = sm.part[0][3 + tid];
+      for (int cr = 1; cr < CT; ++cr) {
+        lo = fminf(lo, sm.part[cr][tid]);
+        hi = fmaxf(hi, sm.part[cr][3 + tid]);
+      }
+      sm.bb[tid] = lo;
+      sm.bb[3 + tid] = hi;
+      const float ext = hi - lo;
+      sm.scale[tid] = ext > 0.0f ? static_cast<float>(1u << prm.axis_bits) / ext : 0.0f;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) {
+      unsigned m = 0u;
+      for (int cr = 0; cr < CT; ++cr) m = max(m, __float_as_uint(sm.part[cr][6]));
+#pragma unroll
+      for (int d = 0; d < 6; ++d) prm.a.bbox[n * 6 + d] = sm.bb[d];
+      prm.a.maxabs_bits[n] = m;
     }
   }
-  float out[7];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    out[d] = block_reduce(mn[d], false, red);
-    out[3 + d] = block_reduce(mx[d], true, red);
-  }
-  out[6] = __uint_as_float(block_reduce_umax(mb, reinterpret_cast<unsigned*>(red)));  // bits, never used as a float
-  bb_cluster_wait();  // the peer CTA is running: its shared memory can be written
-  if (tid < 7) {
-    float v = out[0];
-#pragma unroll
-    for (int d = 1; d < 7; ++d) v = (tid == d) ? out[d] : v;
-    for (int r = 0; r < T; ++r) bb_st_remote(&part[t][tid], static_cast<uint32_t>(r), v);
-  }
-  if (T > 1) bb_cluster_barrier(); else __syncthreads();
-  if (tid < 3) {
-    float lo = part[0][tid], hi = part[0][3 + tid];
-    if (T > 1) {
-      lo = fminf(lo, part[1][tid]);
-      hi = fmaxf(hi, part[1][3 + tid]);
-    }
-    bb[tid] = lo;
-    bb[3 + tid] = hi;
-  }
-  __syncthreads();
-  if (t == 0 && tid == 0) {
-    unsigned m = __float_as_uint(part[0][6]);
-    if (T > 1) m = max(m, __float_as_uint(part[1][6]));
-#pragma unroll
-    for (int d = 0; d < 6; ++d) prm.a.bbox[n * 6 + d] = bb[d];
-    prm.a.maxabs_bits[n] = m;
-  }
 
-  // ---- 2. codes + sort (blocked arrangement: thread tid holds positions tid*ITEMS + i) ------------
+  // ---- 2. keys = (curve code, index) ------------------------------------------------------------------
   const int code_bits = 3 * prm.axis_bits;
-  unsigned keys[ITEMS];
+  KeyT key[ITEMS];
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const int j = tid * ITEMS + i;
-    unsigned code = (1u << code_bits) - 1u;  // padding: largest code, kept behind the valid points by stability
-    if (j < L) code = curve_code(pts + static_cast<size_t>(j) * 3, bb, prm.axis_bits, prm.hilbert != 0);
-    keys[i] = (code << IDX_BITS) | static_cast<unsigned>(j);
+    const int j = r * S + q0 + i * 32;
+    // padding: largest code, kept behind the valid points by stability (they follow them in the input)
+    unsigned code = curve_code_scaled(px[i], py[i], pz[i], sm.bb, sm.scale, prm.axis_bits, prm.hilbert != 0);
+    if (j >= L) code = (1u << code_bits) - 1u;
+    key[i] = (static_cast<KeyT>(code) << IB) | static_cast<KeyT>(j);
   }
-  Sort(temp).Sort(keys, IDX_BITS, IDX_BITS + code_bits);
 
-  // ---- 3. outputs from the sorted registers -----------------------------------------------------
+  // ---- 3. stable LSD radix sort across the C CTAs of this tensor --------------------------------------
+  const int npass = code_bits > kOcDigitBits ? 2 : 1;
+  const int lo_bits = npass == 2 ? code_bits / 2 : code_bits;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int shift = IB + (pass == 0 ? 0 : lo_bits);
+    const int NB = 1 << (pass == 0 ? lo_bits : code_bits - lo_bits);
+    KeyT* stage = sm.buf[(pass + 1) & 1];  // the buffer no peer writes during this pass
+    if (pass == 1) {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) key[i] = sm.buf[0][q0 + i * 32];
+    }
+    for (int b = lane; b < NB; b += 32) sm.wc[warp][b] = 0;
+    __syncwarp();
+    unsigned pre[ITEMS];  // keys of this warp with the same digit that come earlier
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const unsigned d = static_cast<unsigned>(key[i] >> shift) & static_cast<unsigned>(NB - 1);
+      // lanes with the same digit: one ballot per digit bit (independent, pipelined) beats match.any here
+      unsigned peers = FULL;
+#pragma unroll
+      for (int bit = 0; bit < kOcDigitBits; ++bit) {
+        const unsigned bal = __ballot_sync(FULL, (d >> bit) & 1u);
+        peers &= ((d >> bit) & 1u) ? bal : ~bal;
+      }
+      const int leader = __ffs(peers) - 1;
+      unsigned old = 0;
+      if (lane == leader) {
+        old = sm.wc[warp][d];
+        sm.wc[warp][d] = static_cast<unsigned short>(old + __popc(peers));
+      }
+      old = __shfl_sync(FULL, old, leader);
+      pre[i] = old + __popc(peers & ((1u << lane) - 1u));
+      __syncwarp();
+    }
+    __syncthreads();  // (also: every thread has its pass-1 keys in registers before buf[0] becomes the stage)
+    // exclusive prefix over the warps, one digit per step and warp (lane = counting warp); the CTA's
+    // digit total goes to every peer of the tensor
+    for (int b0 = warp * 4; b0 < NB; b0 += kOcWarps * 4) {  // 4 digits per step: independent shuffle chains
+      unsigned v[4], incl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = (b0 + u < NB) ? sm.wc[lane][b0 + u] : 0u;
+        incl[u] = v[u];
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned up = __shfl_up_sync(FULL, incl[u], o);
+          if (lane >= o) incl[u] += up;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b0 + u >= NB) break;
+        sm.wc[lane][b0 + u] = static_cast<unsigned short>(incl[u] - v[u]);
+        const unsigned tot = __shfl_sync(FULL, incl[u], 31);
+        if (lane < C)
+          oc_st_u16(oc_remote(&sm.ctot[r][b0 + u], static_cast<uint32_t>(t * C + lane)), static_cast<unsigned short>(tot));
+      }
+    }
+    bb_cluster_barrier();
+    {
+      // base of (digit, this CTA) = keys of the tensor with a smaller digit + same digit in earlier CTAs;
+      // lbase of the digit = keys of this CTA with a smaller digit
+      unsigned col = 0, below = 0, own = 0;
+      if (tid < NB) {
+        for (int cr = 0; cr < C; ++cr) {
+          const unsigned v = sm.ctot[cr][tid];
+          col += v;
+          if (cr < r) below += v;
+          if (cr == r) own = v;
+        }
+      }
+      unsigned ic = col, io = own;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned uc = __shfl_up_sync(FULL, ic, o), uo = __shfl_up_sync(FULL, io, o);
+        if (lane >= o) { ic += uc; io += uo; }
+      }
+      if (lane == 31) sm.wsum[warp] = make_uint2(ic, io);
+      __syncthreads();
+      if (warp == 0) {
+        const uint2 v = sm.wsum[lane];
+        unsigned sc = v.x, so = v.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned uc = __shfl_up_sync(FULL, sc, o), uo = __shfl_up_sync(FULL, so, o);
+          if (lane >= o) { sc += uc; so += uo; }
+        }
+        sm.wsum[lane] = make_uint2(sc - v.x, so - v.y);
+      }
+      __syncthreads();
+      if (tid < NB) {
+        const uint2 w = sm.wsum[warp];
+        sm.base[tid] = w.x + ic - col + below;
+        sm.lbase[tid] = w.y + io - own;
+      }
+      __syncthreads();
+    }
+    // local order first (plain shared-memory stores), then consecutive threads send consecutive keys:
+    // a run of equal digits lands on consecutive addresses of one peer
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const unsigned d = static_cast<unsigned>(key[i] >> shift) & static_cast<unsigned>(NB - 1);
+      stage[sm.lbase[d] + sm.wc[warp][d] + pre[i]] = key[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const unsigned lq = static_cast<unsigned>(i * kOcThreads + tid);
+      const KeyT k = stage[lq];
+      const unsigned d = static_cast<unsigned>(k >> shift) & static_cast<unsigned>(NB - 1);
+      const unsigned pos = sm.base[d] + (lq - sm.lbase[d]);
+      oc_st(oc_remote(&sm.buf[pass][pos % S], static_cast<uint32_t>(t * C) + pos / S), k);
+    }
+    bb_cluster_barrier();
+  }
+  const KeyT* fkey = sm.buf[npass - 1];
+  const unsigned idx_mask = (1u << IB) - 1u;
+
+  // ---- 4. outputs from the sorted slice: a warp owns whole blocks of 64 sorted points ---------------
   const bool blocks_role = (t == 0) || prm.mode == 2;           // this tensor is scanned as blocks
   const bool query_role = (t == 1) || prm.mode != 1;            // ... and / or asked as queries
   const KnnOrderBuffers& blk = (t == 0) ? prm.a : prm.b;        // search that scans this tensor
   const KnnOrderBuffers& qry = (t == 1 || prm.mode == 0) ? prm.a : prm.b;  // search that asks it
   const int nbox = static_cast<int>((((P + kBoxPoints - 1) / kBoxPoints) + 31) / 32 * 32);
-  const float INF = __int_as_float(0x7f800000);
-  float bmn[3] = {INF, INF, INF}, bmx[3] = {-INF, -INF, -INF};
+  for (int bl = warp; bl < S / kBoxPoints; bl += kOcWarps) {
+    float bmn[3] = {INF, INF, INF}, bmx[3] = {-INF, -INF, -INF};
+    const int gb = r * (S / kBoxPoints) + bl;  // block of the cloud
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int s = tid * ITEMS + i;
-    const unsigned o = keys[i] & ((1u << IDX_BITS) - 1u);
-    float x = 0.f, y = 0.f, z = 0.f, w = INF;
-    unsigned orig = kNoPoint;
-    if (s < L) {
-      const float* src = pts + static_cast<size_t>(o) * 3;
-      x = src[0]; y = src[1]; z = src[2];
-      w = fmaf(z, z, fmaf(y, y, x * x));
-      orig = o;
-      bmn[0] = fminf(bmn[0], x); bmn[1] = fminf(bmn[1], y); bmn[2] = fminf(bmn[2], z);
-      bmx[0] = fmaxf(bmx[0], x); bmx[1] = fmaxf(bmx[1], y); bmx[2] = fmaxf(bmx[2], z);
-    }
-    if (blocks_role && s < nbox * kBoxPoints) {
-      float* dst = blk.blocks + (static_cast<size_t>(n) * nbox + s / kBoxPoints) * kBlockFloats + (s % kBoxPoints);
-      dst[0] = x;
-      dst[kBoxPoints] = y;
-      dst[2 * kBoxPoints] = z;
-      dst[3 * kBoxPoints] = w;
-      dst[4 * kBoxPoints] = __uint_as_float(orig);
-    }
-    if (s < P) {
-      if (query_role) qry.qsorted[static_cast<size_t>(n) * P + s] = make_float4(x, y, z, __uint_as_float(o));
-      prm.codes[t][static_cast<size_t>(n) * P + s] = keys[i] >> IDX_BITS;
-    }
-  }
-  if (blocks_role) {
-    constexpr int TPB = kBoxPoints / ITEMS;  // threads per block of 64 sorted points (consecutive lanes)
-    static_assert(TPB >= 1 && TPB <= 32 && (TPB & (TPB - 1)) == 0, "a block is a power-of-two run of lanes");
-#pragma unroll
-    for (int o2 = TPB / 2; o2 > 0; o2 >>= 1) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        bmn[d] = fminf(bmn[d], __shfl_xor_sync(0xffffffffu, bmn[d], o2));
-        bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(0xffffffffu, bmx[d], o2));
+    for (int h = 0; h < kBoxPoints / 32; ++h) {
+      const int q = bl * kBoxPoints + h * 32 + lane;
+      const int s = r * S + q;
+      const unsigned o = static_cast<unsigned>(fkey[q]) & idx_mask;
+      float x = 0.f, y = 0.f, z = 0.f, w = INF;
+      unsigned orig = kNoPoint;
+      if (s < L) {
+        const float* src = pts + static_cast<size_t>(o) * 3;
+        x = src[0]; y = src[1]; z = src[2];
+        w = fmaf(z, z, fmaf(y, y, x * x));
+        orig = o;
+        bmn[0] = fminf(bmn[0], x); bmn[1] = fminf(bmn[1], y); bmn[2] = fminf(bmn[2], z);
+        bmx[0] = fmaxf(bmx[0], x); bmx[1] = fmaxf(bmx[1], y); bmx[2] = fmaxf(bmx[2], z);
+      }
+      if (blocks_role && gb < nbox) {
+        float* dst = blk.blocks + (static_cast<size_t>(n) * nbox + gb) * kBlockFloats + (h * 32 + lane);
+        dst[0] = x;
+        dst[kBoxPoints] = y;
+        dst[2 * kBoxPoints] = z;
+        dst[3 * kBoxPoints] = w;
+        dst[4 * kBoxPoints] = __uint_as_float(orig);
+      }
+      if (query_role && s < P) {
+        qry.qsorted[static_cast<size_t>(n) * P + s] = make_float4(x, y, z, __uint_as_float(o));
+        if (prm.mode == 0) qry.qhome[static_cast<size_t>(n) * P + s] = static_cast<unsigned>(s);
       }
     }
-    const int b0 = tid / TPB;
-    if (tid % TPB == 0 && b0 < nbox) {
-      float4* dst = blk.boxes + (static_cast<size_t>(n) * nbox + b0) * 2;
-      dst[0] = make_float4(bmn[0], bmn[1], bmn[2], 0.f);
-      dst[1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
+    if (blocks_role && gb < nbox) {
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          bmn[d] = fminf(bmn[d], __shfl_xor_sync(FULL, bmn[d], o2));
+          bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(FULL, bmx[d], o2));
+        }
+      }
+      if (lane == 0) {
+        float4* dst = blk.boxes + (static_cast<size_t>(n) * nbox + gb) * 2;
+        dst[0] = make_float4(bmn[0], bmn[1], bmn[2], 0.f);
+        dst[1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
+      }
     }
   }
+  if (prm.mode == 0) return;  // no remote access after the last cluster barrier
 
-  // ---- 4. homes: lower bound of every query's code among the other tensor's sorted codes ----------
-  if (prm.mode == 0) {
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int s = tid * ITEMS + i;
-      if (s < P) prm.a.qhome[static_cast<size_t>(n) * P + s] = static_cast<unsigned>(s);
-    }
-    return;
-  }
-  __threadfence();
-  bb_cluster_barrier();
-  if (!query_role) return;
-  const int ot = 1 - t;
-  const int Po = prm.P[ot];
-  int64_t Lol = prm.len[ot][n];
-  const int Lo = static_cast<int>(Lol < 0 ? 0 : (Lol > Po ? Po : Lol));
-  const unsigned* ko = prm.codes[ot] + static_cast<size_t>(n) * Po;
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int s = tid * ITEMS + i;
-    if (s >= P) continue;
-    unsigned home = 0;
-    if (s < L) {
-      int lo = 0, hi = Lo;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldcg(ko + mid) < (keys[i] >> IDX_BITS)) lo = mid + 1; else hi = mid;
+  // ---- 5. homes: one lower bound per 16 sorted queries, among the other tensor's sorted codes -------
+  if (query_role) {
+    const int ot = 1 - t;
+    const int Po = prm.P[ot];
+    int64_t Lol = prm.len[ot][n];
+    const int Lo = static_cast<int>(Lol < 0 ? 0 : (Lol > Po ? Po : Lol));
+    for (int g = tid; g < S / 16; g += kOcThreads) {
+      const int q = g * 16;
+      const int s = r * S + q;
+      if (s >= P) continue;
+      unsigned home = 0;
+      if (s < L) {
+        const unsigned target = static_cast<unsigned>(fkey[q] >> IB);
+        int lo = 0, hi = Lo;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          KeyT v;
+          oc_ld(oc_remote(&fkey[mid % S], static_cast<uint32_t>(ot * C + mid / S)), v);
+          if (static_cast<unsigned>(v >> IB) < target) lo = mid + 1; else hi = mid;
+        }
+        home = static_cast<unsigned>(lo);
       }
-      home = static_cast<unsigned>(lo);
+      unsigned* dst = qry.qhome + static_cast<size_t>(n) * P + s;
+      const int cnt = min(16, P - s);
+      for (int e = 0; e < cnt; ++e) dst[e] = home;
     }
-    qry.qhome[static_cast<size_t>(n) * P + s] = home;
   }
+  bb_cluster_barrier();  // a CTA's shared memory stays alive until its peers have finished reading it
 }
 
-template <int ITEMS>
-int launch_fused_order(const FusedOrderParams& prm, int N, cudaStream_t st) {
-  using Sort = cub::BlockRadixSort<unsigned, kFusedThreads, ITEMS>;
-  auto kern = order_cloud_kernel<ITEMS>;
-  const size_t smem = sizeof(typename Sort::TempStorage);
+template <int ITEMS, typename KeyT>
+int launch_cluster_order(const ClusterOrderParams& prm, int N, cudaStream_t st) {
+  auto kern = order_cluster_kernel<ITEMS, KeyT>;
+  const size_t smem = sizeof(OcSmem<ITEMS, KeyT>);
   POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int T = prm.mode == 0 ? 1 : 2;
+  const int CT = (prm.mode == 0 ? 1 : 2) * prm.C;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(T, static_cast<unsigned>(N));
-  cfg.blockDim = dim3(kFusedThreads);
+  cfg.gridDim = dim3(static_cast<unsigned>(CT), static_cast<unsigned>(N));
+  cfg.blockDim = dim3(kOcThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = T;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(CT);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, prm));
-  POPS_LAUNCH_OK("order_cloud_kernel");
+  POPS_LAUNCH_OK("order_cluster_kernel");
   return POPS_OK;
 }
 
-// mode as in FusedOrderParams; returns POPS_OK, or -1 when the shape does not fit (caller falls back)
+template <int ITEMS>
+int launch_cluster_order_k(const ClusterOrderParams& prm, int N, cudaStream_t st) {
+  if (3 * prm.axis_bits + prm.idx_bits <= 32) return launch_cluster_order<ITEMS, unsigned>(prm, N, st);
+  return launch_cluster_order<ITEMS, unsigned long long>(prm, N, st);
+}
+
+// mode as in ClusterOrderParams; returns POPS_OK, or -1 when the shape does not fit (caller falls back)
 int fused_order(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N, int P1, int P2,
-                int mode, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
+                  int mode, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
+  if (get_option("knn_fused_prepass", 1) == 0) return -1;  // 0: the multi-launch path (test / tuning aid)
   const int Pmax = mode == 0 ? P2 : std::max(P1, P2);
-  // up to 8 items per thread by default (knn_fused_items = 16 admits clouds of up to 16384 points): N or
-  // 2N CTAs leave most of the 148 SMs idle, which costs more GPU time than the launches it saves once the
-  // clouds are large (T shape, N = 32: 0.96 vs 0.915 ms per call); up to 8192 points the single launch
-  // wins on hosts where the step is launch-bound (chamfer step 0.50 vs 0.60 ms) and costs ~4 % where it
-  // is not (0.446 vs 0.427 ms)
-  const int items = get_option("knn_fused_items", 8) <= 8 ? 8 : 16;  // the two compiled forms; nothing larger exists
-  if (Pmax > kFusedThreads * items || get_option("knn_fused_prepass", 1) == 0) return -1;
-  FusedOrderParams prm;
+  const int T = mode == 0 ? 1 : 2;
+  const int cmax = kOcMaxCtas / T;
+  // slice size: the smallest (most CTAs per cloud) that still fits the grid into one wave of 1-CTA SMs;
+  // if none does, 4096 positions per CTA when the cluster can hold the cloud that way
+  const int forced = get_option("knn_cluster_items", 0);
+  auto ctas_for = [&](int it) {  // CTAs per tensor with `it` items per thread, 0: does not fit a cluster
+    if (forced > 0 && it != forced) return 0;
+    int c = 1;
+    while (c * kOcThreads * it < Pmax) c *= 2;
+    return c <= cmax ? c : 0;
+  };
+  int items = 0, C = 0;
+  for (int it : {2, 4, 8}) {
+    const int c = ctas_for(it);
+    if (c > 0 && int64_t(N) * T * c <= num_sms()) { items = it; C = c; break; }
+  }
+  if (items == 0) {
+    for (int it : {4, 8, 2}) {
+      const int c = ctas_for(it);
+      if (c > 0) { items = it; C = c; break; }
+    }
+  }
+  if (items == 0) return -1;
+  ClusterOrderParams prm;
   prm.p[0] = p2; prm.p[1] = p1; prm.len[0] = len2; prm.len[1] = len1; prm.P[0] = P2; prm.P[1] = P1;
   prm.mode = mode;
   const int want = (clog2(std::max(Pmax, 1)) + 4 + 2) / 3;
-  const int forced = get_option("knn_axis_bits", 0);
-  prm.axis_bits = std::min(6, forced > 0 ? forced : std::max(4, want));  // 18 code bits + 13-14 index bits = one key
+  const int fbits = get_option("knn_axis_bits", 0);
+  prm.axis_bits = std::min(6, fbits > 0 ? fbits : std::max(4, want));  // <= 18 code bits: two 9-bit passes
   prm.hilbert = get_option("knn_curve", 1) != 0;
+  prm.C = C;
+  prm.idx_bits = clog2(int64_t(C) * kOcThreads * items);
   prm.a = a; prm.b = b;
-  prm.codes[0] = a.keys_out;                                   // [N][P2]
-  prm.codes[1] = a.keys_out + static_cast<size_t>(N) * P2;     // [N][P1]
-  if (Pmax <= kFusedThreads * 8) return launch_fused_order<8>(prm, N, st);
-  return launch_fused_order<16>(prm, N, st);
+  if (items == 2) return launch_cluster_order_k<2>(prm, N, st);
+  if (items == 4) return launch_cluster_order_k<4>(prm, N, st);
+  return launch_cluster_order_k<8>(prm, N, st);
 }
 
 size_t cub_temp_bytes_for(int64_t items) {
@@ -713,6 +974,11 @@ size_t knn_order_workspace_bytes(int64_t N, int64_t P1, int64_t P2) {
 
 int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2,
                       int N, int P1, int P2, bool self_knn, const KnnOrderBuffers& b, cudaStream_t st) {
+  struct Prof {  // per-call device time of the whole pre-pass under pops_profile_enable(1)
+    cudaStream_t s;
+    explicit Prof(cudaStream_t s_) : s(s_) { profile_begin("knn_order", s); }
+    ~Prof() { profile_end("knn_order", s); }
+  } prof(st);
   {
     const int rc = fused_order(p1, p2, len1, len2, N, P1, P2, self_knn ? 0 : 1, b, b, st);
     if (rc >= 0) return rc;
@@ -759,6 +1025,11 @@ int knn_order_prepass(const float* p1, const float* p2, const int64_t* len1, con
 // buffers are used; b.maxabs_bits / b.bbox are not written (the caller points them at a's).
 int knn_order_prepass_pair(const float* p1, const float* p2, const int64_t* len1, const int64_t* len2, int N,
                            int P1, int P2, const KnnOrderBuffers& a, const KnnOrderBuffers& b, cudaStream_t st) {
+  struct Prof {
+    cudaStream_t s;
+    explicit Prof(cudaStream_t s_) : s(s_) { profile_begin("knn_order", s); }
+    ~Prof() { profile_end("knn_order", s); }
+  } prof(st);
   {
     const int rc = fused_order(p1, p2, len1, len2, N, P1, P2, 2, a, b, st);
     if (rc >= 0) return rc;

@@ -316,8 +316,8 @@ def test_pair_search_matches_two_calls():
     from pytorch3d_pointops_b200 import _lib
 
     lib = _lib.load()
-    # both pre-passes: the single-launch one (a CTA sorts a cloud of <= 8192 points in shared memory)
-    # and the device-wide sort (forced for the small shapes, natural for the 9000-point one)
+    # both pre-passes: the single-launch one (a thread-block cluster sorts the pair in distributed shared
+    # memory) and the device-wide sort
     for fused, (N, P1, P2, D, K, norm) in [(f, c) for f in (1, 0) for c in cases]:
         lib.pops_set_option(b"knn_fused_prepass", fused)
         p1 = torch.rand(N, P1, D, generator=gen).to(DEV)
@@ -436,3 +436,60 @@ def test_pruned_search_both_thread_shapes(oracle):
     oi, od = oracle.knn_points_idx(q1, big, Lq, Lb, 2, 8, threads=8)
     gi, gd = _C.knn_points_idx(q1.to(DEV), big.to(DEV), Lq.to(DEV), Lb.to(DEV), 2, 8, -1)
     assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("items", [0, 2, 4, 8])
+def test_cluster_prepass_every_slice_size(oracle, items):
+    """order_cluster_kernel (knn_order.cu): 1, 2, 4 or 8 CTAs per tensor, 2 / 4 / 8 keys per thread, 32- and
+    64-bit sort keys, one or two tensors, ragged / empty / tiny clouds, duplicated points (equal codes
+    straddling CTA borders), a flat cloud (one axis without extent).  Every configuration must give the
+    oracle's rows and, on the larger shapes, the rows of the device-wide-sort pre-pass."""
+    from pytorch3d_pointops_b200 import _lib
+
+    _C, _, _ = _ops()
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(900 + items)
+    try:
+        lib.pops_set_option(b"knn_cluster_items", items)
+        lib.pops_set_option(b"knn_order", 1)
+        # small: against the oracle.  (N, P1, P2, K, self)
+        for N, P1, P2, K, selfk in [(3, 700, 700, 8, True), (4, 3000, 2100, 4, False), (2, 5000, 5000, 16, True),
+                                    (2, 100, 9000, 1, False), (1, 64, 64, 3, True)]:
+            p2 = torch.rand(N, P2, 3, generator=gen)
+            p2[:, : P2 // 4] = p2[:, P2 // 4 : 2 * (P2 // 4)]  # duplicates: long runs of equal codes
+            p2[-1, :, 2] = 0.25                                 # a flat cloud
+            l2 = torch.randint(1, P2 + 1, (N,), generator=gen)
+            l2[0] = P2
+            if selfk:
+                p1, l1 = p2, l2
+            else:
+                p1 = torch.rand(N, P1, 3, generator=gen) * 1.3 - 0.1  # queries outside the blocks' box
+                l1 = torch.randint(0, P1 + 1, (N,), generator=gen)
+                if N > 2:
+                    l2[1] = 0  # nothing to search
+            oi, od = oracle.knn_points_idx(p1, p2, l1, l2, 2, K, threads=8)
+            d1, g1 = p1.to(DEV), l1.to(DEV)
+            d2, g2 = (d1, g1) if selfk else (p2.to(DEV), l2.to(DEV))  # same tensors: the self-search pre-pass
+            gi, gd = _C.knn_points_idx(d1, d2, g1, g2, 2, K, -1)
+            assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od), (items, N, P1, P2, K, selfk)
+            if not selfk:
+                i12, d12, i21, d21 = _C.knn_points_idx_pair(d1, d2, g1, g2, 2, K)
+                ri, rd = oracle.knn_points_idx(p2, p1, l2, l1, 2, K, threads=8)
+                assert torch.equal(i12.cpu(), oi) and torch.equal(d12.cpu(), od), (items, "pair 12")
+                assert torch.equal(i21.cpu(), ri) and torch.equal(d21.cpu(), rd), (items, "pair 21")
+        # large: against the device-wide sort (64-bit keys beyond 16384 positions per tensor)
+        for N, P1, P2, K, selfk in [(2, 40000, 40000, 8, True), (2, 20000, 30000, 4, False), (3, 16384, 16384, 16, True)]:
+            p2 = torch.rand(N, P2, 3, generator=gen).to(DEV)
+            l2 = torch.randint(P2 // 2, P2 + 1, (N,), generator=gen).to(DEV)
+            p1 = p2 if selfk else torch.rand(N, P1, 3, generator=gen).to(DEV)
+            l1 = l2 if selfk else torch.randint(P1 // 2, P1 + 1, (N,), generator=gen).to(DEV)
+            got = _C.knn_points_idx(p1, p2, l1, l2, 2, K, -1)
+            lib.pops_set_option(b"knn_fused_prepass", 0)
+            want = _C.knn_points_idx(p1, p2, l1, l2, 2, K, -1)
+            lib.pops_set_option(b"knn_fused_prepass", 1)
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), (items, N, P1, P2, K, selfk)
+    finally:
+        lib.pops_set_option(b"knn_cluster_items", 0)
+        lib.pops_set_option(b"knn_order", -1)
+        lib.pops_set_option(b"knn_fused_prepass", 1)
