@@ -54,6 +54,13 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, int a, int b, int c
                : "memory");
 }
 
+// 16 bytes into a peer CTA's shared memory, completing on THAT CTA's mbarrier (both addresses shared::cluster)
+__device__ __forceinline__ void st_async_v4(uint32_t addr, int a, int b, int c, int d, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(mbar)
+               : "memory");
+}
+
 // warp arg-max with first-index tie break.  Returns true in the winning lane.
 __device__ __forceinline__ bool warp_argmax(int key, int idx, int* wkey, int* widx) {
   const int mk = __reduce_max_sync(0xffffffffu, key);
@@ -68,9 +75,14 @@ template <int PT>
 __global__ void __launch_bounds__(kFps3Threads, 1)
 fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ lengths,
               const int64_t* __restrict__ Ks, const int64_t* __restrict__ start_idxs, int P,
-              int max_K, int C, int64_t* __restrict__ out) {
+              int max_K, int C, int push, int64_t* __restrict__ out) {
   __shared__ __align__(16) FpsSlot wslots[2][kFps3Warps];  // per-warp winners, double buffered
-  __shared__ __align__(16) FpsSlot cslots[2][16];         // per-CTA winners of the cluster
+  // winners of the cluster, double buffered: one per CTA (push = 0) or one per warp of every CTA (push = 1)
+  __shared__ __align__(16) FpsSlot cslots[2][16 * kFps3Warps];
+  __shared__ __align__(8) uint64_t bars[2];  // push = 1: "all slots of this parity have landed"
+  // push = 1: the CTA's points again, [3][PT * threads]: the winner's coordinates are read by index instead
+  // of being selected out of the owning lane's registers (3 x PT selects per iteration)
+  extern __shared__ __align__(16) float spts[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (C > 1) ? static_cast<int>(cluster_ctarank()) : 0;
@@ -91,22 +103,40 @@ fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ leng
   last = min(max(last, 0), L - 1);
 
   // point i of this thread has index  i*stride + base  (indices ascend with i)
-  const int stride = C * kFps3Threads;
+  const int stride = C * kFps3Threads;  // a power of two
+  const int lstride = 31 - __clz(stride);
   const int base = rank * kFps3Threads + tid;
+  // coordinates are kept NEGATED: last - p = last + (-p) exactly, and the packed add takes no negation
   float x[PT], y[PT], z[PT], mind[PT];
 #pragma unroll
   for (int i = 0; i < PT; ++i) {
     const int p = i * stride + base;
     const bool v = p < L;
-    x[i] = v ? pts[static_cast<size_t>(p) * 3 + 0] : 0.0f;
-    y[i] = v ? pts[static_cast<size_t>(p) * 3 + 1] : 0.0f;
-    z[i] = v ? pts[static_cast<size_t>(p) * 3 + 2] : 0.0f;
+    const float vx = v ? pts[static_cast<size_t>(p) * 3 + 0] : 0.0f;
+    const float vy = v ? pts[static_cast<size_t>(p) * 3 + 1] : 0.0f;
+    const float vz = v ? pts[static_cast<size_t>(p) * 3 + 2] : 0.0f;
+    x[i] = -vx; y[i] = -vy; z[i] = -vz;
     mind[i] = v ? FLT_MAX : -1.0f;  // -1: never the maximum, min() keeps it
+    if (C > 1 && push) {
+      spts[i * kFps3Threads + tid] = vx;
+      spts[(PT + i) * kFps3Threads + tid] = vy;
+      spts[(2 * PT + i) * kFps3Threads + tid] = vz;
+    }
   }
   float lx = pts[static_cast<size_t>(last) * 3 + 0];
   float ly = pts[static_cast<size_t>(last) * 3 + 1];
   float lz = pts[static_cast<size_t>(last) * 3 + 2];
 
+  const uint32_t slot_bytes = static_cast<uint32_t>(C) * kFps3Warps * 32u;  // what one iteration delivers to a CTA
+  if (C > 1 && push) {
+    if (tid == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      mbar_fence_init();
+      mbar_arrive_expect_tx(&bars[1], slot_bytes);             // iteration 1
+      if (kn > 2) mbar_arrive_expect_tx(&bars[0], slot_bytes);  // iteration 2
+    }
+  }
   if (C > 1) cluster_barrier();  // every CTA of the cluster is running before the first remote store
   for (int k = 1; k < kn; ++k) {
     const int par = k & 1;
@@ -117,9 +147,9 @@ fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ leng
       for (int i = 0; i < PT; i += 2) {
         const int i1 = (i + 1 < PT) ? i + 1 : i;
         // packed subtract / multiply (IEEE, unfused), scalar adds (ptxas would fuse mul2+add2)
-        const float2 dx = __fadd2_rn(make_float2(lx, lx), make_float2(-x[i], -x[i1]));
-        const float2 dy = __fadd2_rn(make_float2(ly, ly), make_float2(-y[i], -y[i1]));
-        const float2 dz = __fadd2_rn(make_float2(lz, lz), make_float2(-z[i], -z[i1]));
+        const float2 dx = __fadd2_rn(make_float2(lx, lx), make_float2(x[i], x[i1]));
+        const float2 dy = __fadd2_rn(make_float2(ly, ly), make_float2(y[i], y[i1]));
+        const float2 dz = __fadd2_rn(make_float2(lz, lz), make_float2(z[i], z[i1]));
         const float2 xx = __fmul2_rn(dx, dx), yy = __fmul2_rn(dy, dy), zz = __fmul2_rn(dz, dz);
         const float d0 = __fadd_rn(__fadd_rn(xx.x, yy.x), zz.x);
         const float d1 = __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y);
@@ -128,7 +158,7 @@ fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ leng
         best = fmaxf(best, fmaxf(mind[i], mind[i1]));
       }
     } else {
-      const float dx = __fsub_rn(lx, x[0]), dy = __fsub_rn(ly, y[0]), dz = __fsub_rn(lz, z[0]);
+      const float dx = __fadd_rn(lx, x[0]), dy = __fadd_rn(ly, y[0]), dz = __fadd_rn(lz, z[0]);
       const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
       mind[0] = fminf(mind[0], d);
       best = mind[0];
@@ -144,13 +174,51 @@ fps_d3_kernel(const float* __restrict__ points, const int64_t* __restrict__ leng
       cand = ci * stride + base;
     }
     const int widx = __reduce_min_sync(0xffffffffu, cand);
+    if (C > 1 && push) {
+      // One-sided exchange, no CTA or cluster barrier: every WARP sends its winner to every CTA of the
+      // cluster (lanes 0..15: first half of the slot to CTA `lane`, lanes 16..31: second half), each
+      // store completing 16 bytes on the receiver's mbarrier; a CTA waits on its own mbarrier only.
+      // Slot reuse is safe without further synchronisation: a peer sends iteration k+2 only after it
+      // has received iteration k+1 from every warp here, and a warp sends k+1 after it has read k.
+      // the warp's winner is one of this CTA's points: index -> (slot i, thread) -> shared-memory copy
+      const int wi = widx >> lstride, wt = (widx & (stride - 1)) - rank * kFps3Threads;
+      const float bx = spts[wi * kFps3Threads + wt];
+      const float by = spts[(PT + wi) * kFps3Threads + wt];
+      const float bz = spts[(2 * PT + wi) * kFps3Threads + wt];
+      const int dst = lane & 15;
+      if (dst < C) {
+        const uint32_t rs = map_to_cta(smem_u32(&cslots[par][rank * kFps3Warps + warp]), static_cast<uint32_t>(dst));
+        const uint32_t rb = map_to_cta(smem_u32(&bars[par]), static_cast<uint32_t>(dst));
+        if (lane < 16) st_async_v4(rs, wkey, widx, __float_as_int(bx), __float_as_int(by), rb);
+        else st_async_v4(rs + 16, __float_as_int(bz), 0, 0, 0, rb);
+      }
+      mbar_wait(&bars[par], static_cast<uint32_t>((k - 1) >> 1) & 1u);
+      if (tid == 0 && k + 2 < kn) mbar_arrive_expect_tx(&bars[par], slot_bytes);  // arm this parity for iteration k + 2
+      const int nslots = C * kFps3Warps;
+      int bk = static_cast<int>(0x80000000u), bi = 0x7fffffff, bs = 0;
+#pragma unroll
+      for (int u = 0; u < (16 * kFps3Warps) / 32; ++u) {
+        const int sl = lane + u * 32;
+        if (sl < nslots) {
+          const int2 ki = *reinterpret_cast<const int2*>(&cslots[par][sl]);
+          if (ki.x > bk || (ki.x == bk && ki.y < bi)) { bk = ki.x; bi = ki.y; bs = sl; }
+        }
+      }
+      const int ck = __reduce_max_sync(0xffffffffu, bk);
+      const int cidx = __reduce_min_sync(0xffffffffu, bk == ck ? bi : 0x7fffffff);
+      const int wl = __ffs(__ballot_sync(0xffffffffu, bk == ck && bi == cidx)) - 1;
+      const int ws = __shfl_sync(0xffffffffu, bs, wl);
+      lx = cslots[par][ws].x; ly = cslots[par][ws].y; lz = cslots[par][ws].z;
+      if (rank == 0 && tid == 0) o[k] = cidx;
+      continue;
+    }
     if (cand == widx) {  // exactly one lane (indices are unique)
       float bx = x[0], by = y[0], bz = z[0];
 #pragma unroll
       for (int i = 1; i < PT; ++i)
         if (ci == i) { bx = x[i]; by = y[i]; bz = z[i]; }
       FpsSlot s;
-      s.key = wkey; s.idx = widx; s.x = bx; s.y = by; s.z = bz; s.pad0 = s.pad1 = s.pad2 = 0;
+      s.key = wkey; s.idx = widx; s.x = -bx; s.y = -by; s.z = -bz; s.pad0 = s.pad1 = s.pad2 = 0;
       wslots[par][warp] = s;
     }
     __syncthreads();
@@ -259,7 +327,10 @@ int launch_fps_d3(const float* points, const int64_t* lengths, const int64_t* K,
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(N) * C);
   cfg.blockDim = dim3(kFps3Threads);
-  cfg.dynamicSmemBytes = 0;
+  const int push = get_option("fps_push", 1);  // 1: one-sided mbarrier exchange | 0: CTA winner + cluster barrier
+  const size_t smem = (C > 1 && push) ? size_t(3) * PT * kFps3Threads * 4 : 0;
+  POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -270,7 +341,7 @@ int launch_fps_d3(const float* points, const int64_t* lengths, const int64_t* K,
   cfg.numAttrs = 1;
   if (C > 8) POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   profile_begin("fps", st);
-  POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, points, lengths, K, start, P, max_K, C, out));
+  POPS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, points, lengths, K, start, P, max_K, C, push, out));
   profile_end("fps", st);
   POPS_LAUNCH_OK("fps_d3_kernel");
   return POPS_OK;
