@@ -21,6 +21,7 @@
 //   other D: exact distance on an AoS tile.
 #include <cfloat>
 
+#include "bq_prune.cuh"
 #include "common.cuh"
 
 namespace pops {
@@ -36,6 +37,7 @@ struct BqParams {
   float* dists;
   int P1, P2, D, K, TP;
   float radius2;
+  const unsigned* taken;  // scan kernel only: taken[n] != 0 -> bq_prune_kernel answers cloud n (nullptr: none)
 };
 
 // exact sequential scan, any D (AoS tile)
@@ -219,6 +221,7 @@ ball_query_scan_kernel(const BqParams prm) {
   const int L2 = static_cast<int>(L2l < 0 ? 0 : (L2l > prm.P2 ? prm.P2 : L2l));
   const float INF = __int_as_float(0x7f800000);
   const float r2 = prm.radius2;
+  if (prm.taken != nullptr && prm.taken[n] != 0u) return;  // answered by bq_prune_kernel
 
   float q[Q][3], a[Q][3], qq[Q], qmax[Q], T[Q];
   int count[Q];
@@ -343,7 +346,17 @@ ball_query_scan_kernel(const BqParams prm) {
 
 using namespace pops;
 
-extern "C" size_t pops_ball_query_workspace_bytes(int64_t, int64_t, int64_t, int64_t, int64_t) {
+namespace {
+// shapes on which a cloud may take the Hilbert-ordered search (bq_prune.cu); the choice per cloud is made
+// on the device (bq_cloud_spatial)
+bool bq_spatial_shape(int64_t P1, int64_t P2, int64_t D, int64_t K) {
+  return D == 3 && P1 >= 1024 && P2 >= kBqSpatialMinPoints && K <= kBqSpatialMaxK && get_option("bq_spatial", -1) != 0 &&
+         get_option("bq_scan", 1) != 0;
+}
+}  // namespace
+
+extern "C" size_t pops_ball_query_workspace_bytes(int64_t N, int64_t P1, int64_t P2, int64_t D, int64_t K) {
+  if (N > 0 && bq_spatial_shape(P1, P2, D, K)) return knn_order_workspace_bytes(N, P1, P2);
   return 256;
 }
 
@@ -351,8 +364,6 @@ extern "C" int pops_ball_query(const float* p1, const float* p2, const int64_t* 
                                const int64_t* lengths2, int64_t N, int64_t P1, int64_t P2,
                                int64_t D, int64_t K, float radius, int64_t* idx, float* dists,
                                void* workspace, size_t workspace_bytes, pops_stream_t stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   POPS_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && D >= 0 && K >= 0, "negative size");
   if (N == 0 || P1 == 0 || K == 0) return POPS_OK;
   POPS_CHECK_ARG(p1 && p2 && lengths1 && lengths2 && idx && dists, "null pointer argument");
@@ -362,6 +373,29 @@ extern "C" int pops_ball_query(const float* p1, const float* p2, const int64_t* 
   prm.p1 = p1; prm.p2 = p2; prm.len1 = lengths1; prm.len2 = lengths2; prm.idx = idx; prm.dists = dists;
   prm.P1 = int(P1); prm.P2 = int(P2); prm.D = int(D); prm.K = int(K);
   prm.radius2 = radius * radius;  // f32 product, ball_query_cpu.cpp:26
+  prm.taken = nullptr;
+  if (bq_spatial_shape(P1, P2, D, K)) {
+    POPS_CHECK_ARG(workspace && workspace_bytes >= knn_order_workspace_bytes(N, P1, P2), "ball_query: workspace too small");
+    KnnOrderBuffers ob;
+    knn_order_carve(workspace, N, P1, P2, &ob);
+    const bool self = (p1 == p2) && (lengths1 == lengths2) && (P1 == P2);
+    int rc = knn_order_prepass(p1, p2, lengths1, lengths2, int(N), int(P1), int(P2), self, ob, st);
+    if (rc != POPS_OK) return rc;
+    unsigned* flags = ob.keys_in;  // N words of the pre-pass scratch, free again once the order is built
+    profile_begin("ball_query", st);
+    rc = bq_prune_search(ob, p2, lengths1, lengths2, int(N), int(P1), int(P2), int(K), radius, prm.radius2,
+                         get_option("bq_spatial", -1), flags, idx, dists, st);
+    if (rc != POPS_OK) return rc;
+    prm.taken = flags;
+    prm.TP = kBqsTile;
+    const size_t smem = size_t(4 * kBqsTile + 16) * 4 + size_t(kBqsCap) * kBqsQ * kBqsThreads * 2;
+    POPS_CUDA_OK(cudaFuncSetAttribute(ball_query_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    dim3 sgrid(static_cast<unsigned>(ceil_div(P1, kBqsQ * kBqsThreads)), static_cast<unsigned>(N));
+    ball_query_scan_kernel<<<sgrid, kBqsThreads, smem, st>>>(prm);
+    profile_end("ball_query", st);
+    POPS_LAUNCH_OK("ball_query_scan_kernel");
+    return POPS_OK;
+  }
   dim3 grid(static_cast<unsigned>(ceil_div(P1, kBqThreads)), static_cast<unsigned>(N));
   if (D == 3 && P1 >= 1024 && get_option("bq_scan", 1)) {
     prm.TP = kBqsTile;
