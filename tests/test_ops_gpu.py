@@ -67,6 +67,95 @@ def test_ball_query_offsets(oracle):
         assert torch.equal(gi.cpu(), oi) and torch.equal(gd.cpu(), od)
 
 
+@pytest.fixture
+def bq_spatial_forced():
+    """Every finite cloud of an eligible shape takes the Hilbert-ordered search (bq_prune.cu)."""
+    from pytorch3d_pointops_b200 import _lib
+
+    lib = _lib.load()
+    lib.pops_set_option(b"bq_spatial", 1)
+    yield lib
+    lib.pops_set_option(b"bq_spatial", -1)
+
+
+def _bq_both(oracle, p1, p2, l1, l2, K, r, self_search=False):
+    from pytorch3d_pointops_b200 import _C
+
+    oi, od = oracle.ball_query_idx(p1, p2, l1, l2, K, r)
+    d1, g1 = p1.to(DEV), l1.to(DEV)
+    d2, g2 = (d1, g1) if self_search else (p2.to(DEV), l2.to(DEV))
+    gi, gd = _C.ball_query(d1, d2, g1, g2, K, r)
+    assert torch.equal(gi.cpu(), oi), (K, r)
+    assert torch.equal(gd.cpu(), od), (K, r)
+
+
+def test_ball_query_spatial_vs_oracle(oracle, bq_spatial_forced):
+    """bq_prune_kernel on what stresses it: sparse and crowded balls (hit columns cut back to K many
+    times), K = 1 .. 64, ragged / empty / tiny clouds, p1 != p2 with queries outside the cloud's box,
+    duplicated points, a flat cloud, clouds far from the origin (filter margin), and the per-cloud
+    dispatch leaving non-finite clouds to the exact scan."""
+    gen = torch.Generator().manual_seed(77)
+    for N, P1, P2, K, r, selfk in [(3, 2500, 2500, 32, 0.1, True), (2, 1024, 6000, 64, 0.15, False),
+                                   (2, 3000, 2048, 1, 0.05, False), (2, 4000, 4000, 16, 0.4, True),
+                                   (1, 1100, 9000, 5, 0.03, False), (2, 2100, 2100, 64, 1.5, True)]:
+        p2 = torch.rand(N, P2, 3, generator=gen)
+        p2[:, : P2 // 8] = p2[:, P2 // 8 : 2 * (P2 // 8)]  # duplicated points: equal distances, equal codes
+        p2[-1, :, 1] = 0.5                                  # a flat cloud
+        l2 = torch.randint(P2 // 2, P2 + 1, (N,), generator=gen)
+        if selfk:
+            p1, l1 = p2, l2
+        else:
+            p1 = torch.rand(N, P1, 3, generator=gen) * 1.4 - 0.2
+            l1 = torch.randint(0, P1 + 1, (N,), generator=gen)
+            l1[0] = P1
+            if N > 1:
+                l2[1] = 0  # nothing to find
+        _bq_both(oracle, p1, p2, l1, l2, K, r, selfk)
+    # offsets and scales: the expanded-form filter must keep every true hit
+    for off, scale in ((1000.0, 1.0), (0.0, 1e-6), (-3e4, 10.0)):
+        p = (torch.rand(2, 3000, 3, generator=gen) * scale + off).contiguous()
+        L = torch.tensor([3000, 2222])
+        _bq_both(oracle, p, p, L, L, 16, 0.12 * scale, True)
+    # one cloud non-finite, one huge: both answered by the exact scan, the others by the ordered search
+    p = torch.rand(4, 2600, 3, generator=gen)
+    p[1, 7, 2] = float("nan")
+    p[2, :, :] *= 3e19
+    L = torch.tensor([2600, 2600, 2600, 2000])
+    _bq_both(oracle, p, p, L, L, 8, 0.1, True)
+
+
+def test_ball_query_spatial_ties_on_the_radius(oracle, bq_spatial_forced):
+    """Integer-grid cloud with the radius on exact inter-point distances: strict '<' on fl(r * r), with
+    block-box lower bounds equal to r^2 (a block at exactly the radius holds no hit), many equal distances."""
+    ax = torch.arange(14, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3).contiguous()  # 2744 points
+    perm = torch.randperm(grid.shape[1], generator=torch.Generator().manual_seed(3))
+    grid = grid[:, perm].contiguous()
+    L = torch.tensor([grid.shape[1]])
+    for r in (1.0, 2.0, 3.0, 2.2360679):
+        for K in (7, 33, 64):
+            _bq_both(oracle, grid, grid, L, L, K, r, True)
+
+
+def test_ball_query_auto_dispatch_mixed_batch(oracle):
+    """Default dispatch on a batch whose clouds differ: a sparse cloud (ordered search), a crowded one and a
+    short one (index scan) in one call; each row equals the oracle's whichever kernel produced it."""
+    gen = torch.Generator().manual_seed(5)
+    p = torch.rand(3, 6000, 3, generator=gen)
+    p[1] = p[1] * 0.05 + 0.4  # 8000x denser: every ball is crowded
+    L = torch.tensor([6000, 6000, 1500])
+    _bq_both(oracle, p, p, L, L, 32, 0.04, True)
+
+
+@pytest.mark.parametrize("P2", [70000])
+def test_ball_query_spatial_wide_indices(oracle, bq_spatial_forced, P2):
+    """Clouds beyond 65536 points keep 32-bit hit indices."""
+    gen = torch.Generator().manual_seed(11)
+    p2 = torch.rand(1, P2, 3, generator=gen)
+    p1 = p2[:, -1500:].contiguous()
+    _bq_both(oracle, p1, p2, torch.tensor([1500]), torch.tensor([P2]), 24, 0.03)
+
+
 # ------------------------------------------------------------------ farthest point sampling
 def test_fps_golden(golden):
     from pytorch3d_pointops_b200 import _C
