@@ -109,6 +109,73 @@ __device__ __forceinline__ void warp_sort_u32(unsigned (&v)[NPL], int lane) {
   }
 }
 
+// Same network on two independent sets at once: set A in the low halves, set B in the high halves of the
+// registers (VIMNMX.U16x2: one instruction takes both minima or both maxima).
+template <int NPL>
+__device__ __forceinline__ void warp_sort_u16x2(unsigned (&v)[NPL], int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int N = 32 * NPL;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j >= NPL) {
+        const int lj = j / NPL;
+        const bool lower = (lane & lj) == 0;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const unsigned o = __shfl_xor_sync(FULL, v[r], lj);
+          const bool up = ((lane * NPL + r) & k) == 0;
+          v[r] = (up == lower) ? __vminu2(v[r], o) : __vmaxu2(v[r], o);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const int p = r ^ j;
+          if (p > r) {
+            const bool up = ((lane * NPL + r) & k) == 0;
+            const unsigned lo = __vminu2(v[r], v[p]), hi = __vmaxu2(v[r], v[p]);
+            v[r] = up ? lo : hi;
+            v[p] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Warp-wide, 16-bit indices: sort the columns of TWO queries in one pass of the network.
+template <int NPL>
+__device__ __forceinline__ void sort_column_pair(unsigned short* ca, int na, unsigned short* cb, int nb, int keep,
+                                                 int lane) {
+  unsigned v[NPL];
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    const int e = lane * NPL + r;
+    const unsigned a = e < na ? static_cast<unsigned>(ca[e]) : 0xFFFFu;  // (a real index 65535 ties with the padding:
+    const unsigned b = e < nb ? static_cast<unsigned>(cb[e]) : 0xFFFFu;  //  equal values, either order is the same)
+    v[r] = a | (b << 16);
+  }
+  __syncwarp();
+  warp_sort_u16x2<NPL>(v, lane);
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    const int e = lane * NPL + r;
+    if (e < na && e < keep) ca[e] = static_cast<unsigned short>(v[r] & 0xFFFFu);
+    if (e < nb && e < keep) cb[e] = static_cast<unsigned short>(v[r] >> 16);
+  }
+  __syncwarp();
+}
+
+__device__ __noinline__ void sort_column_pair_any(unsigned short* ca, int na, unsigned short* cb, int nb, int keep,
+                                                  int lane) {
+  const int n = max(na, nb);
+  if (n <= 1) return;
+  if (n <= 32) sort_column_pair<1>(ca, na, cb, nb, keep, lane);
+  else if (n <= 64) sort_column_pair<2>(ca, na, cb, nb, keep, lane);
+  else sort_column_pair<4>(ca, na, cb, nb, keep, lane);
+}
+
 // Warp-wide: sort the n (<= 32 * NPL) hits of one column, write the smallest min(n, keep) back in
 // ascending order.
 template <int NPL, typename IDX>
@@ -385,9 +452,17 @@ bq_prune_kernel(const BqPruneParams prm) {
   }
 
   // ---- select: the warp sorts every query's column; the first min(hits, K) indices are the answer ----
-  for (int ql = 0; ql < 32; ++ql) {
-    const int nq = __shfl_sync(FULL, nhits, ql);
-    if (nq > 1) sort_column_any<IDX>(hits_warp + static_cast<size_t>(ql) * COLI, nq, K, lane);
+  if constexpr (sizeof(IDX) == 2) {  // two queries per pass of the network (packed 16-bit minima / maxima)
+    for (int ql = 0; ql < 32; ql += 2) {
+      const int na = __shfl_sync(FULL, nhits, ql), nb = __shfl_sync(FULL, nhits, ql + 1);
+      sort_column_pair_any(reinterpret_cast<unsigned short*>(hits_warp) + static_cast<size_t>(ql) * COLI, na,
+                           reinterpret_cast<unsigned short*>(hits_warp) + static_cast<size_t>(ql + 1) * COLI, nb, K, lane);
+    }
+  } else {
+    for (int ql = 0; ql < 32; ++ql) {
+      const int nq = __shfl_sync(FULL, nhits, ql);
+      if (nq > 1) sort_column_any<IDX>(hits_warp + static_cast<size_t>(ql) * COLI, nq, K, lane);
+    }
   }
   __syncwarp();
 
