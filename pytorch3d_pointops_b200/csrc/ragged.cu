@@ -19,6 +19,8 @@ namespace pops {
 // segment start in floats), the source with 4-byte loads (its alignment differs from the
 // destination's; the four loads of a chunk hit the same L1 lines).  Every destination float is
 // written exactly once, zero padding included.
+constexpr int kCopyUnroll = 4;
+
 __device__ __forceinline__ void store_chunk(float* __restrict__ dst_seg, int64_t f0, int64_t F, const float (&v)[4]) {
   if (f0 >= 0 && f0 + 4 <= F) {
     *reinterpret_cast<float4*>(dst_seg + f0) = make_float4(v[0], v[1], v[2], v[3]);
@@ -47,6 +49,8 @@ packed_to_padded_kernel(const float* __restrict__ packed, const int64_t* __restr
     const float* src = packed + start * D;
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
     const int64_t nchunks = (F + a + 3) >> 2;
+    // (one chunk per thread: unrolling four, as padded_to_packed_kernel does, measured SLOWER here -- 108 vs
+    //  96 us on 64 clouds x 65536 rows x 16 floats, 26.6 vs 24.6 us at D = 3)
     for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks;
          c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
       const int64_t f0 = 4 * c - a;
@@ -80,16 +84,25 @@ padded_to_packed_kernel(const float* __restrict__ padded, const int64_t* __restr
     const float* src = padded + static_cast<int64_t>(b) * max_size * D;
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
     const int64_t nchunks = (F + a + 3) >> 2;
-    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks;
-         c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-      const int64_t f0 = 4 * c - a;
-      float v[4];
+    // kCopyUnroll chunks per thread and trip, a block apart (coalesced): all 16 loads are requested before
+    // the first store (64 clouds x 65536 rows: D = 3 25.6 -> 22.5 us, D = 16 100 -> 80 us)
+    for (int64_t c0 = static_cast<int64_t>(blockIdx.x) * blockDim.x * kCopyUnroll + threadIdx.x; c0 < nchunks;
+         c0 += static_cast<int64_t>(gridDim.x) * blockDim.x * kCopyUnroll) {
+      float v[kCopyUnroll][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int64_t f = f0 + e - lead;
-        v[e] = (f >= 0 && f < live) ? __ldg(src + f) : 0.0f;
+      for (int k = 0; k < kCopyUnroll; ++k) {
+        const int64_t f0 = 4 * (c0 + k * blockDim.x) - a;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t f = f0 + e - lead;
+          v[k][e] = (f >= 0 && f < live) ? __ldg(src + f) : 0.0f;
+        }
       }
-      store_chunk(dst, f0, F, v);
+#pragma unroll
+      for (int k = 0; k < kCopyUnroll; ++k) {
+        const int64_t c = c0 + k * blockDim.x;
+        if (c < nchunks) store_chunk(dst, 4 * c - a, F, v[k]);
+      }
     }
   }
 }
@@ -257,6 +270,67 @@ gather_rows3_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
   }
 }
 
+// U = 3, a cloud that fits shared memory (M * 12 bytes <= ~220 KB: 16384-point clouds), many more gathered
+// rows than points: the CTA copies ITS cloud into shared memory once (coalesced 16-byte loads, L2 hits
+// after the first CTA of the cloud) and every source row is then a shared-memory read.  What is left
+// for the memory system is the stream itself -- indices in (8 B per row), rows out (12 B per row) -- so
+// the kernel runs at the HBM rate instead of the L1/L2 sector-lookup rate of gather_rows3_kernel.
+// grid (ctas per cloud, N), 1024 threads, one CTA per SM; same row ownership (4 consecutive rows per
+// thread: two 16-byte index loads, three 16-byte stores) and the same masking as gather_rows3_kernel.
+constexpr int kGatherSmemThreads = 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(kGatherSmemThreads, 1)
+gather_rows3_smem_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx,
+                         const int64_t* __restrict__ lengths, unsigned LK, unsigned K, int M, int N,
+                         float* __restrict__ out, int32_t* __restrict__ oob) {
+  extern __shared__ __align__(16) float cloud[];  // [M][3]
+  const unsigned quads = LK >> 2;
+  const int n = blockIdx.y;
+  float* dst = out + static_cast<int64_t>(n) * LK * 3;
+  const int64_t* idx_n = idx + static_cast<int64_t>(n) * LK;
+  const float* x_n = x + static_cast<int64_t>(n) * M * 3;
+  {
+    const int nf4 = (M * 3) >> 2;  // (M * 3) % 4 == 0 and x_n 16-byte aligned: host-checked
+    const float4* src = reinterpret_cast<const float4*>(x_n);
+    float4* d4 = reinterpret_cast<float4*>(cloud);
+    for (int i = threadIdx.x; i < nf4; i += kGatherSmemThreads) d4[i] = __ldg(src + i);
+  }
+  unsigned klim = K;
+  if (MODE == POPS_GATHER_KNN && lengths != nullptr) {
+    const int64_t len = lengths[n];
+    klim = len < 0 ? 0u : (len < static_cast<int64_t>(K) ? static_cast<unsigned>(len) : K);
+  }
+  __syncthreads();
+  for (unsigned t = blockIdx.x * kGatherSmemThreads + threadIdx.x; t < quads; t += gridDim.x * kGatherSmemThreads) {
+    const unsigned r0 = t << 2;
+    const longlong2 ja = __ldcs(reinterpret_cast<const longlong2*>(idx_n + r0));
+    const longlong2 jb = __ldcs(reinterpret_cast<const longlong2*>(idx_n + r0 + 2));
+    const long long j[4] = {ja.x, ja.y, jb.x, jb.y};
+    bool bad = false;
+    float v[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bool take = j[i] >= 0 && j[i] < M;
+      if (MODE == POPS_GATHER_KNN) {
+        const bool live = klim == K || ((r0 + i) % K) < klim;
+        bad = bad || (live && !take);
+        take = take && live;
+      }
+      const float* row = cloud + (take ? static_cast<int>(j[i]) : 0) * 3;
+      const float a = row[0], b = row[1], c = row[2];
+      v[3 * i + 0] = take ? a : 0.0f;
+      v[3 * i + 1] = take ? b : 0.0f;
+      v[3 * i + 2] = take ? c : 0.0f;
+    }
+    if (MODE == POPS_GATHER_KNN && bad && oob != nullptr) *oob = 1;
+    float4* o = reinterpret_cast<float4*>(dst + static_cast<int64_t>(r0) * 3);
+    __stcs(o, make_float4(v[0], v[1], v[2], v[3]));
+    __stcs(o + 1, make_float4(v[4], v[5], v[6], v[7]));
+    __stcs(o + 2, make_float4(v[8], v[9], v[10], v[11]));
+  }
+}
+
 template <int MODE>
 __global__ void gather_backward_kernel(const float* __restrict__ grad_out,
                                        const int64_t* __restrict__ idx,
@@ -388,7 +462,7 @@ extern "C" int pops_padded_to_packed(const float* padded, const int64_t* first_i
   // a cloud's packed segment is at most num_inputs rows; size x for the padded capacity (the usual case)
   // and let threads loop when first_idxs hands one cloud more rows than that
   profile_begin("padded_to_packed", st);
-  padded_to_packed_kernel<<<segment_grid(ceil_div(std::min(max_size, num_inputs) * D + 3, 4), B, 256), 256, 0, st>>>(
+  padded_to_packed_kernel<<<segment_grid(ceil_div(ceil_div(std::min(max_size, num_inputs) * D + 3, 4) + 1, kCopyUnroll), B, 256), 256, 0, st>>>(
       padded, first_idxs, num_inputs, int(B), max_size, int(D), packed);
   profile_end("padded_to_packed", st);
   POPS_LAUNCH_OK("padded_to_packed_kernel");
@@ -418,6 +492,22 @@ extern "C" int pops_gather(const float* x, const int64_t* idx, const int64_t* le
   profile_begin("gather", st);
   if (U == 3 && (L * K) % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && reinterpret_cast<uintptr_t>(idx) % 16 == 0 &&
       reinterpret_cast<uintptr_t>(x) % 8 == 0 && get_option("gather_rows3", 1) != 0) {
+    // clouds that fit shared memory and are gathered from many times over: stage the cloud once per CTA
+    const size_t cloud_bytes = size_t(M) * 12;
+    if (cloud_bytes <= 220 * 1024 && (M * 3) % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && L * K >= 4 * M &&
+        N <= 65535 && get_option("gather_smem", 1) != 0) {
+      const int per_cloud = int(std::max<int64_t>(1, std::min<int64_t>(num_sms() / N, ceil_div(L * K / 4, kGatherSmemThreads))));
+      const dim3 gs(static_cast<unsigned>(per_cloud), static_cast<unsigned>(N));
+      auto k1 = gather_rows3_smem_kernel<POPS_GATHER_KNN>;
+      auto k2 = gather_rows3_smem_kernel<POPS_GATHER_MASKED>;
+      auto kern = mode == POPS_GATHER_KNN ? k1 : k2;
+      POPS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cloud_bytes)));
+      kern<<<gs, kGatherSmemThreads, cloud_bytes, st>>>(x, idx, lengths, unsigned(L * K), unsigned(K), int(M), int(N), out,
+                                                        oob_flag);
+      profile_end("gather", st);
+      POPS_LAUNCH_OK("gather_rows3_smem_kernel");
+      return POPS_OK;
+    }
     const dim3 g3 = segment_grid(L * K / 4, N, 256);
     if (mode == POPS_GATHER_KNN)
       gather_rows3_kernel<POPS_GATHER_KNN><<<g3, 256, 0, st>>>(x, idx, lengths, unsigned(L * K), unsigned(K), int(M), int(N), out, oob_flag);
