@@ -88,16 +88,18 @@ __device__ __forceinline__ void sort_floats(float (&v)[TOTAL]) {
 // Merge one lane's `ns` survivor keys (column S, stride SSTRIDE) into its ascending K-list kept in
 // the OUTPUT arrays (od, oi); warp-converged, `ns_max` = the largest ns in the warp.  Few
 // survivors -> branch-free insertion network per survivor; many -> sort network + bitonic merge.
+// `fresh`: the lane's list is empty and its row not yet written -- nothing is read.
 // Returns min(dkt, the list's K-th distance) for lanes that merged, dkt otherwise.
 template <int KT, int SSTRIDE>
 __device__ __forceinline__ float knn_merge_global(const uint64_t* S, int ns, int ns_max, int K, float* od,
-                                                  int64_t* oi, float dkt) {
+                                                  int64_t* oi, float dkt, bool fresh = false) {
   constexpr int KR = KT;
   uint64_t Lr[KR];
   const bool mine = ns > 0;  // only lanes that hold survivors touch their list
+  // a fresh list reads as (+inf, 0xFFFFFFFF) in its K slots, the value an empty row used to be filled with
 #pragma unroll
-  for (int k = 0; k < KR; ++k) Lr[k] = kEmptyKey;
-  if (mine) {
+  for (int k = 0; k < KR; ++k) Lr[k] = (fresh && k < K) ? 0x7F800000FFFFFFFFull : kEmptyKey;
+  if (mine && !fresh) {
     if (KR >= 4 && (K & 3) == 0) {  // rows are 16-byte aligned: 128-bit loads
 #pragma unroll
       for (int k4 = 0; k4 < KR / 4; ++k4) {

@@ -390,32 +390,56 @@ __global__ void gather_p1_kernel(const float* __restrict__ p1, const int64_t* __
   qhome[static_cast<size_t>(n) * P1 + j] = home;
 }
 
-// One warp per block: min / max corner of its valid points.  Blocks with no valid point come out
-// as (+inf, -inf) and are never intersected.
-__global__ void box_kernel(const float* __restrict__ blocks, int nbox, float4* __restrict__ boxes) {
-  const int n = blockIdx.y;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= nbox) return;
-  const int lane = threadIdx.x & 31;
-  const float* base = blocks + (static_cast<size_t>(n) * nbox + b) * kBlockFloats;
+// Lanes hold the 32 points of half `h` of a block (lane = position in the half).  Stores the boxes of
+// the half's two runs of kSubPoints points into the block's sub-box area and folds the half into the
+// caller's running block box (bmn, bmx: per lane the box of its half-warp; the caller finishes with one
+// xor-16 exchange).  Runs without a valid point come out as (+inf, -inf).
+__device__ __forceinline__ void half_block_boxes(float x, float y, float z, bool valid, float* block_base, int h,
+                                                 int lane, bool store, float (&bmn)[3], float (&bmx)[3]) {
+  static_assert(kSubPoints == 16 && kBoxPoints == 64, "two sub-boxes per 32-lane half");
   const float INF = __int_as_float(0x7f800000);
-  float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
-  for (int i = lane; i < kBoxPoints; i += 32) {
-    if (__float_as_uint(base[4 * kBoxPoints + i]) == kNoPoint) continue;
+  float mn[3] = {valid ? x : INF, valid ? y : INF, valid ? z : INF};
+  float mx[3] = {valid ? x : -INF, valid ? y : -INF, valid ? z : -INF};
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float v = base[d * kBoxPoints + i];
-      mn[d] = fminf(mn[d], v);
-      mx[d] = fmaxf(mx[d], v);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
       mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
+  }
+  if (store && (lane & 15) == 0) {
+    float4* dst = reinterpret_cast<float4*>(block_base + kSubOff) + (h * 2 + (lane >> 4)) * 2;
+    dst[0] = make_float4(mn[0], mn[1], mn[2], 0.f);
+    dst[1] = make_float4(mx[0], mx[1], mx[2], 0.f);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    bmn[d] = fminf(bmn[d], mn[d]);
+    bmx[d] = fmaxf(bmx[d], mx[d]);
+  }
+}
+
+// One warp per block: min / max corner of its valid points (and of its runs of kSubPoints points, stored
+// behind the block's rows).  Blocks with no valid point come out as (+inf, -inf) and are never intersected.
+__global__ void box_kernel(float* __restrict__ blocks, int nbox, float4* __restrict__ boxes) {
+  const int n = blockIdx.y;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= nbox) return;
+  const int lane = threadIdx.x & 31;
+  float* base = blocks + (static_cast<size_t>(n) * nbox + b) * kBlockFloats;
+  const float INF = __int_as_float(0x7f800000);
+  float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+#pragma unroll
+  for (int h = 0; h < kBoxPoints / 32; ++h) {
+    const int i = h * 32 + lane;
+    const bool valid = __float_as_uint(base[4 * kBoxPoints + i]) != kNoPoint;
+    half_block_boxes(base[i], base[kBoxPoints + i], base[2 * kBoxPoints + i], valid, base, h, lane, true, mn, mx);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], 16));
+    mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], 16));
   }
   if (lane == 0) {
     float4* dst = boxes + (static_cast<size_t>(n) * nbox + b) * 2;
@@ -785,6 +809,8 @@ order_cluster_kernel(const ClusterOrderParams prm) {
   for (int bl = warp; bl < S / kBoxPoints; bl += kOcWarps) {
     float bmn[3] = {INF, INF, INF}, bmx[3] = {-INF, -INF, -INF};
     const int gb = r * (S / kBoxPoints) + bl;  // block of the cloud
+    const bool wr = blocks_role && gb < nbox;
+    float* bbase = blk.blocks + (static_cast<size_t>(n) * nbox + gb) * kBlockFloats;
 #pragma unroll
     for (int h = 0; h < kBoxPoints / 32; ++h) {
       const int q = bl * kBoxPoints + h * 32 + lane;
@@ -797,30 +823,26 @@ order_cluster_kernel(const ClusterOrderParams prm) {
         x = src[0]; y = src[1]; z = src[2];
         w = fmaf(z, z, fmaf(y, y, x * x));
         orig = o;
-        bmn[0] = fminf(bmn[0], x); bmn[1] = fminf(bmn[1], y); bmn[2] = fminf(bmn[2], z);
-        bmx[0] = fmaxf(bmx[0], x); bmx[1] = fmaxf(bmx[1], y); bmx[2] = fmaxf(bmx[2], z);
       }
-      if (blocks_role && gb < nbox) {
-        float* dst = blk.blocks + (static_cast<size_t>(n) * nbox + gb) * kBlockFloats + (h * 32 + lane);
+      if (wr) {
+        float* dst = bbase + (h * 32 + lane);
         dst[0] = x;
         dst[kBoxPoints] = y;
         dst[2 * kBoxPoints] = z;
         dst[3 * kBoxPoints] = w;
         dst[4 * kBoxPoints] = __uint_as_float(orig);
       }
+      if (blocks_role) half_block_boxes(x, y, z, s < L, bbase, h, lane, wr, bmn, bmx);
       if (query_role && s < P) {
         qry.qsorted[static_cast<size_t>(n) * P + s] = make_float4(x, y, z, __uint_as_float(o));
         if (prm.mode == 0) qry.qhome[static_cast<size_t>(n) * P + s] = static_cast<unsigned>(s);
       }
     }
-    if (blocks_role && gb < nbox) {
+    if (wr) {
 #pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          bmn[d] = fminf(bmn[d], __shfl_xor_sync(FULL, bmn[d], o2));
-          bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(FULL, bmx[d], o2));
-        }
+      for (int d = 0; d < 3; ++d) {
+        bmn[d] = fminf(bmn[d], __shfl_xor_sync(FULL, bmn[d], 16));
+        bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(FULL, bmx[d], 16));
       }
       if (lane == 0) {
         float4* dst = blk.boxes + (static_cast<size_t>(n) * nbox + gb) * 2;

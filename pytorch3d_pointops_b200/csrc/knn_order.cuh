@@ -8,7 +8,8 @@ namespace pops {
 struct KnnOrderBuffers {
   unsigned* maxabs_bits;  // [N]        max |coordinate| over p1 and p2 of the cloud (float bits)
   float* bbox;            // [N][6]     min xyz, max xyz of the valid p2 points
-  float* blocks;          // [N][nbox][5][kBoxPoints]  x, y, z, w=|p|^2, original index (u32 bits), curve order
+  float* blocks;          // [N][nbox][kBlockFloats]  rows x, y, z, w=|p|^2, original index (u32 bits) of kBoxPoints
+                          //   points in curve order, then the boxes of its kSubBoxes runs of kSubPoints points
   float4* qsorted;        // [N][P1]    x, y, z, original index (u32 bits), curve order
   unsigned* qhome;        // [N][P1]    position in the sorted p2 where the query's code would go
   float4* boxes;          // [N][nbox][2]  (min xyz, -), (max xyz, -) of every kBoxPoints sorted p2 points
@@ -23,7 +24,12 @@ struct KnnOrderBuffers {
 
 constexpr unsigned kNoPoint = 0xFFFFFFFFu;  // "original index" of padding entries
 constexpr int kBoxPoints = 64;               // sorted p2 points per block (one bounding box each)
-constexpr int kBlockFloats = 5 * kBoxPoints; // x, y, z, w, index rows: 1280 bytes per block
+constexpr int kSubPoints = 16;               // consecutive sorted points per sub-box
+constexpr int kSubBoxes = kBoxPoints / kSubPoints;
+constexpr int kSubOff = 5 * kBoxPoints;      // float offset of the sub-boxes inside a block: [kSubBoxes][2] float4
+                                             //   (min xyz, -), (max xyz, -); runs without a valid point: (+inf, -inf)
+// x, y, z, w, index rows + sub-boxes: 1408 contiguous bytes per block (one TMA bulk copy, 128-byte aligned)
+constexpr int kBlockFloats = kSubOff + kSubBoxes * 8;
 
 // boxes per cloud, padded so that a warp can read 32 boxes of any 2048-point tile in bounds
 inline int64_t knn_order_num_boxes(int64_t P2) {

@@ -43,13 +43,14 @@ namespace {
 // inlined, called warp-converged and kept converged.  The groups are re-read from the sorted
 // blocks (L2), two per step for memory-level parallelism; every point gets the exact distance and
 // points with d <= dkt become 64-bit keys in the lane's survivor column; knn_merge_global folds
-// them into the list.  Returns the tightened bound of the K-th distance.
+// them into the list.  `fresh`: the query's list is still empty and its output row unwritten (the first
+// merge does not read it).  Returns (the tightened bound of the K-th distance, fresh afterwards as 0 / 1).
 template <int KT, int CSTRIDE, int SSTRIDE, typename CID>
-__device__ __noinline__ float prune_flush_one(const float* __restrict__ blocks_n, const CID* cand_col,
-                                              int c_end, uint64_t* S, float q0, float q1, float q2,
-                                              float dkt, int K, float* od, int64_t* oi) {
+__device__ __noinline__ float2 prune_flush_one(const float* __restrict__ blocks_n, const CID* cand_col,
+                                               int c_end, uint64_t* S, float q0, float q1, float q2,
+                                               float dkt, bool fresh, int K, float* od, int64_t* oi) {
   constexpr unsigned FULL = 0xffffffffu;
-  if (!__any_sync(FULL, c_end > 0)) return dkt;
+  if (!__any_sync(FULL, c_end > 0)) return make_float2(dkt, fresh ? 1.0f : 0.0f);
   int c = 0;
   for (;;) {
     if (!__any_sync(FULL, c < c_end)) break;
@@ -90,17 +91,25 @@ __device__ __noinline__ float prune_flush_one(const float* __restrict__ blocks_n
     }
     __syncwarp();
     const int ns_max = __reduce_max_sync(FULL, ns);
-    if (ns_max > 0) dkt = knn_merge_global<KT, SSTRIDE>(S, ns, ns_max, K, od, oi, dkt);
+    if (ns_max > 0) {
+      dkt = knn_merge_global<KT, SSTRIDE>(S, ns, ns_max, K, od, oi, dkt, fresh);
+      fresh = fresh && ns == 0;
+    }
     __syncwarp();
   }
-  return dkt;
+  return make_float2(dkt, fresh ? 1.0f : 0.0f);
 }
 
 template <int Q, int KT, int THREADS, typename CID>
 __global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : ((Q == 1 && KT == 1) ? 10 : 8))))
 knn_prune_kernel(const KnnPruneParams prm) {
   constexpr int QPB = Q * THREADS, S = kRingSlots;
-  constexpr bool REFINE = KT <= 4;  // per-query box test before a block is scanned
+  // which runs of kSubPoints points of a fetched block are scanned: every query tests the runs' boxes
+  // against its own bound (K <= 16), or the warp's query box against the warp's largest bound (K = 32: the
+  // extra tests cost more than the 30 % fewer runs give back, 2.36 vs 2.26 ms on the T shape; knn_subq
+  // forces the per-query test)
+  constexpr bool REFINE = KT <= 16;
+  static_assert(kChunk * kGroup == kSubPoints && kSubBoxes == 4, "one overflow-check chunk of the scan = one sub-box");
   // seed blocks: home and its two neighbours in curve order (>= 4 seed points per tournament subset for
   // K <= 16; with one query per thread 3 blocks beat 2 on the T shape: 0.914 vs 0.955 ms at K=16)
   constexpr int NSEED = KT <= 16 ? 3 : 4;
@@ -141,7 +150,9 @@ knn_prune_kernel(const KnnPruneParams prm) {
   // per-query state the dense loop never touches lives in shared memory, not in registers
   float* cold_qq = reinterpret_cast<float*>(smem + SM::cold_off);
   float* cold_dk = cold_qq + QPB;  // upper bound of the final K-th distance (-1: beyond lengths1)
-  unsigned* cold_row = reinterpret_cast<unsigned*>(cold_dk + QPB);  // output row = original query index
+  // output row = original query index; top bit: the list is still empty and the row unwritten
+  unsigned* cold_row = reinterpret_cast<unsigned*>(cold_dk + QPB);
+  constexpr unsigned kFresh = 0x80000000u;
 
   if (lane == 0) {
 #pragma unroll
@@ -184,16 +195,16 @@ knn_prune_kernel(const KnnPruneParams prm) {
     }
     cold_qq[slot] = s;
     cold_dk[slot] = valid ? INF : -1.0f;
-    cold_row[slot] = row;
+    cold_row[slot] = row | (valid ? kFresh : 0u);
     T[t] = valid ? FLT_MAX : -INF;
     cw[t] = cand_base + static_cast<uint32_t>(t) * (32u * CB);
-    // empty list = (+inf, 0xFFFFFFFF) in every slot; rows beyond lengths1 are final zeros
-    if (qi < prm.P1) {
+    // rows beyond lengths1 are final zeros; a valid query's row is first written by its first merge
+    if (qi < prm.P1 && !valid) {
       float* od = out_d + static_cast<size_t>(row) * K;
       int64_t* oi = out_idx + static_cast<size_t>(row) * K;
       for (int k = 0; k < K; ++k) {
-        od[k] = valid ? INF : 0.0f;
-        oi[k] = valid ? static_cast<int64_t>(0xFFFFFFFFll) : 0;
+        od[k] = 0.0f;
+        oi[k] = 0;
       }
     }
   }
@@ -270,7 +281,6 @@ knn_prune_kernel(const KnnPruneParams prm) {
   const float* blocks_n = prm.blocks + static_cast<size_t>(n) * prm.nbox * kBlockFloats;
   float slot_lb = 0.0f;  // lane s: bound of the block in slot s
   int slot_blk = 0;      // lane s: index of the block in slot s
-  float4 slot_lo = make_float4(0.f, 0.f, 0.f, 0.f), slot_hi = slot_lo;  // lane s: its bounding box
   int head = 0, tail = 0;  // blocks issued / scanned
   auto issue = [&](int b) {
     const int s = head & (S - 1);
@@ -284,10 +294,6 @@ knn_prune_kernel(const KnnPruneParams prm) {
     if (lane == s) {
       slot_lb = picked_lb;
       slot_blk = b;
-      if (REFINE) {
-        slot_lo = boxes_n[static_cast<size_t>(b) * 2];  // consumed when the block is scanned: latency hidden
-        slot_hi = boxes_n[static_cast<size_t>(b) * 2 + 1];
-      }
     }
     ++head;
     if (prm.stats && lane == 0) atomicAdd(prm.stats + 0, 1ull);
@@ -314,10 +320,13 @@ knn_prune_kernel(const KnnPruneParams prm) {
         const bool anyc = __any_sync(FULL, c_end > 0);
         if (lane == 0 && anyc) atomicAdd(prm.stats + 4, 1ull);
       }
-      const size_t row = cold_row[slot];
-      const float dkt = prune_flush_one<KT, QPB, THREADS, CID>(
+      const unsigned rw = cold_row[slot];
+      const size_t row = rw & ~kFresh;
+      const float2 fr = prune_flush_one<KT, QPB, THREADS, CID>(
           blocks_n, cand + slot, c_end, surv + tid, -0.5f * a[t][0], -0.5f * a[t][1], -0.5f * a[t][2],
-          cold_dk[slot], K, out_d + row * K, out_idx + row * K);
+          cold_dk[slot], (rw & kFresh) != 0u, K, out_d + row * K, out_idx + row * K);
+      const float dkt = fr.x;
+      if (fr.y == 0.0f) cold_row[slot] = static_cast<unsigned>(row);
       cold_dk[slot] = dkt;
       if (dkt >= 0.0f && dkt < INF) T[t] = __fadd_rn(__fsub_rn(dkt, cold_qq[slot]), E);
       dm = fmaxf(dm, dkt);
@@ -338,7 +347,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
 #pragma unroll
     for (int t = 0; t < Q; ++t) {
       const int slot = slot0 + t * 32;
-      const float U = seed_bound<KT>(ring4, nseed, -0.5f * a[t][0], -0.5f * a[t][1], -0.5f * a[t][2]);
+      const float U = seed_bound<KT>(ring4, nseed, a[t][0], a[t][1], a[t][2], cold_qq[slot], E);
       if (cold_dk[slot] >= 0.0f) {
         cold_dk[slot] = U;  // KT >= K distinct points lie within U
         if (U < INF) T[t] = __fadd_rn(__fsub_rn(U, cold_qq[slot]), E);
@@ -358,26 +367,37 @@ knn_prune_kernel(const KnnPruneParams prm) {
     if (tail == head) break;
     const int s = tail & (S - 1);
     mbar_wait(&bars[s], (tail / S) & 1);
-    bool wanted = __shfl_sync(FULL, slot_lb, s) <= dkmax;  // dkmax may have dropped since the fetch
-    // (small K only: the 6 extra registers per lane cost the K = 16 / 32 variants, which sit at their
-    //  register cap, more in spills than the 25 % fewer blocks give back: 1.28 vs 1.21 ms on the T shape)
-    if (REFINE && wanted && prm.prune) {
-      // per-query refinement: the warp-wide test used the box of ALL its queries against the LARGEST
-      // bound; scan only if some query's own bound reaches the block (same exact lower bound, with
-      // the query as a degenerate box)
-      float4 lo, hi;
-      lo.x = __shfl_sync(FULL, slot_lo.x, s); lo.y = __shfl_sync(FULL, slot_lo.y, s); lo.z = __shfl_sync(FULL, slot_lo.z, s);
-      hi.x = __shfl_sync(FULL, slot_hi.x, s); hi.y = __shfl_sync(FULL, slot_hi.y, s); hi.z = __shfl_sync(FULL, slot_hi.z, s);
-      bool need = false;
+    // dkmax may have dropped since the fetch; then the block's runs of kSubPoints points against their own
+    // boxes (behind the block's rows in the ring slot): bit j of `sub` = run j is scanned
+    unsigned sub = (__shfl_sync(FULL, slot_lb, s) <= dkmax) ? 0xFu : 0u;
+    if (sub && prm.prune) {
+      const float4* sb = ring4 + s * kBlockF4 + kSubOff / 4;
+      if (REFINE || prm.subq) {
+        // per query: the warp-wide test uses the box of ALL its queries against the LARGEST bound; a run is
+        // scanned only if some query's own bound reaches it (same exact lower bound, with the query as a
+        // degenerate box).  No state survives the test: K = 16 / 32 sit at their register cap.
+        sub = 0u;
 #pragma unroll
-      for (int t = 0; t < Q; ++t) {
-        const float qp[3] = {-0.5f * a[t][0], -0.5f * a[t][1], -0.5f * a[t][2]};
-        need = need || (box_lower_bound(lo, hi, qp, qp) <= cold_dk[slot0 + t * 32]);  // dk = -1 beyond lengths1
+        for (int j = 0; j < kSubBoxes; ++j) {
+          const float4 lo = sb[2 * j], hi = sb[2 * j + 1];
+          bool need = false;
+#pragma unroll
+          for (int t = 0; t < Q; ++t) {
+            const float qp[3] = {-0.5f * a[t][0], -0.5f * a[t][1], -0.5f * a[t][2]};
+            need = need || (box_lower_bound(lo, hi, qp, qp) <= cold_dk[slot0 + t * 32]);  // dk = -1 beyond lengths1
+          }
+          sub |= __any_sync(FULL, need) ? (1u << j) : 0u;
+        }
+      } else {
+        const float4 lo = sb[2 * (lane & 3)], hi = sb[2 * (lane & 3) + 1];
+        sub = __ballot_sync(FULL, box_lower_bound(lo, hi, wqlo, wqhi) <= dkmax) & 0xFu;
       }
-      wanted = __any_sync(FULL, need);
     }
-    if (wanted) {
-      if (prm.stats && lane == 0) atomicAdd(prm.stats + 1, 1ull);
+    if (sub) {
+      if (prm.stats && lane == 0) {
+        atomicAdd(prm.stats + 1, 1ull);
+        atomicAdd(prm.stats + 6, static_cast<unsigned long long>(__popc(sub)));
+      }
       const float4* tp = ring4 + s * kBlockF4;
       const unsigned gid0 = static_cast<unsigned>(__shfl_sync(FULL, slot_blk, s)) * kBlockGroups;
       // The flush is a real function call and must not sit inside the dense loop: the current and the
@@ -385,15 +405,15 @@ knn_prune_kernel(const KnnPruneParams prm) {
       // it on EVERY pass (r1 profile: three LDL per chunk, 9 % of all stall samples).  On overflow the
       // loop is left, the buffers are drained, and the scan resumes at the next group with its rows
       // re-read from shared memory.
-      int g = 0;
-      unsigned gid = gid0;
       do {
+        int g = (__ffs(sub) - 1) * kChunk;  // first run still to scan
+        unsigned gid = gid0 + static_cast<unsigned>(g);
         float4 Xc[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) Xc[r] = tp[r * kBlockGroups + g];
         bool over = false;
 #pragma unroll 1
-        for (; g < kBlockGroups && !over; g += kChunk) {
+        for (; g < kBlockGroups && !over && ((sub >> (g / kChunk)) & 1u); g += kChunk) {
 #pragma unroll
           for (int c = 0; c < kChunk; ++c) {
             // next group's rows (the last prefetch of a block reads the index row: in bounds, unused)
@@ -427,21 +447,35 @@ knn_prune_kernel(const KnnPruneParams prm) {
           for (int t = 1; t < Q; ++t) mx = max(mx, cw[t] - static_cast<uint32_t>(t) * (32u * CB));
           over = __any_sync(FULL, mx > cw_limit);
         }
+        sub &= ~((1u << (g / kChunk)) - 1u);  // runs below g are done or were skipped
         if (over) flush_all(true);
-      } while (g < kBlockGroups);
+      } while (sub);
     }
     ++tail;
   }
   flush_all(false);
 
-  // the lists ARE the outputs; only slots beyond lengths2 (K > lengths2) still hold the empty
-  // marker and become the reference's (0, 0) padding
+  // the lists ARE the outputs.  Every valid query has merged at least once (its seed points pass their
+  // own bound); should one not have, its row is the empty list.
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    const unsigned rw = cold_row[slot0 + t * 32];
+    if (rw & kFresh) {
+      const size_t row = rw & ~kFresh;
+      for (int k = 0; k < K; ++k) {
+        out_d[row * K + k] = INF;
+        out_idx[row * K + k] = static_cast<int64_t>(0xFFFFFFFFll);
+      }
+    }
+  }
+  // only slots beyond lengths2 (K > lengths2) still hold the empty marker and become the reference's
+  // (0, 0) padding
   if (L2 < K) {
 #pragma unroll
     for (int t = 0; t < Q; ++t) {
       const int slot = slot0 + t * 32;
       if (cold_dk[slot] < 0.0f) continue;
-      const size_t row = cold_row[slot];
+      const size_t row = cold_row[slot] & ~kFresh;
       for (int k = L2; k < K; ++k) {
         out_d[row * K + k] = 0.0f;
         out_idx[row * K + k] = 0;
@@ -491,6 +525,7 @@ int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64
   prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits; prm.idx = idx; prm.dists = dists;
   prm.P1 = P1; prm.P2 = P2; prm.K = K; prm.nbox = static_cast<int>(knn_order_num_boxes(P2));
   prm.prune = prune;
+  prm.subq = get_option("knn_subq", 0);  // 1: per-query sub-box test for every K (tuning aid; K <= 4 always)
   const int stats = get_option("knn_stats", 0);
   prm.stats = nullptr;
   if (stats) POPS_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&prm.stats), g_knn_stats));
@@ -502,7 +537,7 @@ int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64
 
 // development aid: read and reset the counters collected under POPS_KNN_STATS=1
 // [0] blocks fetched, [1] blocks scanned, [2] flush rounds, [3] buffered groups, [4] non-empty
-// per-slot flushes, [5] warps
+// per-slot flushes, [5] warps, [6] sub-boxes scanned
 }  // namespace pops
 
 extern "C" int pops_knn_debug_stats(unsigned long long* out8) {

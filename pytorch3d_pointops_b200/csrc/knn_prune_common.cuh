@@ -20,6 +20,7 @@ struct KnnPruneParams {
   float* dists;
   int P1, P2, K, nbox;
   int prune;  // 0: visit every block (brute force in the same order); measurement aid
+  int subq;   // 1: per-query sub-box test for every K
   unsigned long long* stats;  // development counters (POPS_KNN_STATS=1), else nullptr
 };
 
@@ -86,14 +87,18 @@ __device__ __forceinline__ void exact4(float q0, float q1, float q2, float4 X, f
   d4[3] = __fadd_rn(__fadd_rn(xx23.y, yy23.y), zz23.y);
 }
 
-// Seed bound of one query: exact distances to the `nseed` blocks at the start of the warp's ring;
-// minimum over each of NS interleaved subsets of the points (NS distinct points: the subsets are
-// disjoint), then the KT-th smallest of those minima.  KT distinct points lie within the result,
-// so it bounds the K-th distance (K <= KT) from above.  +inf when fewer than KT subsets hold a
-// valid point.  NS = 2 KT subsets of >= 4 points put the bound near the (1.1 KT)-th nearest seed
+// Seed bound of one query from the `nseed` blocks at the start of the warp's ring.  Every seed point
+// gets the EXPANDED form s = w - 2 q.p of the scan (3 FMA per point, a_d = -2 q_d); the minimum of s
+// over each of NS interleaved subsets of the points, then the KT-th smallest of those minima, U_s: KT
+// distinct points (the subsets are disjoint) have s <= U_s.  By the filter's error bound read the
+// other way (|s + qq - d_ref| plus the roundings of forming the sum stay below E), each of
+// them has a reference distance d_ref <= fl(fl(U_s + qq) + E), which therefore bounds the K-th
+// distance (K <= KT) from above.  +inf when fewer than KT subsets hold a valid point (padding entries
+// carry w = +inf).  K = 1 takes the exact distances.  NS = 2 KT subsets of >= 4 points put the bound near the (1.1 KT)-th nearest seed
 // point.  Not inlined: runs once per query.
 template <int KT, int SLOTF4 = kBlockF4>
-__device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q0, float q1, float q2) {
+__device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float a0, float a1, float a2, float qq,
+                                         float E) {
   constexpr int NS = KT == 1 ? 1 : (KT == 4 ? 16 : 2 * KT);
   constexpr int UG = NS >= 4 ? NS / 4 : 1;  // groups per unrolled step: subset index stays static
   static_assert(UG <= kBlockGroups, "a step stays inside one block");
@@ -101,6 +106,25 @@ __device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q
   float mins[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) mins[i] = INF;
+  if (KT == 1) {
+    // K = 1: the exact distance instead (no E floor under the bound: a self-search starts at U = 0, and a
+    // chamfer pair of near-identical clouds at its true, tiny nearest distance)
+    float m = INF;
+    for (int s = 0; s < nseed; ++s) {
+      const float4* tp = ring4 + s * SLOTF4;
+#pragma unroll 4
+      for (int g = 0; g < kBlockGroups; ++g) {
+        const float4 W = tp[3 * kBlockGroups + g];
+        float d4[4];
+        exact4(-0.5f * a0, -0.5f * a1, -0.5f * a2, tp[g], tp[kBlockGroups + g], tp[2 * kBlockGroups + g], d4);
+        const float w4[4] = {W.x, W.y, W.z, W.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m = fminf(m, (w4[i] == INF) ? INF : d4[i]);
+      }
+    }
+    return m;
+  }
+  const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2);
   for (int s = 0; s < nseed; ++s) {
     const float4* tp = ring4 + s * SLOTF4;  // SLOTF4: float4 between consecutive ring slots
 #pragma unroll 1
@@ -108,23 +132,28 @@ __device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q
 #pragma unroll
       for (int u = 0; u < UG; ++u) {
         const int g = g0 + u;
-        const float4 W = tp[3 * kBlockGroups + g];
-        float d4[4];
-        exact4(q0, q1, q2, tp[g], tp[kBlockGroups + g], tp[2 * kBlockGroups + g], d4);
-        const float w4[4] = {W.x, W.y, W.z, W.w};
+        const float4 X = tp[g], Y = tp[kBlockGroups + g], Z = tp[2 * kBlockGroups + g], W = tp[3 * kBlockGroups + g];
+        float2 s01 = make_float2(W.x, W.y), s23 = make_float2(W.z, W.w);
+        s01 = __ffma2_rn(A0, make_float2(X.x, X.y), s01);
+        s23 = __ffma2_rn(A0, make_float2(X.z, X.w), s23);
+        s01 = __ffma2_rn(A1, make_float2(Y.x, Y.y), s01);
+        s23 = __ffma2_rn(A1, make_float2(Y.z, Y.w), s23);
+        s01 = __ffma2_rn(A2, make_float2(Z.x, Z.y), s01);
+        s23 = __ffma2_rn(A2, make_float2(Z.z, Z.w), s23);
+        const float s4[4] = {s01.x, s01.y, s23.x, s23.y};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float dv = (w4[i] == INF) ? INF : d4[i];  // padding entries carry w = +inf
           float& m = mins[(u * 4 + i) % NS];
-          m = fminf(m, dv);
+          m = fminf(m, s4[i]);
         }
       }
     }
   }
-  if (NS == 1) return mins[0];
+  auto up = [&](float us) { return us < INF ? __fadd_rn(__fadd_rn(us, qq), E) : INF; };
+  if (NS == 1) return up(mins[0]);
   if (NS != 2 * KT) {  // KT = 4: 4th smallest of 16
     sort_floats<NS, 0, NS>(mins);
-    return mins[KT - 1];
+    return up(mins[KT - 1]);
   }
   // KT-th smallest of 2 KT values: sort both halves, then max_i min(A[i], B[KT-1-i])
   constexpr int H = NS / 2;
@@ -133,7 +162,7 @@ __device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float q
   float U = fminf(mins[0], mins[H + H - 1]);
 #pragma unroll
   for (int i = 1; i < H; ++i) U = fmaxf(U, fminf(mins[i], mins[H + H - 1 - i]));
-  return U;
+  return up(U);
 }
 
 }  // namespace
