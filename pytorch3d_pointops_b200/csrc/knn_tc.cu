@@ -54,7 +54,8 @@ constexpr int TC_KBLK = 32;      // floats per k-block: one 128-byte swizzle spa
 constexpr int TC_ABUF = 4;       // accumulator buffers (4 x 128 = all 512 TMEM columns)
 constexpr int TC_LIST = 32;      // the re-rank keeps the 32 smallest s of a query (K <= 16)
 constexpr int TC_GCAP = 128;     // candidates a (query, column half) can hold in global memory (≈55 used on C5)
-constexpr int TC_TOUR = 32;      // tournament minima per thread; threshold = their 16th smallest
+constexpr int TC_TOUR = 32;      // tournament minima per query row (TC_HALVES threads x TC_TSLOT); threshold = their 16th smallest
+constexpr int TC_TSLOT = 16;     // tournament slots per thread: slot i = minimum over columns 2i, 2i+1 of every 32-column chunk
 constexpr int TC_CAND = 24;      // candidate entries a thread stages in shared memory between flushes
 constexpr int TC_SUB = 8;        // columns between two staging-overflow checks
 constexpr int TC_HALVES = 2;      // epilogue warps per TMEM lane quarter: each takes half of a tile's columns
@@ -76,6 +77,7 @@ struct TcParams {
   int KB;                  // k-blocks = ceil(D / 32)
   int nstage;              // stages of the p2 ring
   int dbg;                 // development: 1 = never buffer a candidate (timing the MMA pipeline alone)
+  int seed_tiles;          // tiles of the seed pass (evaluated twice; the real pass starts with their threshold)
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -116,6 +118,13 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// Same arrival without release semantics: for "this TMEM buffer is drained", where the only thing the
+// waiter depends on is the completion of this warp's tcgen05.ld (tcgen05.wait::ld + fence::before_thread_sync
+// precede it).  A release at cluster scope would also wait for every shared / global store of the warp
+// (the candidate appends), which nobody on the other side reads.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {  // one warp of EACH CTA
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -344,15 +353,15 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   // Seed pass: the first tiles are evaluated twice -- first for the tournament only (no candidate
   // is staged), so that the real pass starts with a finite threshold instead of buffering the first
   // few hundred points of every query.  Sequence of tiles for all roles: 0..S-1, then 0..num_tiles-1.
-  const int S_seed = num_tiles >= 16 ? 4 : 0;
+  const int S_seed = num_tiles >= 4 * prm.seed_tiles ? prm.seed_tiles : 0;
   const int seq_tiles = S_seed + num_tiles;
 
   float* sA = reinterpret_cast<float*>(smem);                                  // KB x 16 KB
   float* sB = reinterpret_cast<float*>(smem + static_cast<size_t>(KB) * TC_STAGE_BYTES);  // NST x 16 KB
   unsigned char* rest = smem + static_cast<size_t>(KB + NST) * TC_STAGE_BYTES;
   uint2* cand = reinterpret_cast<uint2*>(rest);                                // TC_CAND x TC_CSTRIDE staged (s, j)
-  float* sX = reinterpret_cast<float*>(rest + size_t(TC_CAND) * TC_CSTRIDE * 8);  // TC_TOUR x TC_M: minima exchange
-  float* sW = sX + TC_TOUR * TC_M;                                             // per epilogue warp: 2 x TC_N/TC_HALVES norms
+  float* sX = reinterpret_cast<float*>(rest + size_t(TC_CAND) * TC_CSTRIDE * 8);  // TC_TSLOT x TC_M: minima exchange
+  float* sW = sX + TC_TSLOT * TC_M;                                             // per epilogue warp: 2 x TC_N/TC_HALVES norms
   float* sT = sW + 4 * TC_HALVES * 2 * (2 * TC_N / TC_HALVES);                 // TC_M tournament bounds
   uint64_t* bars = reinterpret_cast<uint64_t*>(sT + TC_M);
   uint64_t* full = bars;                       // [TC_MAX_STAGES]  TMA -> MMA
@@ -472,14 +481,15 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int qi = q_base + row;
     const float INF = __int_as_float(0x7f800000);
     constexpr int HC = TN / TC_HALVES;       // columns per half
-    static_assert(HC % 32 == 0 && TC_TOUR == 32, "column c of a chunk feeds tournament slot c");
+    static_assert(HC % 32 == 0 && TC_TSLOT == 16 && TC_TOUR == TC_HALVES * TC_TSLOT && TC_SUB == 8,
+                  "columns 2i, 2i+1 of a chunk feed tournament slot i; the two threads of a row hold 32 disjoint subsets");
     const bool live = qi < L1 && !(prm.dbg & 1);
     const size_t qrow = static_cast<size_t>(n) * prm.P1 + min(qi, prm.P1 - 1);
     const float E2 = 2.0f * tc_error_bound(prm.xq[static_cast<size_t>(n) * prm.P1pad + min(qi, prm.P1pad - 1)],
                                            __uint_as_float(prm.maxw_bits[n]), prm.D);
-    float mins[TC_TOUR];   // running minima of s over 32 disjoint subsets of this thread's columns
+    float mins[TC_TSLOT];  // running minima of s over 16 disjoint subsets of this thread's columns
 #pragma unroll
-    for (int i = 0; i < TC_TOUR; ++i) mins[i] = INF;
+    for (int i = 0; i < TC_TSLOT; ++i) mins[i] = INF;
     float T = live ? INF : -INF;   // append threshold; rows beyond lengths1 never buffer anything
     uint2* garr = prm.cands + (qrow * TC_HALVES + half) * TC_GCAP;
     unsigned gcount = 0;
@@ -510,17 +520,21 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_wait_parked(&tfull[b], (tt / ABUF) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(b * TN + half * HC);
+      // The accumulators of chunk c + 1 are requested as soon as chunk c's have been turned into s values
+      // (its registers are free then) and arrive while the hit tests and appends of chunk c run.
+      const int nchunk = (prm.dbg & 2) ? 0 : HC / 32;  // dbg 2: drain nothing (MMA / TMA pipeline alone)
+      uint32_t acc[32];
+      if (nchunk > 0) tmem_ld_x32(taddr, acc);
 #pragma unroll 1
-      for (int c = 0; c < ((prm.dbg & 2) ? 0 : HC / 32); ++c) {  // dbg 2: drain nothing (MMA / TMA pipeline alone)
-        uint32_t acc[32];
-        tmem_ld_x32(taddr + static_cast<uint32_t>(c * 32), acc);
+      for (int c = 0; c < nchunk; ++c) {
         tmem_ld_wait(acc);
         if (prm.dbg & 4) {  // dbg 4: read the accumulators, evaluate nothing
           if (acc[0] == 0x12345678u && acc[31] == 0x9abcdef0u) T = 0.0f;
+          if (c + 1 < nchunk) tmem_ld_x32(taddr + static_cast<uint32_t>((c + 1) * 32), acc);
           continue;
         }
         const uint32_t jc = static_cast<uint32_t>(t * TN + half * HC + c * 32);
-        // straight-line part first (32 independent columns: norms, s, tournament), hit tests after
+        // straight-line part first (32 independent columns: norms, s, pair minima, tournament), hit tests after
         float sv[32];
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -533,16 +547,17 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           sv[i4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(acc[i4 * 4 + 2]), w2);
           sv[i4 * 4 + 3] = fmaf(-2.0f, __uint_as_float(acc[i4 * 4 + 3]), w3);
         }
+        if (c + 1 < nchunk) tmem_ld_x32(taddr + static_cast<uint32_t>((c + 1) * 32), acc);
+        float m2[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mins[i] = fminf(mins[i], sv[i]);
+        for (int i = 0; i < 16; ++i) {
+          m2[i] = fminf(sv[2 * i], sv[2 * i + 1]);
+          mins[i] = fminf(mins[i], m2[i]);
+        }
         float m8[32 / TC_SUB];
 #pragma unroll
-        for (int sub = 0; sub < 32 / TC_SUB; ++sub) {
-          float m = fminf(sv[sub * TC_SUB], sv[sub * TC_SUB + 1]);
-#pragma unroll
-          for (int i = 2; i < TC_SUB; ++i) m = fminf(m, sv[sub * TC_SUB + i]);
-          m8[sub] = m;
-        }
+        for (int sub = 0; sub < 32 / TC_SUB; ++sub)
+          m8[sub] = fminf(fminf(m2[sub * 4], m2[sub * 4 + 1]), fminf(m2[sub * 4 + 2], m2[sub * 4 + 3]));
         // the append code is skipped unless some lane has a hit among the columns (never while seeding)
         if (!seeding && __any_sync(FULL, fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])) <= T)) {
 #pragma unroll
@@ -558,6 +573,9 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               }
             }
             if (__any_sync(FULL, cw > cw_limit)) {
+              // a real call: the accumulators in flight must have landed before their registers may be
+              // saved and restored around it
+              tmem_ld_wait(acc);
               gcount = tc_flush_stage(cand_col, static_cast<int>((cw - cand_base) / CSTRIDE), T, garr, gcount);
               cw = cand_base;
             }
@@ -568,12 +586,11 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(tempty_l + static_cast<uint32_t>(b * 8)); else mbar_arrive(&tempty[b]);
+        if (PAIR) mbar_arrive_cluster_relaxed(tempty_l + static_cast<uint32_t>(b * 8)); else mbar_arrive(&tempty[b]);
       }
       // refresh the threshold: after tiles 1, 2, 3, 4, 6, 8, 12, 16, ... and then every 16th.  The
-      // two threads of a row (one per column half) pool their minima slot by slot -- slot i then
-      // covers the union of both slot-i subsets, still 32 disjoint subsets of everything the row
-      // has seen -- and half 0 takes the 16th smallest of the pooled 32.
+      // two threads of a row (one per column half) hold 16 minima each over disjoint subsets of their
+      // columns; half 0 takes the 16th smallest of the 32.
       const int v = t + 1;
       const bool pow2 = (v & (v - 1)) == 0;
       const bool pow2x3 = (v % 3 == 0) && (((v / 3) & ((v / 3) - 1)) == 0);
@@ -581,14 +598,18 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (refresh) {
         if (half != 0) {
 #pragma unroll
-          for (int i = 0; i < TC_TOUR; ++i) sX[i * TC_M + row] = mins[i];
+          for (int i = 0; i < TC_TSLOT; ++i) sX[i * TC_M + row] = mins[i];
         }
         asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_HALVES) : "memory");
         if (half == 0) {
-          // 16th smallest of the 32 pooled minima: sort both halves, then max_i min(A[i], B[15-i])
+          // 16th smallest of the row's 32 minima (16 of each half's thread, 32 disjoint subsets of everything
+          // the row has seen): sort both halves, then max_i min(A[i], B[15-i])
           float tmp[TC_TOUR];
 #pragma unroll
-          for (int i = 0; i < TC_TOUR; ++i) tmp[i] = fminf(mins[i], sX[i * TC_M + row]);
+          for (int i = 0; i < TC_TSLOT; ++i) {
+            tmp[i] = mins[i];
+            tmp[TC_TSLOT + i] = sX[i * TC_M + row];
+          }
           sort_floats<16, 0, TC_TOUR>(tmp);
           sort_floats<16, 16, TC_TOUR>(tmp);
           float U = fminf(tmp[0], tmp[31]);
@@ -956,7 +977,7 @@ TcLayout tc_layout(int64_t N, int64_t P1, int64_t P2) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 inline size_t tc_smem_fixed(int KB) {
-  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_CSTRIDE * 8 + size_t(TC_TOUR) * TC_M * 4 + 4 * 2 * 2 * TC_N * 4 + TC_M * 4 +
+  return size_t(KB) * TC_STAGE_BYTES + size_t(TC_CAND) * TC_CSTRIDE * 8 + size_t(TC_TSLOT) * TC_M * 4 + 4 * 2 * 2 * TC_N * 4 + TC_M * 4 +
          (2 * TC_MAX_STAGES + 2 * TC_ABUF + 2) * 8 +
          1024 /* alignment */;
 }
@@ -1023,6 +1044,7 @@ int knn_tc_search(const float* p1, const float* p2, const int64_t* len1, const i
   prm.P1 = P1; prm.P2 = P2; prm.P2pad = l.P2pad; prm.P1pad = l.P1pad; prm.D = D;
   prm.KB = (D + TC_KBLK - 1) / TC_KBLK;
   prm.dbg = get_option("tc_dbg", 0);
+  prm.seed_tiles = std::max(1, std::min(64, get_option("tc_seed", 4)));
   const size_t fixed = tc_smem_fixed(prm.KB);
   prm.nstage = static_cast<int>(std::min<size_t>(TC_MAX_STAGES, (kSmemLimit - fixed) / TC_STAGE_BYTES));
   const size_t smem = fixed + size_t(prm.nstage) * TC_STAGE_BYTES;
