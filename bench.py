@@ -172,7 +172,8 @@ def make_ball_inputs(rank: int, clouds: int):
 
 def ncu_dram_bytes(summary_name: str, kernel_substr: str = None):
     """dram__bytes_read.sum + dram__bytes_write.sum of a committed `ncu --set full` summary
-    (profiles/<summary_name>), for the first kernel whose name contains kernel_substr; or None."""
+    (profiles/<summary_name>), for the first kernel whose name (or the "# shape" note under it) contains
+    kernel_substr; or None."""
     path = os.path.join(REPO, "profiles", summary_name)
     if not os.path.isfile(path):
         return None
@@ -186,6 +187,8 @@ def ncu_dram_bytes(summary_name: str, kernel_substr: str = None):
                     break
                 active = kernel_substr is None or kernel_substr in ln
                 total, seen = 0.0, 0
+            elif ln.startswith("#") and kernel_substr and kernel_substr in ln:
+                active = True
             elif active and ln.startswith(("dram__bytes_read.sum =", "dram__bytes_write.sum =")):
                 val, u = ln.split("=")[1].split()[:2]
                 total += float(val) * unit.get(u, 1.0)
@@ -628,8 +631,9 @@ def run_ours(args, rank, world, local_rank):
         hbm["secondary_gather"] = {
             "metric": "gathered_rows_per_sec", "value": rows * world / (g3_ms * 1e-3), "unit": "rows/s",
             "workload": f"knn_gather of the T shape's KNN indices: x ({B},{P},U) f32, idx ({B},{P},{K_NN}) i64",
-            "roofline": hbm_line("gather_kernel<KNN,U=3>", g3_ms, rows * (8 + 12 + 12), rows * (8 + 12) + B * P * 12,
-                                 hbm_peak, peak_src, ncu_dram_bytes("r02_hbm_kernels_ncu_full.txt", "gather_kernel")),
+            "roofline": hbm_line("gather_rows3_smem_kernel<KNN> (U=3, the cloud staged in shared memory)", g3_ms,
+                                 rows * (8 + 12 + 12), rows * (8 + 12) + B * P * 12,
+                                 hbm_peak, peak_src, ncu_dram_bytes("r02_hbm_kernels_ncu_full.txt", "T shape: knn_gather")),
             "u16": hbm_line("gather_kernel<KNN,V4> U=16", g16_ms, rows * (8 + 64 + 64), rows * (8 + 64) + B * P * 64,
                             hbm_peak, peak_src)}
         del feat16
