@@ -103,23 +103,36 @@ def chamfer_distance_sharded(x, y, x_lengths=None, y_lengths=None, x_features=No
     # up front.  Everything stays on the device: no host <-> device copy or sync on this path (the first
     # version built the divisor with new_tensor(), two blocking copies per step: 0.47 ms on a 0.47 ms step)
     need_div = batch_reduction == "mean" and (weights is not None or n_clouds_global is None)
+    div_local = None
     if need_div:
         div_local = weights.sum().reshape(1).to(local.dtype) if weights is not None else local.new_full((1,), float(n_local))
-        packed = torch.cat([local.detach(), div_local.detach()])
-    else:
-        packed = local.detach().clone()
-    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    total = packed[:local.shape[0]]
-    if batch_reduction == "mean":
-        if not need_div:
-            div = float(max(n_clouds_global, 1))
-        elif weights is None:
-            div = packed[-1].clamp(min=1)
-        else:
+    fixed_div = float(max(n_clouds_global, 1)) if (batch_reduction == "mean" and not need_div) else 1.0
+    out = _ShardedSum.apply(local, div_local, fixed_div, weights is not None, group)
+    parts = out.unbind(0)
+    out_feats = {k: parts[1 + i] for i, k in enumerate(names)} if feats is not None else None
+    return parts[0], out_feats
+
+
+class _ShardedSum(torch.autograd.Function):
+    """value = (sum over ranks of `local`) / div, gradient = d(local) / div (the other ranks' terms are
+    constants).  One autograd node and three small launches around the all-reduce: the chamfer step is
+    launch-bound, and the composed version (detach, clone, subtract, add, divide, index) added 0.24 ms
+    to a 0.41 ms step on two B200s."""
+
+    @staticmethod
+    def forward(ctx, local, div_local, fixed_div, weighted, group):
+        n = local.shape[0]
+        packed = torch.cat([local, div_local]) if div_local is not None else local.clone()
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        if div_local is None:
+            div = fixed_div
+        elif weighted:  # sum of weights; an all-zero batch divides by 1 (functions/chamfer.py)
             div = torch.where(packed[-1] == 0, torch.ones_like(packed[-1]), packed[-1])
-    else:
-        div = 1.0
-    # value = global sum / div;  gradient = d(local sum)/div  (other ranks' terms are constants)
-    out = (local + (total - local.detach())) / div
-    out_feats = {k: out[1 + i] for i, k in enumerate(names)} if feats is not None else None
-    return out[0], out_feats
+        else:
+            div = packed[-1].clamp(min=1)
+        ctx.div = div
+        return packed[:n] / div
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return grad_out / ctx.div, None, None, None, None

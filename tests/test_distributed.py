@@ -46,7 +46,7 @@ def _worker(rank, world, port, ret):
     xn, yn = torch.randn(N, P, 3, generator=g), torch.randn(N, P, 3, generator=g)
     w = torch.tensor([1.0, 0.5, 0.0, 2.0, 1.5])
     ok = True
-    for (wts, br) in ((None, "mean"), (w, "mean"), (None, "sum")):
+    for (wts, br, ncg) in ((None, "mean", N), (w, "mean", N), (None, "sum", N), (None, "mean", None)):
         xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
         full, full_f = O.chamfer_distance(xr, yr, xl, yl, {"n": xn}, {"n": yn}, wts, br, "mean",
                                           feature_names=["n"])
@@ -56,7 +56,7 @@ def _worker(rank, world, port, ret):
         loss, lf = chamfer_distance_sharded(
             xs, ys, xl[lo:hi], yl[lo:hi], {"n": xn[lo:hi]}, {"n": yn[lo:hi]},
             None if wts is None else wts[lo:hi], br, "mean", feature_names=["n"],
-            n_clouds_global=N, _local_fn=O.chamfer_distance)
+            n_clouds_global=ncg, _local_fn=O.chamfer_distance)
         (loss + lf["n"]).backward()
         ok &= torch.allclose(loss.detach(), full.detach(), rtol=1e-5, atol=1e-7)
         ok &= torch.allclose(lf["n"].detach(), full_f["n"].detach(), rtol=1e-5, atol=1e-7)
