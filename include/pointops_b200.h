@@ -59,12 +59,18 @@ int64_t pops_launch_count(void);
  *               pre-pass (a thread-block cluster sorts a cloud, or the two clouds of a pair, in
  *               distributed shared memory) for clouds of up to 65536 points (32768 with two tensors);
  *               knn_cluster_items 0 auto | 2 | 4 | 8: sort keys per thread of that kernel
+ *   knn_subq    1: every query tests the 16-point runs of a fetched block against its own bound for every K
+ *               (default: K <= 16; K = 32 tests the warp's query box) -- tuning aid
  *   knn_tc      -1 auto | 0 never | 1 whenever the shape allows: tensor-core path for 32 <= D <= 256
- *   tc_cluster  CTAs that share every p2 stage by TMA multicast (1 | 2 | 4) */
+ *   tc_cluster  CTAs that share every p2 stage by TMA multicast (1 | 2 | 4); tc_pair 1 | 0: cta_group::2 pairs
+ *   tc_seed     tiles of the tensor-core scan's seed pass (default 4); tc_dbg: development switches
+ *               (1 never stage a candidate, 2 drain nothing, 4 read accumulators only: NOT valid searches)
+ *   bq_spatial  -1 per cloud on the device | 0 index-order scan | 1 Hilbert-ordered ball query
+ *   gather_rows3 / gather_smem, knn_backward_rows  1 | 0: the specialised gather / backward kernels */
 void pops_set_option(const char* name, int value);
 /* Development counters of the pruned D=3 search, read and reset (needs knn_stats = 1):
  * [0] blocks fetched, [1] blocks scanned, [2] flush rounds, [3] buffered groups, [4] non-empty
- * per-slot flushes, [5] warps. */
+ * per-slot flushes, [5] warps, [6] 16-point runs scanned. */
 int pops_knn_debug_stats(unsigned long long* out8);
 
 /* Optional per-kernel timing (bench.py "roofline"): while enabled, the library brackets its
