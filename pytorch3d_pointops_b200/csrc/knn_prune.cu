@@ -112,8 +112,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   static_assert(kChunk * kGroup == kSubPoints && kSubBoxes == 4, "one overflow-check chunk of the scan = one sub-box");
   // seed blocks: home and its two neighbours in curve order (>= 4 seed points per tournament subset for
   // K <= 16; with one query per thread 3 blocks beat 2 on the T shape: 0.914 vs 0.955 ms at K=16)
-  constexpr int NSEED = KT <= 16 ? 3 : 4;
-  static_assert(NSEED <= S, "the seed blocks sit in the ring together");
+  const int NSEED = prm.nseed > 0 ? min(prm.nseed, S) : (KT <= 16 ? 3 : 4);  // the seed blocks sit in the ring together
   using SM = PruneSmem<Q, THREADS, CID, KT>;
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr unsigned FULL = 0xffffffffu;
@@ -300,7 +299,8 @@ knn_prune_kernel(const KnnPruneParams prm) {
   };
 
   // ---- flush glue ------------------------------------------------------------------------------------
-  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(prune_buf_cap(KT) - kChunk) * CBYTES;
+  const int bufcap = prm.bufcap > 0 ? min(prm.bufcap, prune_buf_cap(KT)) : prune_buf_cap(KT);
+  const uint32_t cw_limit = cand_base + static_cast<uint32_t>(bufcap - kChunk) * CBYTES;
   // only_full: drain just the query slots in which some lane's buffer is nearly full
   auto flush_all = [&](bool only_full) {
     if (prm.stats && lane == 0) atomicAdd(prm.stats + 2, 1ull);
@@ -525,6 +525,8 @@ int knn_prune_search(const KnnOrderBuffers& ob, const int64_t* len1, const int64
   prm.len1 = len1; prm.len2 = len2; prm.maxabs_bits = ob.maxabs_bits; prm.idx = idx; prm.dists = dists;
   prm.P1 = P1; prm.P2 = P2; prm.K = K; prm.nbox = static_cast<int>(knn_order_num_boxes(P2));
   prm.prune = prune;
+  prm.nseed = get_option("knn_nseed", 0);    // seed blocks (0: 3 for K <= 16, else 4) -- tuning aid
+  prm.bufcap = get_option("knn_bufcap", 0);  // candidate groups buffered per query before a flush (0: the allocated capacity)
   prm.subq = get_option("knn_subq", 0);  // 1: per-query sub-box test for every K (tuning aid; K <= 4 always)
   const int stats = get_option("knn_stats", 0);
   prm.stats = nullptr;

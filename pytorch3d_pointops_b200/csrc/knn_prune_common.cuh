@@ -21,6 +21,7 @@ struct KnnPruneParams {
   int P1, P2, K, nbox;
   int prune;  // 0: visit every block (brute force in the same order); measurement aid
   int subq;   // 1: per-query sub-box test for every K
+  int nseed, bufcap;  // tuning aids (0: defaults)
   unsigned long long* stats;  // development counters (POPS_KNN_STATS=1), else nullptr
 };
 
@@ -28,7 +29,10 @@ namespace {
 
 constexpr int kRingSlots = 4;   // blocks resident per warp
 constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
-// candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total)
+// candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total).
+// Larger buffers mean fewer flush rounds (K = 16: 48 instead of 24 entries is 5 % faster at EQUAL shared-memory
+// allocation), but the 3 KB more per CTA push 8 CTAs past the 196 KB carve-out: L1 drops from 60 to 28 KB and
+// the kernel loses 9 % (698 -> 762 us; the flush's re-reads and the list rows live in L1) -- net slower.
 constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : 24); }
 constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
 constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
