@@ -614,20 +614,28 @@ def run_ours(args, rank, world, local_rank):
         from pytorch3d_pointops_b200.functions.packed_to_padded import packed_to_padded, padded_to_packed
 
         h_steps = 10
+
+        def hooked(fn, name, steps=h_steps):
+            """average device time of the library kernel `name` over `steps` calls of fn, by the library's event
+            hooks.  Warm-up runs with the hooks OFF (a call that ends with a host sync leaves the device idle,
+            and the next call's begin event would cover the host's launch gap), timed calls get a device lead."""
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            lib.pops_profile_reset()
+            lib.pops_profile_enable(1)
+            tm.run(fn, steps, warmup=0, reduce=False, lead=True)
+            lib.pops_profile_enable(0)
+            ms, _ = kernel_ms(name)
+            lib.pops_profile_reset()
+            return ms
+
         # knn_gather on the T shape's KNN indices (U = 3: xyz; U = 16: a feature row)
         idx_T, _ = step_resident()
         rows = B * P * K_NN
-        lib.pops_profile_enable(1)
-        tm.run(lambda: knn_gather(p_dev, idx_T, len_dev), h_steps, reduce=False, lead=True)
-        lib.pops_profile_enable(0)
-        g3_ms, _ = kernel_ms(b"gather")
-        lib.pops_profile_reset()
+        g3_ms = hooked(lambda: knn_gather(p_dev, idx_T, len_dev), b"gather")
         feat16 = torch.rand(B, P, 16, device=dev)
-        lib.pops_profile_enable(1)
-        tm.run(lambda: knn_gather(feat16, idx_T, len_dev), h_steps, reduce=False, lead=True)
-        lib.pops_profile_enable(0)
-        g16_ms, _ = kernel_ms(b"gather")
-        lib.pops_profile_reset()
+        g16_ms = hooked(lambda: knn_gather(feat16, idx_T, len_dev), b"gather")
         hbm["secondary_gather"] = {
             "metric": "gathered_rows_per_sec", "value": rows * world / (g3_ms * 1e-3), "unit": "rows/s",
             "workload": f"knn_gather of the T shape's KNN indices: x ({B},{P},U) f32, idx ({B},{P},{K_NN}) i64",
@@ -639,11 +647,7 @@ def run_ours(args, rank, world, local_rank):
         del feat16
         # KNN backward on the T shape
         gd = torch.rand(B, P, K_NN, device=dev)
-        lib.pops_profile_enable(1)
-        tm.run(lambda: _C.knn_points_backward(p_dev, p_dev, len_dev, len_dev, idx_T, 2, gd), h_steps, reduce=False, lead=True)
-        lib.pops_profile_enable(0)
-        kb_ms, _ = kernel_ms(b"knn_backward")
-        lib.pops_profile_reset()
+        kb_ms = hooked(lambda: _C.knn_points_backward(p_dev, p_dev, len_dev, len_dev, idx_T, 2, gd), b"knn_backward")
         hbm["secondary_knn_backward"] = {
             "metric": "knn_backward_entries_per_sec", "value": rows * world / (kb_ms * 1e-3), "unit": "(query,neighbour) pairs/s",
             "workload": f"_C.knn_points_backward on the T shape: idx/grad_dists ({B},{P},{K_NN}), D=3, norm 2",
@@ -660,17 +664,9 @@ def run_ours(args, rank, world, local_rank):
         pk = {}
         for Dp in (3, 16):
             packed = torch.rand(F_rows, Dp, device=dev)
-            lib.pops_profile_enable(1)
-            tm.run(lambda: packed_to_padded(packed, first, mx), h_steps, reduce=False, lead=True)
-            lib.pops_profile_enable(0)
-            a_ms, _ = kernel_ms(b"packed_to_padded")
-            lib.pops_profile_reset()
+            a_ms = hooked(lambda: packed_to_padded(packed, first, mx), b"packed_to_padded")
             padded = packed_to_padded(packed, first, mx)
-            lib.pops_profile_enable(1)
-            tm.run(lambda: padded_to_packed(padded, first, F_rows), h_steps, reduce=False, lead=True)
-            lib.pops_profile_enable(0)
-            b_ms, _ = kernel_ms(b"padded_to_packed")
-            lib.pops_profile_reset()
+            b_ms = hooked(lambda: padded_to_packed(padded, first, F_rows), b"padded_to_packed")
             by_a = F_rows * Dp * 4 + 64 * mx * Dp * 4
             by_b = 2 * F_rows * Dp * 4
             pk[f"D{Dp}"] = {"packed_to_padded": hbm_line("packed_to_padded_kernel", a_ms, by_a, by_a, hbm_peak, peak_src,

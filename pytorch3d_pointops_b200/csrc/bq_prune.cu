@@ -229,11 +229,11 @@ __device__ __noinline__ void bq_flush(const float* __restrict__ blocks_n, const 
       const float4 Xa = *reinterpret_cast<const float4*>(pa);
       const float4 Ya = *reinterpret_cast<const float4*>(pa + kBoxPoints);
       const float4 Za = *reinterpret_cast<const float4*>(pa + 2 * kBoxPoints);
-      const uint4 Ia = *reinterpret_cast<const uint4*>(pa + 4 * kBoxPoints);
+      const uint4 Ia = *reinterpret_cast<const uint4*>(pa + kIdxOff);
       const float4 Xb = *reinterpret_cast<const float4*>(pb);
       const float4 Yb = *reinterpret_cast<const float4*>(pb + kBoxPoints);
       const float4 Zb = *reinterpret_cast<const float4*>(pb + 2 * kBoxPoints);
-      const uint4 Ib = *reinterpret_cast<const uint4*>(pb + 4 * kBoxPoints);
+      const uint4 Ib = *reinterpret_cast<const uint4*>(pb + kIdxOff);
       float da[4], db[4];
       exact4(q0, q1, q2, Xa, Ya, Za, da);
       exact4(q0, q1, q2, Xb, Yb, Zb, db);
@@ -295,7 +295,7 @@ bq_prune_kernel(const BqPruneParams prm) {
   const float r2 = prm.radius2;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::bars_off) + warp * S;
-  float* ring = reinterpret_cast<float*>(smem + SM::ring_off) + static_cast<size_t>(warp) * S * kBlockFloats;
+  float* ring = reinterpret_cast<float*>(smem + SM::ring_off) + static_cast<size_t>(warp) * S * kScanFloats;
   const float4* ring4 = reinterpret_cast<const float4*>(ring);
   CID* cand = reinterpret_cast<CID*>(smem + SM::cand_off);
   constexpr size_t COLI = SM::col_bytes / sizeof(IDX);  // column stride in index elements
@@ -369,7 +369,7 @@ bq_prune_kernel(const BqPruneParams prm) {
       if (lane == 0) {
         fence_proxy_async();  // the slot's previous contents were read through the generic proxy
         mbar_arrive_expect_tx(&bars[s], kBlockBytes);
-        tma_bulk_g2s(ring + static_cast<size_t>(s) * kBlockFloats, blocks_n + static_cast<size_t>(b) * kBlockFloats,
+        tma_bulk_g2s(ring + static_cast<size_t>(s) * kScanFloats, blocks_n + static_cast<size_t>(b) * kBlockFloats,
                      kBlockBytes, &bars[s]);
       }
       if (lane == s) {

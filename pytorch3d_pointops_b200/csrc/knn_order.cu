@@ -355,7 +355,7 @@ __global__ void gather_p2_kernel(const float* __restrict__ p2, const int64_t* __
   dst[kBoxPoints] = y;
   dst[2 * kBoxPoints] = z;
   dst[3 * kBoxPoints] = w;
-  dst[4 * kBoxPoints] = __uint_as_float(orig);
+  dst[kIdxOff] = __uint_as_float(orig);
 }
 
 __global__ void gather_p1_kernel(const float* __restrict__ p1, const int64_t* __restrict__ len1,
@@ -433,7 +433,7 @@ __global__ void box_kernel(float* __restrict__ blocks, int nbox, float4* __restr
 #pragma unroll
   for (int h = 0; h < kBoxPoints / 32; ++h) {
     const int i = h * 32 + lane;
-    const bool valid = __float_as_uint(base[4 * kBoxPoints + i]) != kNoPoint;
+    const bool valid = __float_as_uint(base[kIdxOff + i]) != kNoPoint;
     half_block_boxes(base[i], base[kBoxPoints + i], base[2 * kBoxPoints + i], valid, base, h, lane, true, mn, mx);
   }
 #pragma unroll
@@ -490,7 +490,7 @@ __global__ void gather_pair_kernel(const float* __restrict__ pts, const int64_t*
   dst[kBoxPoints] = y;
   dst[2 * kBoxPoints] = z;
   dst[3 * kBoxPoints] = w;
-  dst[4 * kBoxPoints] = __uint_as_float(orig);
+  dst[kIdxOff] = __uint_as_float(orig);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -830,7 +830,7 @@ order_cluster_kernel(const ClusterOrderParams prm) {
         dst[kBoxPoints] = y;
         dst[2 * kBoxPoints] = z;
         dst[3 * kBoxPoints] = w;
-        dst[4 * kBoxPoints] = __uint_as_float(orig);
+        dst[kIdxOff] = __uint_as_float(orig);
       }
       if (blocks_role) half_block_boxes(x, y, z, s < L, bbase, h, lane, wr, bmn, bmx);
       if (query_role && s < P) {

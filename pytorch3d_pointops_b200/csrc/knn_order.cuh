@@ -8,8 +8,8 @@ namespace pops {
 struct KnnOrderBuffers {
   unsigned* maxabs_bits;  // [N]        max |coordinate| over p1 and p2 of the cloud (float bits)
   float* bbox;            // [N][6]     min xyz, max xyz of the valid p2 points
-  float* blocks;          // [N][nbox][kBlockFloats]  rows x, y, z, w=|p|^2, original index (u32 bits) of kBoxPoints
-                          //   points in curve order, then the boxes of its kSubBoxes runs of kSubPoints points
+  float* blocks;          // [N][nbox][kBlockFloats]  rows x, y, z, w=|p|^2 of kBoxPoints points in curve order, the
+                          //   boxes of its kSubBoxes runs of kSubPoints points, the row of original indices (u32 bits)
   float4* qsorted;        // [N][P1]    x, y, z, original index (u32 bits), curve order
   unsigned* qhome;        // [N][P1]    position in the sorted p2 where the query's code would go
   float4* boxes;          // [N][nbox][2]  (min xyz, -), (max xyz, -) of every kBoxPoints sorted p2 points
@@ -26,10 +26,14 @@ constexpr unsigned kNoPoint = 0xFFFFFFFFu;  // "original index" of padding entri
 constexpr int kBoxPoints = 64;               // sorted p2 points per block (one bounding box each)
 constexpr int kSubPoints = 16;               // consecutive sorted points per sub-box
 constexpr int kSubBoxes = kBoxPoints / kSubPoints;
-constexpr int kSubOff = 5 * kBoxPoints;      // float offset of the sub-boxes inside a block: [kSubBoxes][2] float4
-                                             //   (min xyz, -), (max xyz, -); runs without a valid point: (+inf, -inf)
-// x, y, z, w, index rows + sub-boxes: 1408 contiguous bytes per block (one TMA bulk copy, 128-byte aligned)
-constexpr int kBlockFloats = kSubOff + kSubBoxes * 8;
+// One block = 1408 contiguous, 128-byte aligned bytes: rows x, y, z, w of its kBoxPoints points, the boxes of
+// its kSubBoxes runs of kSubPoints points ([kSubBoxes][2] float4: (min xyz, -), (max xyz, -); runs without a
+// valid point: (+inf, -inf)), then the row of original indices.  A scan needs the first kScanFloats only (one
+// TMA bulk copy of 1152 bytes); the index row is read when a buffered group gets its exact distance.
+constexpr int kSubOff = 4 * kBoxPoints;
+constexpr int kIdxOff = kSubOff + kSubBoxes * 8;
+constexpr int kScanFloats = kIdxOff;
+constexpr int kBlockFloats = kIdxOff + kBoxPoints;
 
 // boxes per cloud, padded so that a warp can read 32 boxes of any 2048-point tile in bounds
 inline int64_t knn_order_num_boxes(int64_t P2) {

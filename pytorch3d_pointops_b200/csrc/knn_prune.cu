@@ -16,7 +16,8 @@
 //             operations, and rounding is monotone, so "bound > K-th distance" proves that no
 //             point of the block can enter any list of the warp -- no epsilon (box_lower_bound).
 //     fetch   each surviving block arrives by ONE TMA bulk copy (cp.async.bulk + mbarrier) into the
-//             warp's private ring of 4 slots, up to 3 blocks ahead of the scan.
+//             warp's private ring of 3 slots (K = 32: 4), up to 2 (3) blocks ahead of the scan; only the part of a
+//             block a scan reads travels (rows x, y, z, w and the run boxes: 1152 bytes).
 //     seed    before the first scan the warp evaluates the exact distances to its first 1-4 blocks
 //             and keeps, per query, the minimum over each of 2 KT interleaved subsets; the KT-th
 //             smallest of those minima bounds the K-th distance from above (KT distinct points are
@@ -65,11 +66,11 @@ __device__ __noinline__ float2 prune_flush_one(const float* __restrict__ blocks_
       const float4 Xa = *reinterpret_cast<const float4*>(pa);
       const float4 Ya = *reinterpret_cast<const float4*>(pa + kBoxPoints);
       const float4 Za = *reinterpret_cast<const float4*>(pa + 2 * kBoxPoints);
-      const uint4 Ia = *reinterpret_cast<const uint4*>(pa + 4 * kBoxPoints);
+      const uint4 Ia = *reinterpret_cast<const uint4*>(pa + kIdxOff);
       const float4 Xb = *reinterpret_cast<const float4*>(pb);
       const float4 Yb = *reinterpret_cast<const float4*>(pb + kBoxPoints);
       const float4 Zb = *reinterpret_cast<const float4*>(pb + 2 * kBoxPoints);
-      const uint4 Ib = *reinterpret_cast<const uint4*>(pb + 4 * kBoxPoints);
+      const uint4 Ib = *reinterpret_cast<const uint4*>(pb + kIdxOff);
       float da[4], db[4];
       exact4(q0, q1, q2, Xa, Ya, Za, da);
       exact4(q0, q1, q2, Xb, Yb, Zb, db);
@@ -103,7 +104,7 @@ __device__ __noinline__ float2 prune_flush_one(const float* __restrict__ blocks_
 template <int Q, int KT, int THREADS, typename CID>
 __global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : ((Q == 1 && KT == 1) ? 10 : 8))))
 knn_prune_kernel(const KnnPruneParams prm) {
-  constexpr int QPB = Q * THREADS, S = kRingSlots;
+  constexpr int QPB = Q * THREADS, S = prune_ring_slots(KT), PF = S - 1;  // ring slots, blocks in flight ahead of the scan
   // which runs of kSubPoints points of a fetched block are scanned: every query tests the runs' boxes
   // against its own bound (K <= 16), or the warp's query box against the warp's largest bound (K = 32: the
   // extra tests cost more than the 30 % fewer runs give back, 2.36 vs 2.26 ms on the T shape; knn_subq
@@ -142,7 +143,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   }
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::bars_off) + warp * S;
-  float* ring = reinterpret_cast<float*>(smem + SM::ring_off) + static_cast<size_t>(warp) * S * kBlockFloats;
+  float* ring = reinterpret_cast<float*>(smem + SM::ring_off) + static_cast<size_t>(warp) * S * kScanFloats;
   const float4* ring4 = reinterpret_cast<const float4*>(ring);
   CID* cand = reinterpret_cast<CID*>(smem + SM::cand_off);
   uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off);
@@ -282,12 +283,12 @@ knn_prune_kernel(const KnnPruneParams prm) {
   int slot_blk = 0;      // lane s: index of the block in slot s
   int head = 0, tail = 0;  // blocks issued / scanned
   auto issue = [&](int b) {
-    const int s = head & (S - 1);
+    const int s = head % S;
     __syncwarp();
     if (lane == 0) {
       fence_proxy_async();  // the slot's previous contents were read through the generic proxy
       mbar_arrive_expect_tx(&bars[s], kBlockBytes);
-      tma_bulk_g2s(ring + static_cast<size_t>(s) * kBlockFloats, blocks_n + static_cast<size_t>(b) * kBlockFloats,
+      tma_bulk_g2s(ring + static_cast<size_t>(s) * kScanFloats, blocks_n + static_cast<size_t>(b) * kBlockFloats,
                    kBlockBytes, &bars[s]);
     }
     if (lane == s) {
@@ -359,13 +360,13 @@ knn_prune_kernel(const KnnPruneParams prm) {
 
   // ---- main loop ---------------------------------------------------------------------------------
   for (;;) {
-    while (head - tail < kPrefetch) {
+    while (head - tail < PF) {
       const int b = pick();
       if (b < 0) break;
       issue(b);
     }
     if (tail == head) break;
-    const int s = tail & (S - 1);
+    const int s = tail % S;
     mbar_wait(&bars[s], (tail / S) & 1);
     // dkmax may have dropped since the fetch; then the block's runs of kSubPoints points against their own
     // boxes (behind the block's rows in the ring slot): bit j of `sub` = run j is scanned

@@ -27,16 +27,20 @@ struct KnnPruneParams {
 
 namespace {
 
-constexpr int kRingSlots = 4;   // blocks resident per warp
+constexpr int kRingSlots = 4;   // blocks resident per warp (ball query; KNN: prune_ring_slots)
 constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
+// KNN: K <= 16 keeps 3 blocks per warp (2 in flight ahead of the scan).  With the index row out of the ring slot
+// that is 19.2 KB of shared memory per CTA: 8 CTAs fit the 164 KB carve-out and the L1 grows from 60 to 92 KB
+// (the flush's re-reads of buffered groups and the list rows live there).  K = 32 seeds from 4 blocks.
+constexpr int prune_ring_slots(int KT) { return KT <= 16 ? 3 : 4; }
 // candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total).
 // Larger buffers mean fewer flush rounds (K = 16: 48 instead of 24 entries is 5 % faster at EQUAL shared-memory
 // allocation), but the 3 KB more per CTA push 8 CTAs past the 196 KB carve-out: L1 drops from 60 to 28 KB and
 // the kernel loses 9 % (698 -> 762 us; the flush's re-reads and the list rows live in L1) -- net slower.
 constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : 24); }
-constexpr int kBlockF4 = kBlockFloats / 4;        // 80 float4 per block
+constexpr int kBlockF4 = kScanFloats / 4;         // float4 per ring slot: the part of a block a scan reads
 constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
-constexpr uint32_t kBlockBytes = kBlockFloats * 4;
+constexpr uint32_t kBlockBytes = kScanFloats * 4;  // bytes of one TMA bulk copy (rows x, y, z, w + run boxes)
 static_assert((kRingSlots & (kRingSlots - 1)) == 0 && kRingSlots <= 32, "slot metadata sits in lanes");
 
 
@@ -48,7 +52,8 @@ struct PruneSmem {
   static constexpr int QPB = Q * THREADS;
   static constexpr size_t bars_off = 0;
   static constexpr size_t ring_off = 256;
-  static constexpr size_t ring_bytes = size_t(WARPS) * kRingSlots * kBlockBytes;
+  static constexpr int SLOTS = prune_ring_slots(KT);
+  static constexpr size_t ring_bytes = size_t(WARPS) * SLOTS * kBlockBytes;
   static constexpr size_t cand_off = ring_off + ring_bytes;
   static constexpr size_t cand_bytes = size_t(prune_buf_cap(KT)) * QPB * sizeof(CID);  // global group ids
   static constexpr size_t surv_off = (cand_off + cand_bytes + 15) / 16 * 16;
@@ -56,7 +61,7 @@ struct PruneSmem {
   static constexpr size_t cold_off = surv_off + surv_bytes;
   static constexpr size_t cold_bytes = size_t(3) * QPB * 4;  // qq, dk, output row per query
   static constexpr size_t total = cold_off + cold_bytes;
-  static_assert(WARPS * kRingSlots * 8 <= ring_off, "mbarriers overlap the ring");
+  static_assert(WARPS * SLOTS * 8 <= ring_off, "mbarriers overlap the ring");
 };
 
 // Lower bound of the reference distance between ANY query in the box [qlo, qhi] and ANY point in
