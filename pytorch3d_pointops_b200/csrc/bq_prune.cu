@@ -13,8 +13,9 @@
 //                             points (rows x, y, z, w = |p|^2, original index) with one box each.
 //   this kernel               one warp = 32 consecutive sorted queries.
 //     walk    every block whose box lies within radius of the warp's query box (exact lower bound of
-//             the reference distance: knn_prune_common.cuh), refined per block by the queries' own
-//             bounds; blocks arrive by TMA bulk copies into the warp's ring, as in knn_prune.cu.
+//             the reference distance: knn_prune_common.cuh); blocks arrive by TMA bulk copies into the
+//             warp's ring, as in knn_prune.cu, and are scanned run by run: a run of 16 points only if
+//             some query's own ball reaches the run's box.
 //     scan    the KNN scan: expanded-form filter against (r^2 - |q|^2) + E, group ids appended,
 //             predicated, to the query's candidate buffer.
 //     flush   buffered groups re-read from the sorted blocks (L2), exact unfused distance, strict
@@ -361,7 +362,6 @@ bq_prune_kernel(const BqPruneParams prm) {
 
     const float* blocks_n = prm.blocks + static_cast<size_t>(n) * prm.nbox * kBlockFloats;
     int slot_blk = 0;  // lane s: block in ring slot s
-    float4 slot_lo = make_float4(0.f, 0.f, 0.f, 0.f), slot_hi = slot_lo;
     int head = 0, tail = 0;
     auto issue = [&](int b) {
       const int s = head & (S - 1);
@@ -372,11 +372,7 @@ bq_prune_kernel(const BqPruneParams prm) {
         tma_bulk_g2s(ring + static_cast<size_t>(s) * kScanFloats, blocks_n + static_cast<size_t>(b) * kBlockFloats,
                      kBlockBytes, &bars[s]);
       }
-      if (lane == s) {
-        slot_blk = b;
-        slot_lo = boxes_n[static_cast<size_t>(b) * 2];  // consumed when the block is scanned: latency hidden
-        slot_hi = boxes_n[static_cast<size_t>(b) * 2 + 1];
-      }
+      if (lane == s) slot_blk = b;
       ++head;
     };
 
@@ -400,26 +396,31 @@ bq_prune_kernel(const BqPruneParams prm) {
       if (tail == head) break;
       const int s = tail & (S - 1);
       mbar_wait(&bars[s], (tail / S) & 1);
-      // the warp-wide test used the box of ALL its queries: scan only if some query's own ball reaches the block
-      float4 lo, hi;
-      lo.x = __shfl_sync(FULL, slot_lo.x, s); lo.y = __shfl_sync(FULL, slot_lo.y, s); lo.z = __shfl_sync(FULL, slot_lo.z, s);
-      hi.x = __shfl_sync(FULL, slot_hi.x, s); hi.y = __shfl_sync(FULL, slot_hi.y, s); hi.z = __shfl_sync(FULL, slot_hi.z, s);
-      const bool need = valid && box_lower_bound(lo, hi, qown, qown) < r2;
-      if (__any_sync(FULL, need)) {
+      // the warp-wide test used the box of ALL its queries: a run of kSubPoints points of the block is scanned
+      // only if some query's own ball reaches the run's box (the boxes arrive with the block, knn_order.cuh)
+      static_assert(kChunk * kGroup == kSubPoints && kSubBoxes == 4, "one overflow-check chunk of the scan = one run");
+      const float4* sb = ring4 + s * kBlockF4 + kSubOff / 4;
+      unsigned sub = 0u;
+#pragma unroll
+      for (int j = 0; j < kSubBoxes; ++j) {
+        const bool need = valid && box_lower_bound(sb[2 * j], sb[2 * j + 1], qown, qown) < r2;
+        sub |= __any_sync(FULL, need) ? (1u << j) : 0u;
+      }
+      if (sub) {
         const float4* tp = ring4 + s * kBlockF4;
         const unsigned gid0 = static_cast<unsigned>(__shfl_sync(FULL, slot_blk, s)) * kBlockGroups;
-        int g = 0;
-        unsigned gid = gid0;
         do {  // (the flush is a call and stays outside the dense loop, as in knn_prune.cu)
+          int g = (__ffs(sub) - 1) * kChunk;  // first run still to scan
+          unsigned gid = gid0 + static_cast<unsigned>(g);
           float4 Xc[4];
 #pragma unroll
           for (int r = 0; r < 4; ++r) Xc[r] = tp[r * kBlockGroups + g];
           bool over = false;
 #pragma unroll 1
-          for (; g < kBlockGroups && !over; g += kChunk) {
+          for (; g < kBlockGroups && !over && ((sub >> (g / kChunk)) & 1u); g += kChunk) {
 #pragma unroll
             for (int c = 0; c < kChunk; ++c) {
-              float4 Xn[4];  // next group's rows (the last prefetch of a block reads the index row: in bounds, unused)
+              float4 Xn[4];  // next group's rows (the last prefetch of a block reads the run boxes: in bounds, unused)
 #pragma unroll
               for (int r = 0; r < 4; ++r) Xn[r] = tp[r * kBlockGroups + g + c + 1];
               float2 s01 = make_float2(Xc[3].x, Xc[3].y), s23 = make_float2(Xc[3].z, Xc[3].w);
@@ -443,8 +444,9 @@ bq_prune_kernel(const BqPruneParams prm) {
             }
             over = __any_sync(FULL, cw > cw_limit);
           }
+          sub &= ~((1u << (g / kChunk)) - 1u);  // runs below g are done or were skipped
           if (over) flush();
-        } while (g < kBlockGroups);
+        } while (sub);
       }
       ++tail;
     }
