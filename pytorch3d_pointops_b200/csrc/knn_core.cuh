@@ -60,23 +60,44 @@ __device__ __forceinline__ void insert_network(uint64_t (&Lr)[KT], uint64_t key)
 
 static_assert(kSurvCap == 16, "sort16 assumes 16 survivor slots");
 
-// Batcher odd-even merge sort of v[OFF .. OFF+N) (N a power of two), ascending; fully unrolled, so
-// every index is static and the values stay in registers (63 compare-exchanges for N = 16).
+// Batcher odd-even merge sort of v[OFF .. OFF+N), N in {4, 8, 16}, ascending, from compare-exchange tables
+// (generated offline, verified with the 0-1 principle): one flat, fully unrolled loop, so every index is
+// static and the values stay in registers.  (The nested-loop formulation of the same network left one
+// stage rolled with run-time indices: the whole array then lives in local memory.)
+constexpr int kSort4N = 5;
+__device__ constexpr unsigned char kSort4A[kSort4N] = {0,2,0,1,1};
+__device__ constexpr unsigned char kSort4B[kSort4N] = {1,3,2,3,2};
+constexpr int kSort8N = 19;
+__device__ constexpr unsigned char kSort8A[kSort8N] = {0,2,4,6,0,1,4,5,1,5,0,1,2,3,2,3,1,3,5};
+__device__ constexpr unsigned char kSort8B[kSort8N] = {1,3,5,7,2,3,6,7,2,6,4,5,6,7,4,5,2,4,6};
 template <int N, int OFF, int TOTAL>
 __device__ __forceinline__ void sort_floats(float (&v)[TOTAL]) {
+  if constexpr (N == 4 || N == 8 || N == 16) {
+    constexpr int NCE = N == 4 ? kSort4N : (N == 8 ? kSort8N : kSort16N);
 #pragma unroll
-  for (int p = 1; p < N; p *= 2) {
+    for (int e = 0; e < NCE; ++e) {
+      const int ia = OFF + (N == 4 ? kSort4A[e] : (N == 8 ? kSort8A[e] : kSort16A[e]));
+      const int ib = OFF + (N == 4 ? kSort4B[e] : (N == 8 ? kSort8B[e] : kSort16B[e]));
+      const float lo = fminf(v[ia], v[ib]);
+      const float hi = fmaxf(v[ia], v[ib]);
+      v[ia] = lo;
+      v[ib] = hi;
+    }
+  } else {  // any other power of two (K = 32 seeds sort 2 x 32 values): the same network from nested loops
 #pragma unroll
-    for (int k = p; k >= 1; k /= 2) {
+    for (int p = 1; p < N; p *= 2) {
 #pragma unroll
-      for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
+      for (int k = p; k >= 1; k /= 2) {
 #pragma unroll
-        for (int i = 0; i < k; ++i) {
-          if (i <= N - j - k - 1 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-            const float lo = fminf(v[OFF + i + j], v[OFF + i + j + k]);
-            const float hi = fmaxf(v[OFF + i + j], v[OFF + i + j + k]);
-            v[OFF + i + j] = lo;
-            v[OFF + i + j + k] = hi;
+        for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
+#pragma unroll
+          for (int i = 0; i < k; ++i) {
+            if (i <= N - j - k - 1 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+              const float lo = fminf(v[OFF + i + j], v[OFF + i + j + k]);
+              const float hi = fmaxf(v[OFF + i + j], v[OFF + i + j + k]);
+              v[OFF + i + j] = lo;
+              v[OFF + i + j + k] = hi;
+            }
           }
         }
       }

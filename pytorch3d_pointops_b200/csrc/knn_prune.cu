@@ -218,6 +218,14 @@ knn_prune_kernel(const KnnPruneParams prm) {
       wqhi[d] = fmaxf(wqhi[d], __shfl_xor_sync(FULL, wqhi[d], o));
     }
   }
+  // the warp's query box is only needed when a chunk of block boxes is tested (and by the K = 32 run test):
+  // it waits in shared memory, not in six registers of a kernel that sits at its register cap
+  float* wbox = reinterpret_cast<float*>(smem + SM::wbox_off) + warp * 8;
+  if (lane < 3) {  // (selects, not wqlo[lane]: a run-time index would put the arrays in local memory)
+    wbox[lane] = lane == 0 ? wqlo[0] : (lane == 1 ? wqlo[1] : wqlo[2]);
+    wbox[4 + lane] = lane == 0 ? wqhi[0] : (lane == 1 ? wqhi[1] : wqhi[2]);
+  }
+  __syncwarp();
   float dkmax = INF;  // largest bound over the warp's valid queries
 
   // ---- block walk: outward from the warp's home block, 32 blocks (one chunk) per side at a time
@@ -231,7 +239,8 @@ knn_prune_kernel(const KnnPruneParams prm) {
   auto chunk_bounds = [&](int c) -> float {  // lane j: bound for block c*32 + j
     if (!prm.prune) return 0.0f;
     const float4* bx = boxes_n + static_cast<size_t>(c * 32 + lane) * 2;  // nbox is a multiple of 32
-    return box_lower_bound(bx[0], bx[1], wqlo, wqhi);
+    const float qlo[3] = {wbox[0], wbox[1], wbox[2]}, qhi[3] = {wbox[4], wbox[5], wbox[6]};
+    return box_lower_bound(bx[0], bx[1], qlo, qhi);
   };
   auto valid_mask = [&](int c) -> unsigned {
     const int left = nblk - (c << 5);
@@ -391,7 +400,8 @@ knn_prune_kernel(const KnnPruneParams prm) {
         }
       } else {
         const float4 lo = sb[2 * (lane & 3)], hi = sb[2 * (lane & 3) + 1];
-        sub = __ballot_sync(FULL, box_lower_bound(lo, hi, wqlo, wqhi) <= dkmax) & 0xFu;
+        const float qlo[3] = {wbox[0], wbox[1], wbox[2]}, qhi[3] = {wbox[4], wbox[5], wbox[6]};
+        sub = __ballot_sync(FULL, box_lower_bound(lo, hi, qlo, qhi) <= dkmax) & 0xFu;
       }
     }
     if (sub) {

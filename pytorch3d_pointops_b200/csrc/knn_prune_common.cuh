@@ -60,7 +60,8 @@ struct PruneSmem {
   static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
   static constexpr size_t cold_off = surv_off + surv_bytes;
   static constexpr size_t cold_bytes = size_t(3) * QPB * 4;  // qq, dk, output row per query
-  static constexpr size_t total = cold_off + cold_bytes;
+  static constexpr size_t wbox_off = cold_off + cold_bytes;  // per warp: min xyz, -, max xyz, - of its queries
+  static constexpr size_t total = wbox_off + size_t(WARPS) * 32;
   static_assert(WARPS * SLOTS * 8 <= ring_off, "mbarriers overlap the ring");
 };
 
