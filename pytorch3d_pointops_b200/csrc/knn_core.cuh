@@ -183,10 +183,15 @@ __device__ __forceinline__ float knn_merge_global(const uint64_t* S, int ns, int
         }
       }
     }
-    uint64_t worst = kEmptyKey;
+    // K == KT (the usual K = 1, 4, 8, 16, 32) reads the last register; otherwise the compiler indexes the
+    // list through local memory (KT stores and a load), which then stay on this cold path
+    uint64_t worst = Lr[KR - 1];
+    if (K != KR) {
+      worst = kEmptyKey;
 #pragma unroll
-    for (int k = 0; k < KR; ++k)
-      if (k == K - 1) worst = Lr[k];
+      for (int k = 0; k < KR; ++k)
+        if (k == K - 1) worst = Lr[k];
+    }
     // the list's K-th entry (+inf while it is not full), or a tighter bound the caller had
     dkt = fminf(dkt, key_dist(worst));
   }

@@ -147,9 +147,8 @@ knn_prune_kernel(const KnnPruneParams prm) {
   const float4* ring4 = reinterpret_cast<const float4*>(ring);
   CID* cand = reinterpret_cast<CID*>(smem + SM::cand_off);
   uint64_t* surv = reinterpret_cast<uint64_t*>(smem + SM::surv_off);
-  // per-query state the dense loop never touches lives in shared memory, not in registers
-  float* cold_qq = reinterpret_cast<float*>(smem + SM::cold_off);
-  float* cold_dk = cold_qq + QPB;  // upper bound of the final K-th distance (-1: beyond lengths1)
+  // per-query state the dense loop never touches lives in shared memory, not in registers (|q|^2: qq_of)
+  float* cold_dk = reinterpret_cast<float*>(smem + SM::cold_off);  // upper bound of the final K-th distance (-1: beyond lengths1)
   // output row = original query index; top bit: the list is still empty and the row unwritten
   unsigned* cold_row = reinterpret_cast<unsigned*>(cold_dk + QPB);
   constexpr unsigned kFresh = 0x80000000u;
@@ -183,17 +182,14 @@ knn_prune_kernel(const KnnPruneParams prm) {
     if (qi < prm.P1) v = qs[qi];
     const unsigned row = __float_as_uint(v.w);
     const float qv[3] = {valid ? v.x : 0.0f, valid ? v.y : 0.0f, valid ? v.z : 0.0f};
-    float s = 0.0f;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      s = fmaf(qv[d], qv[d], s);
       a[t][d] = -2.0f * qv[d];
       if (valid) {
         wqlo[d] = fminf(wqlo[d], qv[d]);
         wqhi[d] = fmaxf(wqhi[d], qv[d]);
       }
     }
-    cold_qq[slot] = s;
     cold_dk[slot] = valid ? INF : -1.0f;
     cold_row[slot] = row | (valid ? kFresh : 0u);
     T[t] = valid ? FLT_MAX : -INF;
@@ -208,6 +204,9 @@ knn_prune_kernel(const KnnPruneParams prm) {
       }
     }
   }
+  // |q|^2 of query slot t as the filter uses it: a = -2 q, and scaling by powers of two commutes with rounding,
+  // so this is the fmaf chain over q itself (not worth a word of shared memory per query)
+  auto qq_of = [&](int t) { return 0.25f * fmaf(a[t][2], a[t][2], fmaf(a[t][1], a[t][1], a[t][0] * a[t][0])); };
   if (wq0 >= L1) return;  // no valid query in this warp; warps never meet again
   if (prm.stats && lane == 0) atomicAdd(prm.stats + 5, 1ull);
 #pragma unroll
@@ -338,7 +337,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
       const float dkt = fr.x;
       if (fr.y == 0.0f) cold_row[slot] = static_cast<unsigned>(row);
       cold_dk[slot] = dkt;
-      if (dkt >= 0.0f && dkt < INF) T[t] = __fadd_rn(__fsub_rn(dkt, cold_qq[slot]), E);
+      if (dkt >= 0.0f && dkt < INF) T[t] = __fadd_rn(__fsub_rn(dkt, qq_of(t)), E);
       dm = fmaxf(dm, dkt);
     }
     dkmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(dm)));
@@ -357,10 +356,10 @@ knn_prune_kernel(const KnnPruneParams prm) {
 #pragma unroll
     for (int t = 0; t < Q; ++t) {
       const int slot = slot0 + t * 32;
-      const float U = seed_bound<KT>(ring4, nseed, a[t][0], a[t][1], a[t][2], cold_qq[slot], E);
+      const float U = seed_bound<KT>(ring4, nseed, a[t][0], a[t][1], a[t][2], qq_of(t), E);
       if (cold_dk[slot] >= 0.0f) {
         cold_dk[slot] = U;  // KT >= K distinct points lie within U
-        if (U < INF) T[t] = __fadd_rn(__fsub_rn(U, cold_qq[slot]), E);
+        if (U < INF) T[t] = __fadd_rn(__fsub_rn(U, qq_of(t)), E);
         dm = fmaxf(dm, U);
       }
     }

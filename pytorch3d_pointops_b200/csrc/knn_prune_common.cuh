@@ -34,10 +34,11 @@ constexpr int kPrefetch = 3;    // blocks in flight ahead of the scan
 // (the flush's re-reads of buffered groups and the list rows live there).  K = 32 seeds from 4 blocks.
 constexpr int prune_ring_slots(int KT) { return KT <= 16 ? 3 : 4; }
 // candidate groups a query can buffer between flushes (a query meets ~K/4 + curve scatter groups in total).
-// Larger buffers mean fewer flush rounds (K = 16: 48 instead of 24 entries is 5 % faster at EQUAL shared-memory
-// allocation), but the 3 KB more per CTA push 8 CTAs past the 196 KB carve-out: L1 drops from 60 to 28 KB and
-// the kernel loses 9 % (698 -> 762 us; the flush's re-reads and the list rows live in L1) -- net slower.
-constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : 24); }
+// Larger buffers mean fewer flush rounds (K = 16: 24 -> 28 -> 32 entries: 614 -> 593 -> ... us), as long as the CTA
+// stays inside its shared-memory carve-out: 48 entries (3 KB more) pushed 8 CTAs from the 196 KB into the 228 KB
+// carve-out, L1 dropped from 60 to 28 KB and the kernel lost 9 % (the flush's re-reads and the list rows live
+// in L1).  K = 16 takes the 32 entries that still fit under 164 KB.
+constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : (KT == 16 ? 32 : 24)); }
 constexpr int kBlockF4 = kScanFloats / 4;         // float4 per ring slot: the part of a block a scan reads
 constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
 constexpr uint32_t kBlockBytes = kScanFloats * 4;  // bytes of one TMA bulk copy (rows x, y, z, w + run boxes)
@@ -50,8 +51,11 @@ template <int Q, int THREADS, typename CID, int KT>
 struct PruneSmem {
   static constexpr int WARPS = THREADS / 32;
   static constexpr int QPB = Q * THREADS;
-  static constexpr size_t bars_off = 0;
-  static constexpr size_t ring_off = 256;
+  // Every byte counts: 8 CTAs x (total + 1 KB reserved) must stay within the 164 KB shared-memory carve-out
+  // (knn_prune_common.cuh: prune_ring_slots) -- K = 16, one query per thread: 19 840 of 19 968 bytes.
+  static constexpr size_t bars_off = 0;      // WARPS x SLOTS mbarriers (<= 64 bytes)
+  static constexpr size_t wbox_off = 64;     // per warp: min xyz, -, max xyz, - of its queries (WARPS x 32 bytes)
+  static constexpr size_t ring_off = 128;
   static constexpr int SLOTS = prune_ring_slots(KT);
   static constexpr size_t ring_bytes = size_t(WARPS) * SLOTS * kBlockBytes;
   static constexpr size_t cand_off = ring_off + ring_bytes;
@@ -59,10 +63,9 @@ struct PruneSmem {
   static constexpr size_t surv_off = (cand_off + cand_bytes + 15) / 16 * 16;
   static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
   static constexpr size_t cold_off = surv_off + surv_bytes;
-  static constexpr size_t cold_bytes = size_t(3) * QPB * 4;  // qq, dk, output row per query
-  static constexpr size_t wbox_off = cold_off + cold_bytes;  // per warp: min xyz, -, max xyz, - of its queries
-  static constexpr size_t total = wbox_off + size_t(WARPS) * 32;
-  static_assert(WARPS * SLOTS * 8 <= ring_off, "mbarriers overlap the ring");
+  static constexpr size_t cold_bytes = size_t(2) * QPB * 4;  // dk, output row per query
+  static constexpr size_t total = cold_off + cold_bytes;
+  static_assert(WARPS * SLOTS * 8 <= wbox_off && wbox_off + WARPS * 32 <= ring_off, "mbarriers / query boxes overlap the ring");
 };
 
 // Lower bound of the reference distance between ANY query in the box [qlo, qhi] and ANY point in
