@@ -39,7 +39,10 @@ namespace pops {
 
 namespace {
 
-constexpr int kBqHitCap = 128;       // hits a query holds between two cuts (>= K + 8)
+constexpr int kBqHitCap = 100;       // hits a query holds between two cuts (>= K + 8).  With 3 ring slots a CTA takes
+                                     // 23.2 KB (16-bit ids): 8 CTAs per SM inside the 196 KB carve-out (128 hits and 4
+                                     // slots: 31.2 KB, 7 CTAs, 228 KB carve-out = 28 KB of L1)
+constexpr int kBqRingSlots = 3;      // blocks resident per warp, kBqRingSlots - 1 in flight ahead of the scan
 constexpr int kBqCandCap = 24;       // candidate groups a query buffers between flushes
 constexpr int kBqThreadsP = 64;      // two independent warps per CTA
 
@@ -64,8 +67,8 @@ template <typename CID, typename IDX>
 struct BqSmem {
   static constexpr int WARPS = kBqThreadsP / 32;
   static constexpr size_t bars_off = 0;
-  static constexpr size_t ring_off = 256;
-  static constexpr size_t ring_bytes = size_t(WARPS) * kRingSlots * kBlockBytes;
+  static constexpr size_t ring_off = 128;
+  static constexpr size_t ring_bytes = size_t(WARPS) * kBqRingSlots * kBlockBytes;
   static constexpr size_t cand_off = ring_off + ring_bytes;
   static constexpr size_t cand_bytes = size_t(kBqCandCap) * kBqThreadsP * sizeof(CID);
   static constexpr size_t hits_off = (cand_off + cand_bytes + 15) / 16 * 16;
@@ -276,7 +279,7 @@ __device__ __noinline__ void bq_flush(const float* __restrict__ blocks_n, const 
 template <typename CID, typename IDX>
 __global__ void __launch_bounds__(kBqThreadsP, 8)
 bq_prune_kernel(const BqPruneParams prm) {
-  constexpr int S = kRingSlots, THREADS = kBqThreadsP;
+  constexpr int S = kBqRingSlots, THREADS = kBqThreadsP;
   using SM = BqSmem<CID, IDX>;
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr unsigned FULL = 0xffffffffu;
@@ -364,7 +367,7 @@ bq_prune_kernel(const BqPruneParams prm) {
     int slot_blk = 0;  // lane s: block in ring slot s
     int head = 0, tail = 0;
     auto issue = [&](int b) {
-      const int s = head & (S - 1);
+      const int s = head % S;
       __syncwarp();
       if (lane == 0) {
         fence_proxy_async();  // the slot's previous contents were read through the generic proxy
@@ -388,13 +391,13 @@ bq_prune_kernel(const BqPruneParams prm) {
     };
 
     for (;;) {
-      while (head - tail < kPrefetch) {
+      while (head - tail < S - 1) {
         const int b = pick();
         if (b < 0) break;
         issue(b);
       }
       if (tail == head) break;
-      const int s = tail & (S - 1);
+      const int s = tail % S;
       mbar_wait(&bars[s], (tail / S) & 1);
       // the warp-wide test used the box of ALL its queries: a run of kSubPoints points of the block is scanned
       // only if some query's own ball reaches the run's box (the boxes arrive with the block, knn_order.cuh)
