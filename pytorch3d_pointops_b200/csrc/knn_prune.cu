@@ -101,8 +101,13 @@ __device__ __noinline__ float2 prune_flush_one(const float* __restrict__ blocks_
   return make_float2(dkt, fresh ? 1.0f : 0.0f);
 }
 
+// CTAs per SM by variant (64-thread CTAs; sets the register cap): K = 1 and K = 4 fit 96 registers without
+// spilling (10 CTAs; K = 4: 246 -> 228 us on the T shape), K = 8 and K = 16 stay at 8 CTAs / 128 registers
+// (K = 8 at 9 CTAs / 112 registers: 331 vs 326 us; K = 16 spills below 128), K = 32 and the 4-query forms as before
+constexpr int prune_min_ctas(int Q, int KT) { return KT > 16 ? 4 : (Q >= 4 ? 6 : ((Q == 1 && KT <= 4) ? 10 : 8)); }
+
 template <int Q, int KT, int THREADS, typename CID>
-__global__ void __launch_bounds__(THREADS, (KT > 16 ? 4 : (Q >= 4 ? 6 : ((Q == 1 && KT == 1) ? 10 : 8))))
+__global__ void __launch_bounds__(THREADS, prune_min_ctas(Q, KT))
 knn_prune_kernel(const KnnPruneParams prm) {
   constexpr int QPB = Q * THREADS, S = prune_ring_slots(KT), PF = S - 1;  // ring slots, blocks in flight ahead of the scan
   // which runs of kSubPoints points of a fetched block are scanned: every query tests the runs' boxes
