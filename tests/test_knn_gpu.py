@@ -493,3 +493,31 @@ def test_cluster_prepass_every_slice_size(oracle, items):
         lib.pops_set_option(b"knn_cluster_items", 0)
         lib.pops_set_option(b"knn_order", -1)
         lib.pops_set_option(b"knn_fused_prepass", 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [1, 4, 8, 16, 32])
+def test_run_boxes_edge_lengths_and_clusters(oracle, K):
+    """Blocks whose 16-point runs are partly or wholly padding (lengths just around run and block boundaries),
+    points in tight far-apart clusters with exact duplicates (run boxes of zero extent, queries whose bound
+    reaches exactly one cluster), every K bucket of the pruned search: idx and dists equal the oracle's."""
+    _C, _, _ = _ops()
+    gen = torch.Generator().manual_seed(1000 + K)
+    lens = [64, 65, 79, 80, 81, 96, 111, 112, 113, 127, 128, 129, 191, 193, 1000, 1023, 1025, 2047]
+    N, P = len(lens), max(lens)
+    centres = torch.tensor([[0.0, 0.0, 0.0], [10.0, 0.0, 0.0], [0.0, -7.0, 3.0], [5.0, 5.0, 5.0]])
+    which = torch.randint(0, 4, (N, P), generator=gen)
+    p2 = centres[which] + 0.01 * torch.randn(N, P, 3, generator=gen)
+    p2[:, 1::7] = p2[:, 0::7][:, : p2[:, 1::7].shape[1]]  # exact duplicates
+    p1 = centres[torch.randint(0, 4, (N, 200), generator=gen)] + 0.5 * torch.randn(N, 200, 3, generator=gen)
+    l2 = torch.tensor(lens)
+    l1 = torch.randint(1, 201, (N,), generator=gen)
+    oi, od = oracle.knn_points_idx(p1, p2, l1, l2, 2, K)
+    gi, gd = _C.knn_points_idx(p1.to(DEV), p2.to(DEV), l1.to(DEV), l2.to(DEV), 2, K, -1)
+    assert torch.equal(gi.cpu(), oi)
+    assert torch.equal(gd.cpu(), od)
+    # self-search of the same clouds (queries ARE the points: zero distances, ties among the duplicates)
+    oi, od = oracle.knn_points_idx(p2, p2, l2, l2, 2, K)
+    gi, gd = _C.knn_points_idx(p2.to(DEV), p2.to(DEV), l2.to(DEV), l2.to(DEV), 2, K, -1)
+    assert torch.equal(gi.cpu(), oi)
+    assert torch.equal(gd.cpu(), od)
