@@ -107,7 +107,7 @@ __device__ __forceinline__ void exact4(float q0, float q1, float q2, float4 X, f
 // other way (|s + qq - d_ref| plus the roundings of forming the sum stay below E), each of
 // them has a reference distance d_ref <= fl(fl(U_s + qq) + E), which therefore bounds the K-th
 // distance (K <= KT) from above.  +inf when fewer than KT subsets hold a valid point (padding entries
-// carry w = +inf).  K = 1 takes the exact distances.  NS = 2 KT subsets of >= 4 points put the bound near the (1.1 KT)-th nearest seed
+// carry w = +inf).  K = 1 takes the exact distances of its best group.  NS = 2 KT subsets of >= 4 points put the bound near the (1.1 KT)-th nearest seed
 // point.  Not inlined: runs once per query.
 template <int KT, int SLOTF4 = kBlockF4>
 __device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float a0, float a1, float a2, float qq,
@@ -119,25 +119,44 @@ __device__ __noinline__ float seed_bound(const float4* ring4, int nseed, float a
   float mins[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) mins[i] = INF;
+  const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2);
   if (KT == 1) {
-    // K = 1: the exact distance instead (no E floor under the bound: a self-search starts at U = 0, and a
-    // chamfer pair of near-identical clouds at its true, tiny nearest distance)
-    float m = INF;
+    // K = 1: the group of four seed points that holds the smallest expanded-form value, then the EXACT
+    // distances of that one group: the distance of a real point bounds the nearest distance without an E
+    // floor under it (a self-search starts at U = 0, a chamfer pair of near-identical clouds at its true, tiny
+    // nearest distance), for 16 instead of 45 instructions per seed group (the all-exact seed was 27 % of the
+    // K = 1 search's instructions on the chamfer shape)
+    float best = INF;
+    int bg = 0;
     for (int s = 0; s < nseed; ++s) {
       const float4* tp = ring4 + s * SLOTF4;
 #pragma unroll 4
       for (int g = 0; g < kBlockGroups; ++g) {
-        const float4 W = tp[3 * kBlockGroups + g];
-        float d4[4];
-        exact4(-0.5f * a0, -0.5f * a1, -0.5f * a2, tp[g], tp[kBlockGroups + g], tp[2 * kBlockGroups + g], d4);
-        const float w4[4] = {W.x, W.y, W.z, W.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) m = fminf(m, (w4[i] == INF) ? INF : d4[i]);
+        const float4 X = tp[g], Y = tp[kBlockGroups + g], Z = tp[2 * kBlockGroups + g], W = tp[3 * kBlockGroups + g];
+        float2 s01 = make_float2(W.x, W.y), s23 = make_float2(W.z, W.w);
+        s01 = __ffma2_rn(A0, make_float2(X.x, X.y), s01);
+        s23 = __ffma2_rn(A0, make_float2(X.z, X.w), s23);
+        s01 = __ffma2_rn(A1, make_float2(Y.x, Y.y), s01);
+        s23 = __ffma2_rn(A1, make_float2(Y.z, Y.w), s23);
+        s01 = __ffma2_rn(A2, make_float2(Z.x, Z.y), s01);
+        s23 = __ffma2_rn(A2, make_float2(Z.z, Z.w), s23);
+        const float m = fminf(fminf(s01.x, s01.y), fminf(s23.x, s23.y));
+        const bool better = m < best;
+        best = better ? m : best;
+        bg = better ? s * SLOTF4 + g : bg;
       }
     }
+    if (!(best < INF)) return INF;  // no valid seed point
+    const float4* tg = ring4 + bg;
+    const float4 W = tg[3 * kBlockGroups];
+    float d4[4];
+    exact4(-0.5f * a0, -0.5f * a1, -0.5f * a2, tg[0], tg[kBlockGroups], tg[2 * kBlockGroups], d4);
+    const float w4[4] = {W.x, W.y, W.z, W.w};
+    float m = INF;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m = fminf(m, (w4[i] == INF) ? INF : d4[i]);
     return m;
   }
-  const float2 A0 = make_float2(a0, a0), A1 = make_float2(a1, a1), A2 = make_float2(a2, a2);
   for (int s = 0; s < nseed; ++s) {
     const float4* tp = ring4 + s * SLOTF4;  // SLOTF4: float4 between consecutive ring slots
 #pragma unroll 1
