@@ -54,7 +54,8 @@ packed_to_padded_kernel(const float* __restrict__ packed, const int64_t* __restr
     //  a funnel select per chunk instead of four 4-byte loads were slower too, in both kernels: twice the L1
     //  bytes -- D = 3 24.6 -> 28.7 us here, 22.5 -> 41 us for padded_to_packed.  An unpredicated fast path for
     //  interior chunks -- one address, four 4-byte loads, one store -- changed nothing: the four L1 wavefronts
-    //  per 16 bytes are the limit, not the issue slots.)
+    //  per 16 bytes are the limit, not the issue slots.  One aligned 16-byte load per lane with the missing
+    //  floats taken from the next lane by shuffle was slower again: 34.8 us at D = 3, 141 us at D = 16.)
     for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nchunks;
          c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
       const int64_t f0 = 4 * c - a;
