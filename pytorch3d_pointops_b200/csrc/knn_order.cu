@@ -322,8 +322,9 @@ __global__ void morton_keys_kernel(const float* __restrict__ p1, const float* __
   }
 }
 
-// Sorted p2 in BLOCKS of kBoxPoints points: [n][block][row][kBoxPoints], rows x, y, z, w = |p|^2,
-// original index -- one contiguous 1280-byte piece per block, fetched by a single TMA bulk copy.
+// Sorted p2 in BLOCKS of kBoxPoints points (layout: knn_order.cuh): rows x, y, z, w = |p|^2, the boxes of the
+// block's runs (written by box_kernel), the row of original indices -- one contiguous 1408-byte piece per
+// block, of which a single TMA bulk copy fetches the 1152 bytes a scan reads.
 // Padding entries (beyond lengths2, and the tail of the last block): x = y = z = 0, w = +inf,
 // index kNoPoint.
 __global__ void gather_p2_kernel(const float* __restrict__ p2, const int64_t* __restrict__ len2, int P2,

@@ -5,8 +5,8 @@
 // work: a (query, point) pair is evaluated only if the point's block can still hold a neighbour.
 //
 //   pre-pass (knn_order.cu)   both clouds sorted along a Hilbert curve; p2 cut into blocks of 64
-//                             points (1280 contiguous bytes: rows x, y, z, w=|p|^2, original index)
-//                             with one bounding box each.
+//                             points (1408 contiguous bytes: rows x, y, z, w=|p|^2, the boxes of the
+//                             block's four 16-point runs, the original indices) with one bounding box each.
 //   this kernel               one WARP = Q*32 consecutive sorted queries, fully independent of the
 //                             other warps of its CTA (no __syncthreads after start-up).
 //     walk    blocks are visited outward from the warp's own position in the sorted p2.  Lane j of
