@@ -150,13 +150,21 @@ __device__ __forceinline__ float knn_merge_global(const uint64_t* S, int ns, int
 #pragma unroll
     for (int s2 = 0; s2 < kSurvCap; ++s2) Sr[s2] = (s2 < ns) ? S[s2 * SSTRIDE] : kEmptyKey;
     sort16(Sr);
-    // K smallest of (Lr U Sr): C[i] = min(Lr[i], Sr[KR-1-i]) is bitonic, then merge
+    if (KR <= 8 && __all_sync(0xffffffffu, fresh || ns == 0)) {
+      // every list that receives survivors is still empty (a warp's first flush): the sorted survivors ARE the
+      // list, no merge network.  (K <= 8 only: 326 -> 320 us on the T shape at K = 8; for K = 16 / 32 the second
+      // code path costs more than the skipped network saves, 576 -> 600 us.)
 #pragma unroll
-    for (int i = 0; i < KR; ++i) {
-      const int si = KR - 1 - i;
-      if (si < kSurvCap) Lr[i] = (Sr[si] < Lr[i]) ? Sr[si] : Lr[i];
+      for (int i = 0; i < KR; ++i) Lr[i] = (Sr[i] < Lr[i]) ? Sr[i] : Lr[i];  // keeps the (+inf, none) filler where Sr is empty
+    } else {
+      // K smallest of (Lr U Sr): C[i] = min(Lr[i], Sr[KR-1-i]) is bitonic, then merge
+#pragma unroll
+      for (int i = 0; i < KR; ++i) {
+        const int si = KR - 1 - i;
+        if (si < kSurvCap) Lr[i] = (Sr[si] < Lr[i]) ? Sr[si] : Lr[i];
+      }
+      bitonic_merge<KR>(Lr);
     }
-    bitonic_merge<KR>(Lr);
   }
   if (mine) {
     if (KR >= 4 && (K & 3) == 0) {
