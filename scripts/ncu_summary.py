@@ -27,6 +27,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "sm__icc_request_hit_rate.pct",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
 ]
 
