@@ -313,7 +313,7 @@ knn_prune_kernel(const KnnPruneParams prm) {
   };
 
   // ---- flush glue ------------------------------------------------------------------------------------
-  const int bufcap = prm.bufcap > 0 ? min(prm.bufcap, prune_buf_cap(KT)) : prune_buf_cap(KT);
+  const int bufcap = prm.bufcap > 0 ? min(prm.bufcap, prune_buf_cap(KT, Q)) : prune_buf_cap(KT, Q);
   const uint32_t cw_limit = cand_base + static_cast<uint32_t>(bufcap - kChunk) * CBYTES;
   // only_full: drain just the query slots in which some lane's buffer is nearly full
   auto flush_all = [&](bool only_full) {

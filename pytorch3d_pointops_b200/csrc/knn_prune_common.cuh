@@ -39,7 +39,11 @@ constexpr int prune_ring_slots(int KT) { return KT <= 16 ? 3 : 4; }
 // carve-out, L1 dropped from 60 to 28 KB and the kernel lost 9 % (the flush's re-reads and the list rows live
 // in L1).  Inside the 164 KB carve-out K = 16 measured 576 us with 32 entries (8 CTAs per SM), 563 us with 52
 // (7 CTAs: 22 400 bytes each) and 573 us with 84 (6 CTAs): it takes 52.  An earlier FIRST flush only loses.
-constexpr int prune_buf_cap(int KT) { return KT > 16 ? 40 : (KT == 1 ? 12 : (KT == 16 ? 52 : 24)); }
+// (Q = queries per thread: the sizes above are for the forms that run by default, Q = 1 for K <= 16 and Q = 2 for
+//  K = 32; the other forms keep round 1's 24 / 40 entries)
+constexpr int prune_buf_cap(int KT, int Q) {
+  return KT > 16 ? (Q == 2 ? 48 : 40) : (KT == 1 ? 12 : (KT == 16 && Q == 1 ? 52 : 24));
+}
 constexpr int kBlockF4 = kScanFloats / 4;         // float4 per ring slot: the part of a block a scan reads
 constexpr int kBlockGroups = kBoxPoints / kGroup;  // 16 groups of 4 points
 constexpr uint32_t kBlockBytes = kScanFloats * 4;  // bytes of one TMA bulk copy (rows x, y, z, w + run boxes)
@@ -60,7 +64,7 @@ struct PruneSmem {
   static constexpr int SLOTS = prune_ring_slots(KT);
   static constexpr size_t ring_bytes = size_t(WARPS) * SLOTS * kBlockBytes;
   static constexpr size_t cand_off = ring_off + ring_bytes;
-  static constexpr size_t cand_bytes = size_t(prune_buf_cap(KT)) * QPB * sizeof(CID);  // global group ids
+  static constexpr size_t cand_bytes = size_t(prune_buf_cap(KT, Q)) * QPB * sizeof(CID);  // global group ids
   static constexpr size_t surv_off = (cand_off + cand_bytes + 15) / 16 * 16;
   static constexpr size_t surv_bytes = size_t(kSurvCap) * THREADS * 8;
   static constexpr size_t cold_off = surv_off + surv_bytes;
