@@ -37,8 +37,9 @@ constexpr int prune_ring_slots(int KT) { return KT <= 16 ? 3 : 4; }
 // Larger buffers mean fewer flush rounds (K = 16: 24 -> 28 -> 32 entries: 614 -> 593 -> ... us), as long as the CTA
 // stays inside its shared-memory carve-out: 48 entries (3 KB more) pushed 8 CTAs from the 196 KB into the 228 KB
 // carve-out, L1 dropped from 60 to 28 KB and the kernel lost 9 % (the flush's re-reads and the list rows live
-// in L1).  Inside the 164 KB carve-out K = 16 measured 576 us with 32 entries (8 CTAs per SM), 563 us with 52
-// (7 CTAs: 22 400 bytes each) and 573 us with 84 (6 CTAs): it takes 52.  An earlier FIRST flush only loses.
+// in L1).  K = 16 measured 576 us with 32 entries (19.8 KB per CTA, 8 CTAs in the 164 KB carve-out, L1 = 92 KB),
+// 560 us with 52 or 64 (22.4 / 23.9 KB, 8 CTAs in the 196 KB carve-out, L1 = 60 KB: ncu reports 8 resident
+// CTAs) and 573 us with 84 (228 KB carve-out again): it takes 52.  An earlier FIRST flush only loses.
 // (Q = queries per thread: the sizes above are for the forms that run by default, Q = 1 for K <= 16 and Q = 2 for
 //  K = 32; the other forms keep round 1's 24 / 40 entries)
 constexpr int prune_buf_cap(int KT, int Q) {
@@ -57,7 +58,7 @@ struct PruneSmem {
   static constexpr int WARPS = THREADS / 32;
   static constexpr int QPB = Q * THREADS;
   // Every byte counts: 8 CTAs x (total + 1 KB reserved) must stay within the 164 KB shared-memory carve-out
-  // (knn_prune_common.cuh: prune_ring_slots) -- or 7 CTAs, which K = 16 chooses for a larger candidate buffer.
+  // (knn_prune_common.cuh: prune_ring_slots), or at least within the 196 KB one (K = 16 with its 52-entry buffer).
   static constexpr size_t bars_off = 0;      // WARPS x SLOTS mbarriers (<= 64 bytes)
   static constexpr size_t wbox_off = 64;     // per warp: min xyz, -, max xyz, - of its queries (WARPS x 32 bytes)
   static constexpr size_t ring_off = 128;
