@@ -1,6 +1,9 @@
 """One-off stress run: random shapes, lengths, K and geometries through knn_points_idx (D = 3, L2: the pruned
 search, both pre-pass forms), the two-sided pair search and ball_query, each compared bit for bit with the
-CPU oracle.  Test infrastructure (imports oracle/); not part of the product."""
+CPU oracle.  Test infrastructure like the rest of tests/ (imports oracle/); run by hand on a GPU box:
+
+    python tests/stress_parity.py [seed] [cases]
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
